@@ -1,0 +1,154 @@
+/*
+ * l32_ffn.h -- C ABI of the B200-native (sm_100a) Add-RMSNorm + SwiGLU feed-forward hot path.
+ *
+ * This is the drop-in boundary for the LLaMA-3.2 text-decoder block's hot path of
+ * emmanuelalo52/LLaMA-3.2-Multimodal.  Every entry point cites the reference interface it replaces
+ * (paths relative to the reference repository root).  The Python extension modules `rmsnorm` and
+ * `swiglu_fused` (same names as the reference's setup.py:11-41 targets) bind these symbols; see
+ * INTEGRATION.md for the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless stated otherwise; tensors are row-major and contiguous
+ *     along the last dimension.  `dtype` is L32_DTYPE_BF16 or L32_DTYPE_FP16 (storage type of every
+ *     activation / weight / gradient); all arithmetic accumulates in fp32.
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued asynchronously, nothing
+ *     synchronises, nothing allocates (CUDA-graph capturable).  Scratch memory is caller-provided.
+ *   - Return value: 0 on success, negative L32_ERR_* for argument errors, positive = cudaError_t.
+ *   - Inputs are borrowed; outputs are written in place into caller-owned buffers.
+ *   - Weight layout is the Python/HF one: w_gate, w_up are [inter, hidden]; w_down is [hidden, inter]
+ *     (reference Tools/swiglu/FusedSwiglu.py:63-64, Model/model.py:214).
+ */
+#ifndef L32_FFN_H_
+#define L32_FFN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define L32_API __attribute__((visibility("default")))
+#else
+#define L32_API
+#endif
+
+#define L32_DTYPE_BF16 0
+#define L32_DTYPE_FP16 1
+
+#define L32_OK 0
+#define L32_ERR_BAD_DTYPE (-1)
+#define L32_ERR_BAD_SHAPE (-2)
+#define L32_ERR_BAD_ALIGN (-3)
+#define L32_ERR_NULL (-4)
+#define L32_ERR_DRIVER (-5)
+#define L32_ERR_WORKSPACE (-6)
+
+/* ABI version of this header (bumped on any signature change). */
+L32_API int l32_abi_version(void);
+/* Human-readable text for a return code of this library (static storage). */
+L32_API const char* l32_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused residual Add-RMSNorm forward.
+ *   h = x + residual (fp32, residual may be NULL);  y = h * rsqrt(mean(h^2) + eps) * weight
+ * Replaces: rmsnorm_forward, Tools/rmsnorm/rmsnorm.cu:7-32 (kernel Tools/rmsnorm/rmsnorm.cuh:13-108),
+ *           i.e. python `rmsnorm.forward(input, weight, residual, eps) -> [output, rms]`;
+ *           module-level spec LLAMARMSNorm.forward, Model/model.py:164-171.
+ *   x, residual, y, h_out : [rows, hidden]      weight : [hidden]      rms : [rows] fp32
+ *   h_out   : optional; receives h rounded to `dtype` (saved for backward).  May alias `residual`
+ *             (that reproduces the reference kernel's in-place `residual := x + residual`).
+ *   rms     : optional; receives sqrt(mean(h^2) + eps)  (the reference returns rms, not rstd).
+ */
+L32_API int l32_add_rmsnorm_forward(const void* x, const void* residual, const void* weight, void* y, void* h_out,
+                            float* rms, int64_t rows, int hidden, float eps, int dtype, void* stream);
+
+/* RMSNorm backward.
+ *   dx = rstd * (dy*w - xhat * mean(dy*w*xhat)),  xhat = h * rstd,  rstd = 1 / rms
+ *   dweight[c] = sum_rows dy * xhat            (fp32 accumulation, deterministic two-stage reduction)
+ * Replaces: rmsnorm_backward, Tools/rmsnorm/rmsnorm.cu:35-61 (kernel rmsnorm.cuh:110-154),
+ *           python `rmsnorm.backward(grad_out, input, weight, rms) -> [d_input, d_weight]`, with
+ *           `h` = the NORMALISED INPUT x + residual (the reference wrapper wrongly passes pre-add x,
+ *           Model/model.py:144).  d_residual == dx.
+ *   workspace : l32_rmsnorm_backward_workspace_bytes(rows, hidden) bytes, 16-byte aligned.
+ *   dweight   : optional [hidden] in `dtype`.
+ */
+L32_API size_t l32_rmsnorm_backward_workspace_bytes(int64_t rows, int hidden);
+L32_API int l32_rmsnorm_backward(const void* dy, const void* h, const void* weight, const float* rms, void* dx,
+                         void* dweight, void* workspace, size_t workspace_bytes, int64_t rows, int hidden,
+                         int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SwiGLU forward: act = silu(x w_gate^T + b_gate) * (x w_up^T + b_up)
+ * Replaces: swiglu_forward_cuda, Tools/swiglu/swiglu.cu:277-316 (python `swiglu_fused.forward`,
+ *           Tools/swiglu/swiglu_binding.cpp:7-12); math spec = the PyTorch path
+ *           Tools/swiglu/FusedSwiglu.py:18-20.
+ *   x : [tokens, hidden]   w_gate, w_up : [inter, hidden]   b_gate, b_up : optional [inter]
+ *   act : [tokens, inter]  gate_cache, up_cache : optional [tokens, inter] (both or neither; the
+ *   pre-activation gate / up projections, needed by l32_swiglu_backward).
+ * One tcgen05 kernel: the gate/up accumulators live in TMEM and SiLU*mul is applied in the epilogue,
+ * so gate and up never touch HBM unless the caches are requested.  tokens <= 128 takes the
+ * weight-streaming small-M kernel (caches not available there -> falls through to the tiled kernel).
+ */
+L32_API int l32_swiglu_forward(const void* x, const void* w_gate, const void* w_up, const void* b_gate,
+                       const void* b_up, void* act, void* gate_cache, void* up_cache, int64_t tokens,
+                       int hidden, int inter, int dtype, void* stream);
+
+/* SwiGLU backward (SiLU and SiLU' recomputed in registers from the gate cache).
+ * Replaces: swiglu_backward_cuda, declared Tools/swiglu/swiglu.cuh:18-25 and bound at
+ *           swiglu_binding.cpp:15-21 but never defined in the reference (kernel sketch swiglu.cu:179-223).
+ *   d_act : [tokens, inter]  ->  dx : [tokens, hidden] (optional), dw_gate, dw_up : [inter, hidden]
+ *   (optional, both or neither).
+ *   workspace : l32_swiglu_backward_workspace_bytes(tokens, inter) bytes (holds d_gate, d_up).
+ */
+L32_API size_t l32_swiglu_backward_workspace_bytes(int64_t tokens, int inter);
+L32_API int l32_swiglu_backward(const void* d_act, const void* x, const void* w_gate, const void* w_up,
+                        const void* gate_cache, const void* up_cache, void* dx, void* dw_gate, void* dw_up,
+                        void* workspace, size_t workspace_bytes, int64_t tokens, int hidden, int inter,
+                        int dtype, void* stream);
+
+/* Linear forward y = a w^T + bias, w : [out_features, in_features] (nn.Linear layout).
+ * Replaces: the w_down nn.Linear call of FusedFeedforward.forward, Model/model.py:214-217. */
+L32_API int l32_linear_forward(const void* a, const void* w, const void* bias, void* y, int64_t tokens, int in_features,
+                       int out_features, int dtype, void* stream);
+
+/* Whole feed-forward forward: y = (silu(x w_gate^T) * (x w_up^T)) w_down^T.
+ * Replaces: swiglu_down_forward_cuda, Tools/swiglu/swiglu.cu:319-364 (python `swiglu_fused.forward_down`,
+ *           swiglu_binding.cpp:24-31); module-level spec FusedFeedforward.forward, Model/model.py:216-217.
+ *   act_ws : [tokens, inter] scratch in `dtype` (the intermediate; L2/HBM resident between the two GEMMs).
+ *   gate_cache / up_cache : optional, as in l32_swiglu_forward.
+ */
+L32_API int l32_ffn_forward(const void* x, const void* w_gate, const void* w_up, const void* w_down, const void* b_gate,
+                    const void* b_up, const void* b_down, void* y, void* act_ws, void* gate_cache, void* up_cache,
+                    int64_t tokens, int hidden, int inter, int dtype, void* stream);
+
+/* Whole feed-forward backward (down projection included).
+ *   dy : [tokens, hidden].  Outputs (each optional): dx [tokens, hidden], dw_gate / dw_up [inter, hidden]
+ *   (both or neither), dw_down [hidden, inter].
+ *   workspace : l32_ffn_backward_workspace_bytes(tokens, inter) bytes (d_gate, d_up, recomputed act).
+ * No reference counterpart exists (the reference's backward never ran); the
+ * gradient oracle is autograd over Tools/swiglu/FusedSwiglu.py:18-20 + Model/model.py:217.
+ */
+L32_API size_t l32_ffn_backward_workspace_bytes(int64_t tokens, int inter);
+L32_API int l32_ffn_backward(const void* dy, const void* x, const void* w_gate, const void* w_up, const void* w_down,
+                     const void* gate_cache, const void* up_cache, void* dx, void* dw_gate, void* dw_up,
+                     void* dw_down, void* workspace, size_t workspace_bytes, int64_t tokens, int hidden, int inter,
+                     int dtype, void* stream);
+
+/* General tiled GEMM used by the entry points above (exposed for tests, tuning and the tensor-parallel
+ * host code):  D[m,n] = A[m,k] B[n,k]^T  (+ A1 B1^T when a1 != NULL).
+ *   *_mn_major = 0: operand stored [rows][k];  1: stored [k][rows] (i.e. the transpose is consumed in place).
+ *   cta_group: 0 auto, 1, or 2 (CTA pair, UMMA M = 256).  max_ctas: 0 = all SMs.
+ */
+L32_API int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t ldb, int b_mn_major, const void* a1,
+             int64_t lda1, const void* b1, int64_t ldb1, void* d, int64_t ldd, int m, int n, int k, int k1, int dtype,
+             int cta_group, int max_ctas, void* stream);
+
+/* Elementwise helpers (unfused reference points for tests / benchmarks of the fusion saving). */
+L32_API int l32_swiglu_act(const void* gate, const void* up, void* act, int64_t n, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L32_FFN_H_ */

@@ -1,0 +1,24 @@
+"""B200-native (sm_100a) Add-RMSNorm + SwiGLU feed-forward hot path of LLaMA-3.2-Multimodal.
+
+The directory name is not a Python identifier; import it as `llama32_b200` (alias package at the repo root).
+"""
+from .modules import (  # noqa: F401
+    FFNFunction,
+    FusedFeedForward,
+    FusedFeedforward,
+    FusedSwiGLU,
+    LLAMARMSNorm,
+    Linear_LORA,
+    LinearFunction,
+    RMSNormFunction,
+    SwiGLUFunction,
+    convert_feedforward_to_fused,
+    convert_instances,
+    patch_reference,
+)
+
+__all__ = [
+    "FFNFunction", "FusedFeedForward", "FusedFeedforward", "FusedSwiGLU", "LLAMARMSNorm", "Linear_LORA",
+    "LinearFunction", "RMSNormFunction", "SwiGLUFunction", "convert_feedforward_to_fused", "convert_instances",
+    "patch_reference",
+]

@@ -1,0 +1,303 @@
+// C-ABI layer (include/l32_ffn.h): argument validation and composition of the kernels.  No torch types, no
+// allocation, no synchronisation: everything is enqueued on the caller's stream and scratch is caller-provided.
+#include "../../include/l32_ffn.h"
+#include "l32_internal.cuh"
+
+using namespace l32;
+
+namespace {
+
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+inline bool dtype_ok(int dtype) { return dtype == L32_BF16 || dtype == L32_FP16; }
+inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+GemmOperand op(const void* p, int64_t ld, int mn_major) {
+    GemmOperand o;
+    o.ptr = p;
+    o.ld = ld;
+    o.mn_major = mn_major;
+    return o;
+}
+
+GemmProblem blank(int m, int n, int dtype) {
+    GemmProblem g;
+    memset(&g, 0, sizeof(g));
+    g.m = m;
+    g.n = n;
+    g.num_phases = 1;
+    g.dtype = dtype;
+    return g;
+}
+
+// dx[T,H] = d_gate[T,I] * w_gate[I,H] + d_up[T,I] * w_up[I,H]   (weights consumed as MN-major B operands)
+int dgrad_x(const void* d_gate, const void* d_up, const void* w_gate, const void* w_up, void* dx, int tokens, int hidden,
+            int inter, int dtype, cudaStream_t s) {
+    GemmProblem g = blank(tokens, hidden, dtype);
+    g.num_phases = 2;
+    g.k[0] = g.k[1] = inter;
+    g.a[0] = op(d_gate, inter, 0);
+    g.a[1] = op(d_up, inter, 0);
+    g.b[0] = op(w_gate, hidden, 1);
+    g.b[1] = op(w_up, hidden, 1);
+    g.epilogue = EPI_STORE;
+    g.d[0] = dx;
+    g.ldd = hidden;
+    return gemm_sm100(g, s);
+}
+
+// dw[R,C] = lhs[T,R]^T * rhs[T,C]   (both operands consumed as MN-major, reduction over tokens)
+int wgrad(const void* lhs, int r, const void* rhs, int c, void* dw, int tokens, int dtype, cudaStream_t s) {
+    GemmProblem g = blank(r, c, dtype);
+    g.k[0] = tokens;
+    g.a[0] = op(lhs, r, 1);
+    g.b[0] = op(rhs, c, 1);
+    g.epilogue = EPI_STORE;
+    g.d[0] = dw;
+    g.ldd = c;
+    return gemm_sm100(g, s);
+}
+
+bool shapes_ok(int64_t tokens, int hidden, int inter) {
+    return tokens >= 0 && tokens <= 0x7fffffff && hidden > 0 && inter > 0 && (hidden % 8) == 0 && (inter % 8) == 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int l32_abi_version(void) { return 1; }
+
+const char* l32_error_string(int code) {
+    switch (code) {
+        case L32_OK: return "success";
+        case L32_ERR_BAD_DTYPE: return "unsupported dtype (expected L32_DTYPE_BF16 or L32_DTYPE_FP16)";
+        case L32_ERR_BAD_SHAPE: return "unsupported shape (sizes must be positive; hidden/inter multiples of 8)";
+        case L32_ERR_BAD_ALIGN: return "pointer not 16-byte aligned or row pitch not a multiple of 8 elements";
+        case L32_ERR_NULL: return "required pointer is null";
+        case L32_ERR_DRIVER: return "CUDA driver entry point unavailable (cuTensorMapEncodeTiled)";
+        case L32_ERR_WORKSPACE: return "workspace too small or misaligned";
+        default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown error";
+    }
+}
+
+int l32_add_rmsnorm_forward(const void* x, const void* residual, const void* weight, void* y, void* h_out, float* rms,
+                            int64_t rows, int hidden, float eps, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (rows < 0 || hidden <= 0) return L32_ERR_BAD_SHAPE;
+    if (rows == 0) return L32_OK;
+    if (x == nullptr || weight == nullptr || y == nullptr) return L32_ERR_NULL;
+    return static_cast<int>(add_rmsnorm_fwd(x, residual, weight, y, h_out, rms, rows, hidden, eps, dtype, as_stream(stream)));
+}
+
+size_t l32_rmsnorm_backward_workspace_bytes(int64_t rows, int hidden) {
+    if (rows < 0 || hidden <= 0) return 0;
+    return rmsnorm_bwd_workspace_bytes(rows, hidden);
+}
+
+int l32_rmsnorm_backward(const void* dy, const void* h, const void* weight, const float* rms, void* dx, void* dweight,
+                         void* workspace, size_t workspace_bytes, int64_t rows, int hidden, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (rows < 0 || hidden <= 0) return L32_ERR_BAD_SHAPE;
+    if (dy == nullptr || h == nullptr || weight == nullptr || rms == nullptr || dx == nullptr) {
+        if (rows != 0) return L32_ERR_NULL;
+    }
+    if (rows > 0 && (workspace == nullptr || workspace_bytes < rmsnorm_bwd_workspace_bytes(rows, hidden) ||
+                     !is_aligned16(workspace)))
+        return L32_ERR_WORKSPACE;
+    return static_cast<int>(rmsnorm_bwd(dy, h, weight, rms, dx, dweight, static_cast<float*>(workspace), rows, hidden,
+                                        dtype, as_stream(stream)));
+}
+
+int l32_swiglu_forward(const void* x, const void* w_gate, const void* w_up, const void* b_gate, const void* b_up,
+                       void* act, void* gate_cache, void* up_cache, int64_t tokens, int hidden, int inter, int dtype,
+                       void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, inter)) return L32_ERR_BAD_SHAPE;
+    if (tokens == 0) return L32_OK;
+    if (x == nullptr || w_gate == nullptr || w_up == nullptr || act == nullptr) return L32_ERR_NULL;
+    if ((gate_cache == nullptr) != (up_cache == nullptr)) return L32_ERR_NULL;
+    if (tokens <= 128 && gate_cache == nullptr && b_gate == nullptr && b_up == nullptr) {
+        const int rc = ffn_decode_swiglu(x, w_gate, w_up, act, static_cast<int>(tokens), hidden, inter, dtype, as_stream(stream));
+        if (rc != L32_ERR_BAD_SHAPE) return rc;   // shape outside the small-M kernel's envelope: use the tiled kernel
+    }
+    GemmProblem g = blank(static_cast<int>(tokens), inter, dtype);
+    g.k[0] = hidden;
+    g.a[0] = op(x, hidden, 0);
+    g.b[0] = op(w_gate, hidden, 0);
+    g.b[1] = op(w_up, hidden, 0);
+    g.epilogue = EPI_SWIGLU;
+    g.d[0] = act;
+    g.d[1] = gate_cache;
+    g.d[2] = up_cache;
+    g.bias[0] = b_gate;
+    g.bias[1] = b_up;
+    g.ldd = inter;
+    return gemm_sm100(g, as_stream(stream));
+}
+
+int l32_linear_forward(const void* a, const void* w, const void* bias, void* y, int64_t tokens, int in_features,
+                       int out_features, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, in_features, out_features)) return L32_ERR_BAD_SHAPE;
+    if (tokens == 0) return L32_OK;
+    if (a == nullptr || w == nullptr || y == nullptr) return L32_ERR_NULL;
+    if (tokens <= 128 && bias == nullptr) {
+        const int rc = ffn_decode_linear(a, w, y, static_cast<int>(tokens), in_features, out_features, dtype, as_stream(stream));
+        if (rc != L32_ERR_BAD_SHAPE) return rc;
+    }
+    GemmProblem g = blank(static_cast<int>(tokens), out_features, dtype);
+    g.k[0] = in_features;
+    g.a[0] = op(a, in_features, 0);
+    g.b[0] = op(w, in_features, 0);
+    g.epilogue = EPI_STORE;
+    g.d[0] = y;
+    g.bias[0] = bias;
+    g.ldd = out_features;
+    return gemm_sm100(g, as_stream(stream));
+}
+
+int l32_ffn_forward(const void* x, const void* w_gate, const void* w_up, const void* w_down, const void* b_gate,
+                    const void* b_up, const void* b_down, void* y, void* act_ws, void* gate_cache, void* up_cache,
+                    int64_t tokens, int hidden, int inter, int dtype, void* stream) {
+    if (act_ws == nullptr && tokens > 0) return L32_ERR_WORKSPACE;
+    int rc = l32_swiglu_forward(x, w_gate, w_up, b_gate, b_up, act_ws, gate_cache, up_cache, tokens, hidden, inter, dtype, stream);
+    if (rc != L32_OK) return rc;
+    return l32_linear_forward(act_ws, w_down, b_down, y, tokens, inter, hidden, dtype, stream);
+}
+
+size_t l32_swiglu_backward_workspace_bytes(int64_t tokens, int inter) {
+    if (tokens < 0 || inter <= 0) return 0;
+    return 2 * align256(static_cast<size_t>(tokens) * inter * 2);
+}
+
+int l32_swiglu_backward(const void* d_act, const void* x, const void* w_gate, const void* w_up, const void* gate_cache,
+                        const void* up_cache, void* dx, void* dw_gate, void* dw_up, void* workspace,
+                        size_t workspace_bytes, int64_t tokens, int hidden, int inter, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, inter)) return L32_ERR_BAD_SHAPE;
+    if ((dw_gate == nullptr) != (dw_up == nullptr)) return L32_ERR_NULL;
+    cudaStream_t s = as_stream(stream);
+    if (tokens == 0) {
+        if (dw_gate != nullptr) {
+            cudaError_t e = cudaMemsetAsync(dw_gate, 0, static_cast<size_t>(inter) * hidden * 2, s);
+            if (e == cudaSuccess) e = cudaMemsetAsync(dw_up, 0, static_cast<size_t>(inter) * hidden * 2, s);
+            return static_cast<int>(e);
+        }
+        return L32_OK;
+    }
+    if (d_act == nullptr || x == nullptr || w_gate == nullptr || w_up == nullptr || gate_cache == nullptr || up_cache == nullptr)
+        return L32_ERR_NULL;
+    if (workspace == nullptr || workspace_bytes < l32_swiglu_backward_workspace_bytes(tokens, inter) || !is_aligned16(workspace))
+        return L32_ERR_WORKSPACE;
+    const size_t part = align256(static_cast<size_t>(tokens) * inter * 2);
+    void* d_gate = workspace;
+    void* d_up = static_cast<uint8_t*>(workspace) + part;
+    const int t = static_cast<int>(tokens);
+    cudaError_t e = swiglu_bwd_elementwise(d_act, gate_cache, up_cache, d_gate, d_up, tokens * inter, dtype, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    int rc = L32_OK;
+    if (dx != nullptr) rc = dgrad_x(d_gate, d_up, w_gate, w_up, dx, t, hidden, inter, dtype, s);
+    if (rc != L32_OK) return rc;
+    if (dw_gate != nullptr) {
+        rc = wgrad(d_gate, inter, x, hidden, dw_gate, t, dtype, s);
+        if (rc != L32_OK) return rc;
+        rc = wgrad(d_up, inter, x, hidden, dw_up, t, dtype, s);
+    }
+    return rc;
+}
+
+size_t l32_ffn_backward_workspace_bytes(int64_t tokens, int inter) {
+    if (tokens < 0 || inter <= 0) return 0;
+    return 3 * align256(static_cast<size_t>(tokens) * inter * 2);
+}
+
+int l32_ffn_backward(const void* dy, const void* x, const void* w_gate, const void* w_up, const void* w_down,
+                     const void* gate_cache, const void* up_cache, void* dx, void* dw_gate, void* dw_up, void* dw_down,
+                     void* workspace, size_t workspace_bytes, int64_t tokens, int hidden, int inter, int dtype,
+                     void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, inter)) return L32_ERR_BAD_SHAPE;
+    if ((dw_gate == nullptr) != (dw_up == nullptr)) return L32_ERR_NULL;
+    cudaStream_t s = as_stream(stream);
+    const size_t wbytes = static_cast<size_t>(inter) * hidden * 2;
+    if (tokens == 0) {
+        cudaError_t e = cudaSuccess;
+        if (dw_gate != nullptr) {
+            e = cudaMemsetAsync(dw_gate, 0, wbytes, s);
+            if (e == cudaSuccess) e = cudaMemsetAsync(dw_up, 0, wbytes, s);
+        }
+        if (e == cudaSuccess && dw_down != nullptr) e = cudaMemsetAsync(dw_down, 0, wbytes, s);
+        return static_cast<int>(e);
+    }
+    if (dy == nullptr || x == nullptr || w_gate == nullptr || w_up == nullptr || w_down == nullptr || gate_cache == nullptr ||
+        up_cache == nullptr)
+        return L32_ERR_NULL;
+    if (workspace == nullptr || workspace_bytes < l32_ffn_backward_workspace_bytes(tokens, inter) || !is_aligned16(workspace))
+        return L32_ERR_WORKSPACE;
+    const size_t part = align256(static_cast<size_t>(tokens) * inter * 2);
+    void* d_gate = workspace;
+    void* d_up = static_cast<uint8_t*>(workspace) + part;
+    void* act = static_cast<uint8_t*>(workspace) + 2 * part;
+    const int t = static_cast<int>(tokens);
+
+    // d_act = dy * w_down (w_down[H,I] consumed as an MN-major B operand); the epilogue turns it into
+    // d_gate / d_up (SiLU' recomputed in registers) and re-materialises act for the w_down gradient.
+    GemmProblem g = blank(t, inter, dtype);
+    g.k[0] = hidden;
+    g.a[0] = op(dy, hidden, 0);
+    g.b[0] = op(w_down, inter, 1);
+    g.epilogue = EPI_SWIGLU_BWD;
+    g.d[0] = d_gate;
+    g.d[1] = d_up;
+    g.d[2] = (dw_down != nullptr) ? act : nullptr;
+    g.e[0] = gate_cache;
+    g.e[1] = up_cache;
+    g.ldd = inter;
+    int rc = gemm_sm100(g, s);
+    if (rc != L32_OK) return rc;
+    if (dx != nullptr) {
+        rc = dgrad_x(d_gate, d_up, w_gate, w_up, dx, t, hidden, inter, dtype, s);
+        if (rc != L32_OK) return rc;
+    }
+    if (dw_gate != nullptr) {
+        rc = wgrad(d_gate, inter, x, hidden, dw_gate, t, dtype, s);
+        if (rc != L32_OK) return rc;
+        rc = wgrad(d_up, inter, x, hidden, dw_up, t, dtype, s);
+        if (rc != L32_OK) return rc;
+    }
+    if (dw_down != nullptr) rc = wgrad(dy, hidden, act, inter, dw_down, t, dtype, s);
+    return rc;
+}
+
+int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t ldb, int b_mn_major, const void* a1,
+             int64_t lda1, const void* b1, int64_t ldb1, void* d, int64_t ldd, int m, int n, int k, int k1, int dtype,
+             int cta_group, int max_ctas, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (a == nullptr || b == nullptr || d == nullptr) return L32_ERR_NULL;
+    GemmProblem g = blank(m, n, dtype);
+    g.k[0] = k;
+    g.a[0] = op(a, lda, a_mn_major);
+    g.b[0] = op(b, ldb, b_mn_major);
+    if (a1 != nullptr) {
+        if (b1 == nullptr) return L32_ERR_NULL;
+        g.num_phases = 2;
+        g.k[1] = k1;
+        g.a[1] = op(a1, lda1, a_mn_major);
+        g.b[1] = op(b1, ldb1, b_mn_major);
+    }
+    g.epilogue = EPI_STORE;
+    g.d[0] = d;
+    g.ldd = ldd;
+    g.cta_group = cta_group;
+    g.max_ctas = max_ctas;
+    return gemm_sm100(g, as_stream(stream));
+}
+
+int l32_swiglu_act(const void* gate, const void* up, void* act, int64_t n, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (n < 0 || (n % 8) != 0) return L32_ERR_BAD_SHAPE;
+    if (n > 0 && (gate == nullptr || up == nullptr || act == nullptr)) return L32_ERR_NULL;
+    return static_cast<int>(swiglu_act_elementwise(gate, up, act, n, dtype, as_stream(stream)));
+}
+
+}  // extern "C"

@@ -1,0 +1,533 @@
+// K3/K4/K6: persistent warp-specialised tcgen05 GEMM for sm_100a with fused SwiGLU epilogues.
+//
+//   D[M,N] = sum_p A_p[M,K_p] * B_p[N,K_p]^T        (bf16 / fp16 operands, fp32 accumulation in TMEM)
+//
+// Replaces the reference's scalar CUDA-core kernels swiglu_forward_kernel / swiglu_down_forward_kernel /
+// swiglu_backward_kernel (reference Tools/swiglu/swiglu.cu:58-100, :228-272, :179-223) and the cuBLAS
+// F.linear calls of the live PyTorch path (reference Tools/swiglu/FusedSwiglu.py:18-20, Model/model.py:214-217).
+//
+// Structure (one CTA per SM, 256 threads; optional CTA pair = cta_group::2 with UMMA M = 256):
+//   warp 0   : TMA producer  (cp.async.bulk.tensor, 128-byte swizzle, ring of kStages smem slots)
+//   warp 1   : MMA issuer    (tcgen05.mma kind::f16, one elected thread of the leader CTA)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      (tcgen05.ld -> registers -> fused math -> 16-byte global stores)
+// TMEM holds two 256-column fp32 accumulator stages, so the epilogue of tile t overlaps the main loop of
+// tile t+1.  Tiles are visited in a grouped raster so concurrently running CTAs share A and B panels in L2.
+//
+// Epilogues:
+//   EPI_STORE      : D tile is 128*cta_group x 256.
+//   EPI_SWIGLU     : the 256 accumulator columns are [gate(128) | up(128)] of the same 128 act columns;
+//                    act = silu(g) * u is formed in registers, so gate and up never round-trip HBM
+//                    (they are written only when the caller asks for the backward caches).
+//   EPI_SWIGLU_BWD : D = d_act; reads the gate/up caches, recomputes sigmoid/SiLU in registers and emits
+//                    d_gate, d_up (and optionally the recomputed act for the w_down weight gradient).
+// Operands may be K-major ([rows][K]) or MN-major ([K][rows]); the latter serves the backward GEMMs
+// (dgrad through W^T, wgrad through X^T) without any explicit transpose.
+#include "l32_internal.cuh"
+
+#include <mutex>
+
+namespace l32 {
+namespace {
+
+constexpr int kBlockM = 128;   // accumulator rows per CTA (= TMEM lanes)
+constexpr int kBlockK = 64;    // one 128-byte swizzle atom of 16-bit elements
+constexpr int kUmmaK = 16;
+constexpr int kAccCols = 256;  // TMEM columns per accumulator stage (= UMMA N)
+constexpr int kThreads = 256;
+constexpr int kAtomBytes = kBlockK * 128;   // 64 rows x 128 B = 8 KiB: one swizzle-atom column of a tile
+
+template <int kCtaGroup>
+struct TileCfg {
+    static constexpr int kBRows = kAccCols / kCtaGroup;   // B rows (N) staged by one CTA
+    static constexpr int kABytes = kBlockM * kBlockK * 2;
+    static constexpr int kBBytes = kBRows * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (kCtaGroup == 2) ? 6 : 4;
+    static constexpr int kNumBarriers = 2 * kStages + 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kNumBarriers * 8 + 16 + 1024 /* alignment slack */;
+};
+
+struct GemmKernelParams {
+    CUtensorMap map_a[2];
+    CUtensorMap map_b[2];
+    int m, n;
+    int k[2];
+    int num_phases;
+    int a_mn_major, b_mn_major;
+    int tiles_m, tiles_n, raster_group;
+    uint32_t idesc;
+    void* d[3];
+    const void* e[2];
+    const void* bias[2];
+    long long ldd;
+};
+
+// One operand tile of `rows` x 64 (K) elements into shared memory.
+//   K-major : a single box {64 (K), rows}; smem = [rows][128 B], swizzled.
+//   MN-major: rows/64 boxes {64 (MN), 64 (K)}; smem = rows/64 atoms of [64 (K)][128 B].
+template <int kCtaGroup>
+L32_DEVICE void load_tile(const CUtensorMap* map, uint8_t* dst, uint64_t* full_bar, int mn_major, int row0, int rows,
+                          int k0) {
+    if (!mn_major) {
+        if constexpr (kCtaGroup == 2) tma_load_2d_pair(dst, map, full_bar, k0, row0, kEvictNormal);
+        else tma_load_2d(dst, map, full_bar, k0, row0, kEvictNormal);
+    } else {
+        for (int i = 0; i < rows / 64; ++i) {
+            if constexpr (kCtaGroup == 2) tma_load_2d_pair(dst + i * kAtomBytes, map, full_bar, row0 + i * 64, k0, kEvictNormal);
+            else tma_load_2d(dst + i * kAtomBytes, map, full_bar, row0 + i * 64, k0, kEvictNormal);
+        }
+    }
+}
+
+struct TileCoord {
+    int m_blk, n_blk;
+};
+L32_DEVICE TileCoord tile_coord(int t, int tiles_m, int tiles_n, int group) {
+    const int per_group = group * tiles_n;
+    const int g = t / per_group;
+    const int first_m = g * group;
+    const int gsize = min(group, tiles_m - first_m);
+    const int r = t - g * per_group;
+    TileCoord c;
+    c.m_blk = first_m + r % gsize;
+    c.n_blk = r / gsize;
+    return c;
+}
+
+L32_DEVICE void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+L32_DEVICE uint4 ld_global_nc_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// Store 32 consecutive columns of one row (16 packed registers), 8 columns per 16-byte store.
+L32_DEVICE void store_row32(void* base, const uint32_t (&v)[16], int n_valid) {
+    uint8_t* p = static_cast<uint8_t*>(base);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (j * 8 < n_valid) st_global_v4(p + j * 16, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+L32_DEVICE void load_row32(const void* base, uint32_t (&v)[16], int n_valid) {
+    const uint8_t* p = static_cast<const uint8_t*>(base);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 t = make_uint4(0, 0, 0, 0);
+        if (j * 8 < n_valid) t = ld_global_nc_v4(p + j * 16);
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+}
+
+template <int kCtaGroup, int kEpi, typename T>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmKernelParams p) {
+    using Cfg = TileCfg<kCtaGroup>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kTileNOut = (kEpi == EPI_SWIGLU) ? 128 : 256;   // output columns per tile
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const uint32_t lane = lane_id();
+    const uint32_t rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
+    const int cluster_id = blockIdx.x / kCtaGroup;
+    const int num_clusters = gridDim.x / kCtaGroup;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.map_a[0]);
+        tma_prefetch_desc(&p.map_b[0]);
+        if (p.num_phases == 2) tma_prefetch_desc(&p.map_a[1]);
+        if (p.num_phases == 2 || kEpi == EPI_SWIGLU) tma_prefetch_desc(&p.map_b[1]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], kCtaGroup);    // one producer arrival per CTA of the pair (+ tx bytes)
+            mbar_init(&empty_bar[i], 1);           // one tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);               // one tcgen05.commit
+            mbar_init(&tempty_bar[i], 4 * kCtaGroup);  // one arrival per epilogue warp of every CTA
+        }
+        fence_mbar_init();
+    }
+    if constexpr (kCtaGroup == 2) cluster_sync_all();   // both CTAs resident before the paired TMEM allocation
+    if (warp == 2) {
+        tmem_alloc<kCtaGroup>(tmem_slot, 512);
+        tmem_relinquish<kCtaGroup>();
+    }
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                const TileCoord tc = tile_coord(t, p.tiles_m, p.tiles_n, p.raster_group);
+                const int m0 = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM;
+                const int n0 = tc.n_blk * kTileNOut;
+                for (int ph = 0; ph < p.num_phases; ++ph) {
+                    const int num_kb = (p.k[ph] + kBlockK - 1) / kBlockK;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        uint8_t* sa = smem_a + stage * Cfg::kABytes;
+                        uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCtaGroup);
+                        load_tile<kCtaGroup>(&p.map_a[ph], sa, &full_bar[stage], p.a_mn_major, m0, kBlockM, kb * kBlockK);
+                        if constexpr (kEpi == EPI_SWIGLU) {
+                            if constexpr (kCtaGroup == 2) {
+                                // leader stages the gate rows, its peer the up rows of the same 128 act columns
+                                load_tile<2>(&p.map_b[rank], sb, &full_bar[stage], 0, n0, 128, kb * kBlockK);
+                            } else {
+                                load_tile<1>(&p.map_b[0], sb, &full_bar[stage], 0, n0, 128, kb * kBlockK);
+                                load_tile<1>(&p.map_b[1], sb + 128 * 128, &full_bar[stage], 0, n0, 128, kb * kBlockK);
+                            }
+                        } else {
+                            load_tile<kCtaGroup>(&p.map_b[ph], sb, &full_bar[stage], p.b_mn_major,
+                                                 n0 + static_cast<int>(rank) * Cfg::kBRows, Cfg::kBRows, kb * kBlockK);
+                        }
+                        if (rank != 0) mbar_arrive_remote(&full_bar[stage], 0);
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (rank == 0 && lane == 0) {
+            const uint32_t a_kstep = p.a_mn_major ? (kUmmaK * 128) : (kUmmaK * 2);   // bytes per UMMA K step
+            const uint32_t b_kstep = p.b_mn_major ? (kUmmaK * 128) : (kUmmaK * 2);
+            const uint32_t a_lbo = p.a_mn_major ? kAtomBytes : 0;
+            const uint32_t b_lbo = p.b_mn_major ? kAtomBytes : 0;
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kAccCols;
+                uint32_t accumulate = 0;
+                for (int ph = 0; ph < p.num_phases; ++ph) {
+                    const int num_kb = (p.k[ph] + kBlockK - 1) / kBlockK;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
+                        const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
+                            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
+                            umma_f16<kCtaGroup>(d_tmem, adesc, bdesc, p.idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        umma_commit<kCtaGroup>(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                umma_commit<kCtaGroup>(&tfull_bar[acc]);             // accumulator complete -> epilogue
+                acc ^= 1u;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue
+        const uint32_t q = warp - 4;                       // TMEM lane quarter owned by this warp
+        uint32_t acc = 0, acc_phase = 0;
+        const size_t esz = sizeof(T);
+        for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            const TileCoord tc = tile_coord(t, p.tiles_m, p.tiles_n, p.raster_group);
+            const int row = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM + q * 32 + lane;
+            const int n0 = tc.n_blk * kTileNOut;
+            const bool row_ok = row < p.m;
+            const size_t row_off = static_cast<size_t>(row_ok ? row : 0) * static_cast<size_t>(p.ldd);
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * kAccCols;
+
+            if constexpr (kEpi == EPI_STORE) {
+#pragma unroll 1
+                for (int c = 0; c < kAccCols / 32; ++c) {
+                    const int col = n0 + c * 32;
+                    if (col >= p.n) break;
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    tmem_ld_wait();
+                    uint32_t o[16];
+                    const T* bias = static_cast<const T*>(p.bias[0]);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float lo = __uint_as_float(v[2 * j]), hi = __uint_as_float(v[2 * j + 1]);
+                        if (bias != nullptr) {
+                            if (col + 2 * j < p.n) lo += static_cast<float>(bias[col + 2 * j]);
+                            if (col + 2 * j + 1 < p.n) hi += static_cast<float>(bias[col + 2 * j + 1]);
+                        }
+                        o[j] = Pack2<T>::pack(lo, hi);
+                    }
+                    if (row_ok) store_row32(static_cast<uint8_t*>(p.d[0]) + (row_off + col) * esz, o, p.n - col);
+                }
+            } else if constexpr (kEpi == EPI_SWIGLU) {
+#pragma unroll 1
+                for (int c = 0; c < 128 / 32; ++c) {
+                    const int col = n0 + c * 32;
+                    if (col >= p.n) break;
+                    uint32_t g[32], u[32];
+                    tmem_ld_32x32b_x32(taddr + c * 32, g);
+                    tmem_ld_32x32b_x32(taddr + 128 + c * 32, u);
+                    tmem_ld_wait();
+                    const T* bg = static_cast<const T*>(p.bias[0]);
+                    const T* bu = static_cast<const T*>(p.bias[1]);
+                    if (bg != nullptr || bu != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (col + j < p.n) {
+                                if (bg != nullptr) g[j] = __float_as_uint(__uint_as_float(g[j]) + static_cast<float>(bg[col + j]));
+                                if (bu != nullptr) u[j] = __float_as_uint(__uint_as_float(u[j]) + static_cast<float>(bu[col + j]));
+                            }
+                        }
+                    }
+                    uint32_t o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float g0 = __uint_as_float(g[2 * j]), g1 = __uint_as_float(g[2 * j + 1]);
+                        const float u0 = __uint_as_float(u[2 * j]), u1 = __uint_as_float(u[2 * j + 1]);
+                        o[j] = Pack2<T>::pack(silu_f32(g0) * u0, silu_f32(g1) * u1);
+                    }
+                    if (row_ok) store_row32(static_cast<uint8_t*>(p.d[0]) + (row_off + col) * esz, o, p.n - col);
+                    if (p.d[1] != nullptr) {   // backward caches
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = Pack2<T>::pack(__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1]));
+                        if (row_ok) store_row32(static_cast<uint8_t*>(p.d[1]) + (row_off + col) * esz, o, p.n - col);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = Pack2<T>::pack(__uint_as_float(u[2 * j]), __uint_as_float(u[2 * j + 1]));
+                        if (row_ok) store_row32(static_cast<uint8_t*>(p.d[2]) + (row_off + col) * esz, o, p.n - col);
+                    }
+                }
+            } else {   // EPI_SWIGLU_BWD
+#pragma unroll 1
+                for (int c = 0; c < kAccCols / 32; ++c) {
+                    const int col = n0 + c * 32;
+                    if (col >= p.n) break;
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c * 32, v);
+                    uint32_t gp[16], up[16];
+                    const int nv = row_ok ? (p.n - col) : 0;
+                    load_row32(static_cast<const uint8_t*>(p.e[0]) + (row_off + col) * esz, gp, nv);
+                    load_row32(static_cast<const uint8_t*>(p.e[1]) + (row_off + col) * esz, up, nv);
+                    tmem_ld_wait();
+                    uint32_t odg[16], odu[16], oact[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 g = Pack2<T>::unpack(gp[j]);
+                        const float2 u = Pack2<T>::unpack(up[j]);
+                        const float da0 = __uint_as_float(v[2 * j]), da1 = __uint_as_float(v[2 * j + 1]);
+                        const float s0 = sigmoid_f32(g.x), s1 = sigmoid_f32(g.y);
+                        const float silu0 = g.x * s0, silu1 = g.y * s1;
+                        // d silu(g)/dg = s * (1 + g * (1 - s))
+                        odg[j] = Pack2<T>::pack(da0 * u.x * (s0 * (1.0f + g.x * (1.0f - s0))),
+                                                da1 * u.y * (s1 * (1.0f + g.y * (1.0f - s1))));
+                        odu[j] = Pack2<T>::pack(da0 * silu0, da1 * silu1);
+                        oact[j] = Pack2<T>::pack(silu0 * u.x, silu1 * u.y);
+                    }
+                    if (row_ok) {
+                        store_row32(static_cast<uint8_t*>(p.d[0]) + (row_off + col) * esz, odg, p.n - col);
+                        store_row32(static_cast<uint8_t*>(p.d[1]) + (row_off + col) * esz, odu, p.n - col);
+                        if (p.d[2] != nullptr)
+                            store_row32(static_cast<uint8_t*>(p.d[2]) + (row_off + col) * esz, oact, p.n - col);
+                    }
+                }
+            }
+            // accumulator stage drained: hand it back to the MMA issuer of the leader CTA
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+                else mbar_arrive_remote(&tempty_bar[acc], 0);
+            }
+            acc ^= 1u;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<kCtaGroup>(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+template <int kCtaGroup, int kEpi, typename T>
+int launch(const GemmKernelParams& kp, int num_tiles, int max_ctas, cudaStream_t s) {
+    using Cfg = TileCfg<kCtaGroup>;
+    auto* kernel = gemm_kernel<kCtaGroup, kEpi, T>;
+    static bool configured = false;   // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        configured = true;
+    }
+    int ctas = num_sms();
+    if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+    int clusters = ctas / kCtaGroup;
+    if (clusters > num_tiles) clusters = num_tiles;
+    if (clusters < 1) clusters = 1;
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(clusters * kCtaGroup));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtaGroup;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, kp);
+    return static_cast<int>(e);
+}
+
+template <int kCtaGroup, typename T>
+int launch_epi(const GemmKernelParams& kp, int epi, int num_tiles, int max_ctas, cudaStream_t s) {
+    switch (epi) {
+        case EPI_STORE: return launch<kCtaGroup, EPI_STORE, T>(kp, num_tiles, max_ctas, s);
+        case EPI_SWIGLU: return launch<kCtaGroup, EPI_SWIGLU, T>(kp, num_tiles, max_ctas, s);
+        case EPI_SWIGLU_BWD: return launch<kCtaGroup, EPI_SWIGLU_BWD, T>(kp, num_tiles, max_ctas, s);
+        default: return L32_ERR_BAD_SHAPE;
+    }
+}
+
+}  // namespace
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        n = v;
+    }
+    return n;
+}
+
+int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                       uint32_t box_rows, uint32_t box_cols, int dtype) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (fn == nullptr) return L32_ERR_DRIVER;
+    if (!is_aligned16(ptr) || (ld_elems % 8) != 0) return L32_ERR_BAD_ALIGN;
+    if (box_rows == 0 || box_rows > 256 || box_cols != 64) return L32_ERR_BAD_SHAPE;
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {ld_elems * 2};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUtensorMapDataType dt = (dtype == L32_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? L32_OK : L32_ERR_DRIVER;
+}
+
+int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
+    if (g.dtype != L32_BF16 && g.dtype != L32_FP16) return L32_ERR_BAD_DTYPE;
+    if (g.m < 0 || g.n <= 0 || g.num_phases < 1 || g.num_phases > 2) return L32_ERR_BAD_SHAPE;
+    if (g.m == 0) return L32_OK;
+    if ((g.n % 8) != 0 || (g.ldd % 8) != 0) return L32_ERR_BAD_ALIGN;
+    if (g.epilogue == EPI_SWIGLU && (g.num_phases != 1 || g.b[0].mn_major || g.b[1].mn_major)) return L32_ERR_BAD_SHAPE;
+    for (int i = 0; i < 3; ++i)
+        if (g.d[i] != nullptr && !is_aligned16(g.d[i])) return L32_ERR_BAD_ALIGN;
+    if (g.d[0] == nullptr) return L32_ERR_NULL;
+    if (g.epilogue == EPI_SWIGLU && (g.d[1] == nullptr) != (g.d[2] == nullptr)) return L32_ERR_NULL;
+    if (g.epilogue == EPI_SWIGLU_BWD) {
+        if (g.d[1] == nullptr || g.e[0] == nullptr || g.e[1] == nullptr) return L32_ERR_NULL;
+        if (!is_aligned16(g.e[0]) || !is_aligned16(g.e[1])) return L32_ERR_BAD_ALIGN;
+    }
+
+    int cta_group = g.cta_group;
+    if (cta_group == 0) cta_group = (g.m > kBlockM) ? 2 : 1;
+    if (cta_group != 1 && cta_group != 2) return L32_ERR_BAD_SHAPE;
+
+    GemmKernelParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.m = g.m;
+    kp.n = g.n;
+    kp.num_phases = g.num_phases;
+    kp.a_mn_major = g.a[0].mn_major;
+    kp.b_mn_major = g.b[0].mn_major;
+    const int tile_n_out = (g.epilogue == EPI_SWIGLU) ? 128 : 256;
+    const int tile_m = kBlockM * cta_group;
+    kp.tiles_m = (g.m + tile_m - 1) / tile_m;
+    kp.tiles_n = (g.n + tile_n_out - 1) / tile_n_out;
+    kp.raster_group = g.raster_group > 0 ? g.raster_group : 16 / cta_group;
+    kp.idesc = make_idesc_f16(g.dtype == L32_BF16, static_cast<uint32_t>(tile_m), kAccCols, g.a[0].mn_major != 0,
+                              g.b[0].mn_major != 0);
+    for (int i = 0; i < 3; ++i) kp.d[i] = g.d[i];
+    kp.e[0] = g.e[0]; kp.e[1] = g.e[1];
+    kp.bias[0] = g.bias[0]; kp.bias[1] = g.bias[1];
+    kp.ldd = g.ldd;
+
+    const int b_box_rows = (g.epilogue == EPI_SWIGLU) ? 128 : kAccCols / cta_group;
+    for (int ph = 0; ph < g.num_phases; ++ph) {
+        if (g.k[ph] <= 0 || (g.k[ph] % 8) != 0) return L32_ERR_BAD_SHAPE;
+        if (g.a[ph].mn_major != g.a[0].mn_major || g.b[ph].mn_major != g.b[0].mn_major) return L32_ERR_BAD_SHAPE;
+        kp.k[ph] = g.k[ph];
+        int rc;
+        if (!g.a[ph].mn_major) rc = make_tensor_map_2d(&kp.map_a[ph], g.a[ph].ptr, g.m, g.k[ph], g.a[ph].ld, kBlockM, kBlockK, g.dtype);
+        else rc = make_tensor_map_2d(&kp.map_a[ph], g.a[ph].ptr, g.k[ph], g.m, g.a[ph].ld, kBlockK, 64, g.dtype);
+        if (rc != L32_OK) return rc;
+        if (g.epilogue != EPI_SWIGLU) {
+            if (!g.b[ph].mn_major) rc = make_tensor_map_2d(&kp.map_b[ph], g.b[ph].ptr, g.n, g.k[ph], g.b[ph].ld, b_box_rows, kBlockK, g.dtype);
+            else rc = make_tensor_map_2d(&kp.map_b[ph], g.b[ph].ptr, g.k[ph], g.n, g.b[ph].ld, kBlockK, 64, g.dtype);
+            if (rc != L32_OK) return rc;
+        }
+    }
+    if (g.epilogue == EPI_SWIGLU) {
+        for (int i = 0; i < 2; ++i) {
+            int rc = make_tensor_map_2d(&kp.map_b[i], g.b[i].ptr, g.n, g.k[0], g.b[i].ld, 128, kBlockK, g.dtype);
+            if (rc != L32_OK) return rc;
+        }
+    }
+
+    const int num_tiles = kp.tiles_m * kp.tiles_n;
+    if (g.dtype == L32_BF16) {
+        if (cta_group == 2) return launch_epi<2, __nv_bfloat16>(kp, g.epilogue, num_tiles, g.max_ctas, s);
+        return launch_epi<1, __nv_bfloat16>(kp, g.epilogue, num_tiles, g.max_ctas, s);
+    }
+    if (cta_group == 2) return launch_epi<2, __half>(kp, g.epilogue, num_tiles, g.max_ctas, s);
+    return launch_epi<1, __half>(kp, g.epilogue, num_tiles, g.max_ctas, s);
+}
+
+}  // namespace l32

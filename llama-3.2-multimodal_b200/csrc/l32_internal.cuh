@@ -1,0 +1,68 @@
+// Internal declarations shared by the kernel translation units and the C-ABI layer (api.cu).
+#pragma once
+#include "ptx_sm100.cuh"
+#include "../../include/l32_ffn.h"   // L32_OK / L32_ERR_* return codes
+#include <cstddef>
+
+namespace l32 {
+
+enum : int { L32_BF16 = 0, L32_FP16 = 1 };
+
+inline bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+int num_sms();
+
+// ---- rmsnorm.cu
+cudaError_t add_rmsnorm_fwd(const void* x, const void* residual, const void* weight, void* y, void* h_out, float* rms,
+                            int64_t rows, int C, float eps, int dtype, cudaStream_t s);
+cudaError_t rmsnorm_bwd(const void* dy, const void* h, const void* weight, const float* rms, void* dx, void* dw,
+                        float* workspace, int64_t rows, int C, int dtype, cudaStream_t s);
+size_t rmsnorm_bwd_workspace_bytes(int64_t rows, int C);
+
+// ---- gemm_sm100.cu : D[M,N] = sum_p A_p[M,K_p] * B_p[N,K_p]^T on tcgen05, fused epilogues
+enum : int {
+    EPI_STORE = 0,       // D -> d[0]                                     (tile 128*cta_group x 256)
+    EPI_SWIGLU = 1,      // b[0]=gate weights, b[1]=up weights; act = silu(g)*u -> d[0]; optional g -> d[1], u -> d[2]
+    EPI_SWIGLU_BWD = 2,  // D = d_act; e[0]=gate cache, e[1]=up cache; d_gate -> d[0], d_up -> d[1], optional act -> d[2]
+};
+
+struct GemmOperand {
+    const void* ptr;   // base pointer (16-byte aligned)
+    int64_t ld;        // row pitch in elements (multiple of 8)
+    int mn_major;      // 0: memory is [rows = M or N][cols = K]  (K contiguous)
+                       // 1: memory is [rows = K][cols = M or N]  (M/N contiguous)
+};
+
+struct GemmProblem {
+    int m, n;               // D is [m, n]; for EPI_SWIGLU n = intermediate size (act columns)
+    int num_phases;         // 1, or 2 for D = A0*B0^T + A1*B1^T (EPI_SWIGLU: must be 1)
+    int k[2];               // reduction length of each phase
+    GemmOperand a[2];       // a[1] used when num_phases == 2
+    GemmOperand b[2];       // EPI_SWIGLU: b[0] = gate weights, b[1] = up weights (both K-major)
+    int epilogue;           // EPI_*
+    void* d[3];             // outputs, see EPI_*; optional ones may be null
+    const void* e[2];       // EPI_SWIGLU_BWD: gate / up caches [m, n]
+    int64_t ldd;            // row pitch of every output / epilogue input, elements
+    const void* bias[2];    // optional per-column bias (bias[0] for D / gate, bias[1] for up)
+    int dtype;              // L32_BF16 / L32_FP16
+    int cta_group;          // 0 = auto, 1 or 2
+    int raster_group;       // 0 = auto: m-tiles per raster group
+    int max_ctas;           // 0 = all SMs (testing / tuning knob)
+};
+int gemm_sm100(const GemmProblem& p, cudaStream_t s);   // returns L32_* / cudaError_t
+
+// ---- elementwise.cu (n = element count, multiple of 8)
+cudaError_t swiglu_bwd_elementwise(const void* d_act, const void* gate, const void* up, void* d_gate, void* d_up,
+                                   int64_t n, int dtype, cudaStream_t s);
+cudaError_t swiglu_act_elementwise(const void* gate, const void* up, void* act, int64_t n, int dtype, cudaStream_t s);
+
+// ---- ffn_decode.cu : weight-streaming small-M FFN (tokens <= 128)
+int ffn_decode_swiglu(const void* x, const void* w_gate, const void* w_up, void* act, int tokens, int hidden, int inter,
+                      int dtype, cudaStream_t s);
+int ffn_decode_linear(const void* a, const void* w, void* y, int tokens, int in_features, int out_features, int dtype,
+                      cudaStream_t s);
+
+// ---- tensor-map helper (gemm_sm100.cu): 2-D row-major [rows, cols] 16-bit tensor, 128-byte swizzled box
+int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                       uint32_t box_rows, uint32_t box_cols, int dtype);
+
+}  // namespace l32

@@ -1,0 +1,316 @@
+"""Host-side mirror of the reference's operator interface for the decoder-block hot path.
+
+Same class names, constructor arguments, attribute names and state_dict keys as the reference:
+  LLAMARMSNorm / RMSNormFunction            reference Model/model.py:135-171
+  SwiGLUFunction / FusedSwiGLU              reference Tools/swiglu/FusedSwiglu.py:14-91
+  FusedFeedforward (+ FusedFeedForward)     reference Model/model.py:210-217, Tools/swiglu/FusedSwiglu.py:94-131
+  Linear_LORA                               reference Model/model.py:107-121
+  convert_feedforward_to_fused              reference Tools/swiglu/FusedSwiglu.py:134-166
+
+Dispatch follows the reference's gate (Model/model.py:165): CUDA tensors of a 16-bit float type run the
+sm_100a kernels through the C-ABI; everything else (fp32, CPU) evaluates the reference's own PyTorch
+expressions, which is what the reference does for those inputs.  The autograd wrappers are the *fixed*
+versions described in SURVEY.md section 8(b): they save what backward needs, honour needs_input_grad,
+never return a gradient for a None input and never mutate caller tensors.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+__all__ = [
+    "RMSNormFunction", "LLAMARMSNorm", "SwiGLUFunction", "FusedSwiGLU", "LinearFunction", "Linear_LORA", "FFNFunction",
+    "FusedFeedforward", "FusedFeedForward", "convert_feedforward_to_fused", "patch_reference", "convert_instances",
+]
+
+
+# ------------------------------------------------------------------------------------------------ RMSNorm
+class RMSNormFunction(torch.autograd.Function):
+    """y = rmsnorm(x + residual) * weight on the sm_100a kernels (reference Model/model.py:135-155)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, eps, residual=None):
+        need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 3))
+        y, rms, h = ops.add_rmsnorm_forward(x, weight, residual, eps, want_h=need_grad, want_rms=need_grad)
+        if need_grad:
+            # without a residual the normalised input is x itself: nothing extra is written
+            ctx.save_for_backward(h if h is not None else x, weight, rms)
+        ctx.has_residual = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        h, weight, rms = ctx.saved_tensors
+        dx, dw = ops.rmsnorm_backward(grad_output, h, weight, rms, want_dweight=ctx.needs_input_grad[1])
+        if dw is not None and dw.dtype != weight.dtype:
+            dw = dw.to(weight.dtype)
+        d_res = dx if (ctx.has_residual and ctx.needs_input_grad[3]) else None
+        return (dx if ctx.needs_input_grad[0] else None), dw, None, d_res
+
+
+class LLAMARMSNorm(nn.Module):
+    """Drop-in for reference Model/model.py:158-171 (same ctor, `.weight`, forward(x, residual=None))."""
+
+    def __init__(self, dim: int, eps: float = 1e-6):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+    def forward(self, x, residual=None):
+        if ops.supported(x):
+            return RMSNormFunction.apply(x, self.weight, self.eps, residual)
+        # reference semantics for fp32 / CPU inputs (Model/model.py:166-171)
+        if residual is not None:
+            x = x + residual
+        variance = x.pow(2).mean(-1, keepdim=True)
+        x = x * torch.rsqrt(variance + self.eps)
+        return x * self.weight
+
+
+# ------------------------------------------------------------------------------------------------ SwiGLU
+def _silu_bwd(d_act, gate, up):
+    s = torch.sigmoid(gate)
+    return d_act * up * (s * (1 + gate * (1 - s))), d_act * (gate * s)
+
+
+class SwiGLUFunction(torch.autograd.Function):
+    """act = silu(x w_gate^T + b_gate) * (x w_up^T + b_up) (reference Tools/swiglu/FusedSwiglu.py:14-40).
+
+    Differentiable on every path (the reference's fallback branch saved nothing and its CUDA backward was
+    never defined); bias gradients are returned when biases exist.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w_gate, w_up, b_gate=None, b_up=None):
+        need_grad = any(ctx.needs_input_grad)
+        ctx.cuda_path = ops.supported(x)
+        if not ctx.cuda_path:
+            gate = F.linear(x, w_gate, b_gate)
+            up = F.linear(x, w_up, b_up)
+            if need_grad:
+                ctx.save_for_backward(x, w_gate, w_up, gate, up)
+            return F.silu(gate) * up
+        act, gate, up = ops.swiglu_forward(x, w_gate, w_up, b_gate, b_up, want_cache=need_grad)
+        if need_grad:
+            ctx.save_for_backward(x, w_gate, w_up, gate, up)
+        return act
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, w_gate, w_up, gate, up = ctx.saved_tensors
+        nx, ng, nu, nbg, nbu = ctx.needs_input_grad
+        if not ctx.cuda_path:
+            d_gate, d_up = _silu_bwd(grad_output, gate, up)
+            dg2, du2 = d_gate.reshape(-1, d_gate.shape[-1]), d_up.reshape(-1, d_up.shape[-1])
+            x2 = x.reshape(-1, x.shape[-1])
+            dx = (d_gate @ w_gate + d_up @ w_up) if nx else None
+            return (dx, dg2.t() @ x2 if ng else None, du2.t() @ x2 if nu else None,
+                    dg2.sum(0) if nbg else None, du2.sum(0) if nbu else None)
+        dx, dwg, dwu, d_gate, d_up = ops.swiglu_backward(grad_output, x, w_gate, w_up, gate, up, want_dx=nx,
+                                                         want_dw=(ng or nu))
+        dbg = d_gate.float().sum(0).to(gate.dtype) if nbg else None
+        dbu = d_up.float().sum(0).to(up.dtype) if nbu else None
+        return dx, (dwg if ng else None), (dwu if nu else None), dbg, dbu
+
+
+class FusedSwiGLU(nn.Module):
+    """Drop-in for reference Tools/swiglu/FusedSwiglu.py:43-91 (params w_gate, w_up [I, H]; b_gate, b_up)."""
+
+    def __init__(self, hidden_size, intermediate_size, bias=False):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.intermediate_size = intermediate_size
+        self.w_gate = nn.Parameter(torch.empty(intermediate_size, hidden_size))
+        self.w_up = nn.Parameter(torch.empty(intermediate_size, hidden_size))
+        if bias:
+            self.b_gate = nn.Parameter(torch.zeros(intermediate_size))
+            self.b_up = nn.Parameter(torch.zeros(intermediate_size))
+        else:
+            self.register_parameter("b_gate", None)
+            self.register_parameter("b_up", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.w_gate, a=5 ** 0.5)
+        nn.init.kaiming_uniform_(self.w_up, a=5 ** 0.5)
+
+    def forward(self, x):
+        return SwiGLUFunction.apply(x, self.w_gate, self.w_up, self.b_gate, self.b_up)
+
+    def extra_repr(self):
+        return (f"hidden_size={self.hidden_size}, intermediate_size={self.intermediate_size}, "
+                f"bias={self.b_gate is not None}")
+
+
+# ------------------------------------------------------------------------------------------------ Linear / LoRA
+class LinearFunction(torch.autograd.Function):
+    """y = a w^T + b on the tcgen05 GEMM; backward = two more GEMMs with MN-major operands (no transposes)."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias=None):
+        ctx.save_for_backward(a, weight)
+        ctx.has_bias = bias is not None
+        return ops.linear_forward(a, weight, bias)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        a, weight = ctx.saved_tensors
+        out_f, in_f = weight.shape
+        gy = grad_y.contiguous().view(-1, out_f)
+        if gy.dtype != a.dtype:
+            gy = gy.to(a.dtype)
+        a2 = a.contiguous().view(-1, in_f)
+        da = dw = db = None
+        if ctx.needs_input_grad[0]:
+            da = ops.gemm(gy, weight.contiguous(), b_mn_major=True).view(a.shape)      # gy [T,out] x W[out,in]
+        if ctx.needs_input_grad[1]:
+            dw = ops.gemm(gy, a2, a_mn_major=True, b_mn_major=True)                     # gy^T a
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = gy.float().sum(0).to(weight.dtype)
+        return da, dw, db
+
+
+def _linear(x, weight, bias=None):
+    if ops.supported(x) and weight.dtype == x.dtype:
+        return LinearFunction.apply(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
+class Linear_LORA(nn.Module):
+    """Drop-in for reference Model/model.py:107-121: frozen base + (alpha/rank) * B(A(dropout(x))).
+
+    The base projection runs on the tcgen05 GEMM; the rank-r side path stays in PyTorch (O(r) work).
+    """
+
+    def __init__(self, in_dim: int, out_dim: int, rank: int, alpha: float, dropout: float):
+        super().__init__()
+        self.linear = nn.Linear(in_dim, out_dim, bias=False)
+        self.lora_a = nn.Linear(in_dim, rank, bias=False)
+        self.lora_b = nn.Linear(rank, out_dim, bias=False)
+        self.rank = rank
+        self.alpha = alpha
+        self.dropout = nn.Dropout(p=dropout)
+        self.linear.weight.requires_grad = False
+        self.lora_a.weight.requires_grad = True
+        self.lora_b.weight.requires_grad = True
+
+    def forward(self, x):
+        base = _linear(x, self.linear.weight, self.linear.bias)
+        return base + (self.alpha / self.rank) * self.lora_b(self.lora_a(self.dropout(x)))
+
+
+# ------------------------------------------------------------------------------------------------ feed-forward
+class FFNFunction(torch.autograd.Function):
+    """Whole feed-forward y = w_down(silu(x w_gate^T) * (x w_up^T)) with a hand-written backward:
+    d_act GEMM whose epilogue recomputes SiLU' in registers, two-phase dX GEMM, three wgrad GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w_gate, w_up, w_down, b_gate=None, b_up=None, b_down=None):
+        need_grad = any(ctx.needs_input_grad)
+        y, gate, up = ops.ffn_forward(x, w_gate, w_up, w_down, b_gate, b_up, b_down, want_cache=need_grad)
+        if need_grad:
+            ctx.save_for_backward(x, w_gate, w_up, w_down, gate, up)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x, w_gate, w_up, w_down, gate, up = ctx.saved_tensors
+        nx, ng, nu, nd, nbg, nbu, nbd = ctx.needs_input_grad
+        dx, dwg, dwu, dwd, d_gate, d_up = ops.ffn_backward(grad_y, x, w_gate, w_up, w_down, gate, up, want_dx=nx,
+                                                           want_dw_gate_up=(ng or nu), want_dw_down=nd)
+        dbg = d_gate.float().sum(0).to(gate.dtype) if nbg else None
+        dbu = d_up.float().sum(0).to(up.dtype) if nbu else None
+        dbd = grad_y.reshape(-1, grad_y.shape[-1]).float().sum(0).to(w_down.dtype) if nbd else None
+        return dx, (dwg if ng else None), (dwu if nu else None), dwd, dbg, dbu, dbd
+
+
+def _is_lora(m) -> bool:
+    return all(hasattr(m, a) for a in ("linear", "lora_a", "lora_b", "rank", "alpha"))
+
+
+class FusedFeedforward(nn.Module):
+    """Drop-in for reference Model/model.py:210-217 (`.swiglu`, `.w_down`; state_dict keys unchanged).
+
+    `w_down` may be swapped for a Linear_LORA (ours or the reference's) by the README's LoRA surgery
+    (reference README.md:179-188); its frozen base then still runs on the tcgen05 GEMM.
+    """
+
+    def __init__(self, hidden_size: int, intermediate_size: int, bias: bool = False):
+        super().__init__()
+        self.hidden_size = hidden_size
+        self.intermediate_size = intermediate_size
+        self.swiglu = FusedSwiGLU(hidden_size, intermediate_size, bias=bias)
+        self.w_down = nn.Linear(intermediate_size, hidden_size, bias=bias)
+
+    def forward(self, x):
+        sw, wd = self.swiglu, self.w_down
+        if ops.supported(x) and sw.w_gate.dtype == x.dtype:
+            if isinstance(wd, nn.Linear) and wd.weight.dtype == x.dtype:
+                return FFNFunction.apply(x, sw.w_gate, sw.w_up, wd.weight, sw.b_gate, sw.b_up, wd.bias)
+            if _is_lora(wd) and wd.linear.weight.dtype == x.dtype:
+                act = sw(x)
+                base = LinearFunction.apply(act, wd.linear.weight, wd.linear.bias)
+                return base + (wd.alpha / wd.rank) * wd.lora_b(wd.lora_a(wd.dropout(act)))
+        return wd(sw(x))
+
+
+FusedFeedForward = FusedFeedforward   # the reference spells it both ways (FusedSwiglu.py:94 vs model.py:210)
+
+
+def convert_feedforward_to_fused(feedforward_module):
+    """w1 = gate, w3 = up, w2 = down (reference Tools/swiglu/FusedSwiglu.py:134-166)."""
+    hidden_size = feedforward_module.w2.out_features
+    intermediate_size = feedforward_module.w1.out_features
+    has_bias = feedforward_module.w1.bias is not None
+    fused = FusedFeedforward(hidden_size, intermediate_size, bias=has_bias)
+    fused = fused.to(device=feedforward_module.w1.weight.device, dtype=feedforward_module.w1.weight.dtype)
+    with torch.no_grad():
+        fused.swiglu.w_gate.copy_(feedforward_module.w1.weight)
+        fused.swiglu.w_up.copy_(feedforward_module.w3.weight)
+        fused.w_down.weight.copy_(feedforward_module.w2.weight)
+        if has_bias:
+            fused.swiglu.b_gate.copy_(feedforward_module.w1.bias)
+            fused.swiglu.b_up.copy_(feedforward_module.w3.bias)
+            fused.w_down.bias.copy_(feedforward_module.w2.bias)
+    return fused
+
+
+def patch_reference(model_module, swiglu_module=None):
+    """Point an imported reference `Model.model` (and `Tools.swiglu.FusedSwiglu`) at this implementation.
+
+    After the call, models built from the reference's own classes (MllamaForConditionalGeneration,
+    TransformerBlock, ...) construct our LLAMARMSNorm / FusedFeedforward / Linear_LORA; existing instances
+    can be converted with `convert_instances`.
+    """
+    model_module.LLAMARMSNorm = LLAMARMSNorm
+    model_module.RMSNormFunction = RMSNormFunction
+    model_module.FusedFeedforward = FusedFeedforward
+    model_module.FusedSwiGLU = FusedSwiGLU
+    model_module.Linear_LORA = Linear_LORA
+    model_module.HAS_RMSNORM_EXT = True
+    if swiglu_module is not None:
+        swiglu_module.SwiGLUFunction = SwiGLUFunction
+        swiglu_module.FusedSwiGLU = FusedSwiGLU
+        swiglu_module.FusedFeedForward = FusedFeedforward
+        swiglu_module.CUDA_AVAILABLE = True
+
+
+def convert_instances(root: nn.Module) -> nn.Module:
+    """Re-class existing reference module instances in place (parameters and state_dict keys untouched)."""
+    for m in root.modules():
+        name = type(m).__name__
+        if name == "LLAMARMSNorm" and not isinstance(m, LLAMARMSNorm):
+            m.__class__ = LLAMARMSNorm
+        elif name == "FusedSwiGLU" and not isinstance(m, FusedSwiGLU):
+            m.__class__ = FusedSwiGLU
+        elif name in ("FusedFeedforward", "FusedFeedForward") and not isinstance(m, FusedFeedforward):
+            m.__class__ = FusedFeedforward
+            if not hasattr(m, "hidden_size"):
+                m.hidden_size = m.swiglu.hidden_size
+                m.intermediate_size = m.swiglu.intermediate_size
+        elif name == "Linear_LORA" and not isinstance(m, Linear_LORA):
+            m.__class__ = Linear_LORA
+    return root

@@ -1,0 +1,258 @@
+"""Tensor-level wrappers over the C-ABI: torch is used only for device memory and the current stream.
+
+Every function takes CUDA bf16/fp16 tensors, allocates outputs with torch, and enqueues the kernels on
+torch's current stream of the tensor's device.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import L32Error, check, lib
+
+_DT = {torch.bfloat16: 0, torch.float16: 1}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise L32Error(f"unsupported dtype {t.dtype}: the sm_100a kernels take bfloat16 or float16") from None
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _check_cuda(*ts):
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise L32Error("expected CUDA tensors (the CUDA path has no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise L32Error(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def supported(x: torch.Tensor) -> bool:
+    """The reference's gate for its CUDA path (Model/model.py:165): CUDA tensor of a 16-bit float type."""
+    return x.is_cuda and x.dtype in _DT
+
+
+# --------------------------------------------------------------------------------------------- RMSNorm
+def add_rmsnorm_forward(x, weight, residual=None, eps=1e-5, *, want_h=False, want_rms=True, h_out=None):
+    """y = rmsnorm(x + residual) * weight.  Returns (y, rms|None, h|None).
+
+    h (= x + residual rounded to x.dtype) is produced only when `want_h` and a residual is given (without a
+    residual h is x itself).  `h_out` lets the raw reference ABI alias h onto `residual`.
+    """
+    _check_cuda(x, weight, residual)
+    hidden = x.shape[-1]
+    xc = x.contiguous()
+    rows = xc.numel() // hidden if hidden else 0
+    rc = None if residual is None else residual.contiguous()
+    if rc is not None and rc.shape != xc.shape:
+        raise L32Error(f"residual shape {tuple(rc.shape)} != input shape {tuple(xc.shape)}")
+    w = weight.contiguous()
+    if w.dtype != xc.dtype:
+        w = w.to(xc.dtype)
+    if w.numel() != hidden:
+        raise L32Error(f"weight has {w.numel()} elements, expected {hidden}")
+    y = torch.empty_like(xc)
+    rms = torch.empty(rows, dtype=torch.float32, device=xc.device) if want_rms else None
+    h = h_out
+    if h is None and want_h and rc is not None:
+        h = torch.empty_like(xc)
+    with torch.cuda.device(xc.device):
+        check(lib().l32_add_rmsnorm_forward(_ptr(xc), _ptr(rc), _ptr(w), _ptr(y), _ptr(h), _ptr(rms), rows, hidden,
+                                            float(eps), _dtype_code(xc), _stream(xc)), "l32_add_rmsnorm_forward")
+    return y.view(x.shape), rms, (h.view(x.shape) if h is not None else None)
+
+
+def rmsnorm_backward(grad_out, h, weight, rms, *, want_dweight=True):
+    """(dx, dweight|None) for y = rmsnorm(h) * weight, given rms = sqrt(mean(h^2) + eps) from the forward."""
+    _check_cuda(grad_out, h, weight, rms)
+    hidden = h.shape[-1]
+    hc = h.contiguous()
+    gc = grad_out.contiguous()
+    if gc.dtype != hc.dtype:
+        gc = gc.to(hc.dtype)
+    rows = hc.numel() // hidden if hidden else 0
+    w = weight.contiguous()
+    if w.dtype != hc.dtype:
+        w = w.to(hc.dtype)
+    dx = torch.empty_like(hc)
+    dw = torch.empty(hidden, dtype=hc.dtype, device=hc.device) if want_dweight else None
+    L = lib()
+    ws_bytes = L.l32_rmsnorm_backward_workspace_bytes(rows, hidden)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=hc.device)
+    with torch.cuda.device(hc.device):
+        check(L.l32_rmsnorm_backward(_ptr(gc), _ptr(hc), _ptr(w), _ptr(rms.contiguous()), _ptr(dx), _ptr(dw), _ptr(ws),
+                                     ws_bytes, rows, hidden, _dtype_code(hc), _stream(hc)), "l32_rmsnorm_backward")
+    return dx.view(h.shape), dw
+
+
+# --------------------------------------------------------------------------------------------- SwiGLU / FFN
+def _flat_tokens(x):
+    hidden = x.shape[-1]
+    xc = x.contiguous()
+    return xc.view(-1, hidden), xc.numel() // hidden if hidden else 0
+
+
+def _check_ffn_weights(x2, w_gate, w_up, w_down=None):
+    inter, hidden = w_gate.shape
+    if x2.shape[1] != hidden or tuple(w_up.shape) != (inter, hidden):
+        raise L32Error(f"shape mismatch: x[..., {x2.shape[1]}], w_gate{tuple(w_gate.shape)}, w_up{tuple(w_up.shape)}")
+    if w_down is not None and tuple(w_down.shape) != (hidden, inter):
+        raise L32Error(f"w_down{tuple(w_down.shape)} is not [hidden={hidden}, inter={inter}]")
+    for w in (w_gate, w_up, w_down):
+        if w is not None and w.dtype != x2.dtype:
+            raise L32Error(f"weight dtype {w.dtype} != activation dtype {x2.dtype}")
+    return hidden, inter
+
+
+def swiglu_forward(x, w_gate, w_up, b_gate=None, b_up=None, *, want_cache=False):
+    """act = silu(x w_gate^T + b_gate) * (x w_up^T + b_up).  Returns (act, gate_cache|None, up_cache|None)."""
+    _check_cuda(x, w_gate, w_up, b_gate, b_up)
+    x2, tokens = _flat_tokens(x)
+    wg, wu = w_gate.contiguous(), w_up.contiguous()
+    hidden, inter = _check_ffn_weights(x2, wg, wu)
+    out_shape = (*x.shape[:-1], inter)
+    act = torch.empty(tokens, inter, dtype=x2.dtype, device=x2.device)
+    gate = torch.empty_like(act) if want_cache else None
+    up = torch.empty_like(act) if want_cache else None
+    bg = None if b_gate is None else b_gate.contiguous().to(x2.dtype)
+    bu = None if b_up is None else b_up.contiguous().to(x2.dtype)
+    with torch.cuda.device(x2.device):
+        check(lib().l32_swiglu_forward(_ptr(x2), _ptr(wg), _ptr(wu), _ptr(bg), _ptr(bu), _ptr(act), _ptr(gate), _ptr(up),
+                                       tokens, hidden, inter, _dtype_code(x2), _stream(x2)), "l32_swiglu_forward")
+    if want_cache:
+        return act.view(out_shape), gate.view(out_shape), up.view(out_shape)
+    return act.view(out_shape), None, None
+
+
+def swiglu_backward(grad_act, x, w_gate, w_up, gate_cache, up_cache, *, want_dx=True, want_dw=True):
+    """(dx|None, dw_gate|None, dw_up|None, d_gate, d_up); d_gate/d_up are views into the workspace."""
+    _check_cuda(grad_act, x, w_gate, w_up, gate_cache, up_cache)
+    x2, tokens = _flat_tokens(x)
+    wg, wu = w_gate.contiguous(), w_up.contiguous()
+    hidden, inter = _check_ffn_weights(x2, wg, wu)
+    ga = grad_act.contiguous().view(-1, inter)
+    if ga.dtype != x2.dtype:
+        ga = ga.to(x2.dtype)
+    dx = torch.empty_like(x2) if want_dx else None
+    dwg = torch.empty_like(wg) if want_dw else None
+    dwu = torch.empty_like(wu) if want_dw else None
+    L = lib()
+    ws_bytes = L.l32_swiglu_backward_workspace_bytes(tokens, inter)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x2.device)
+    with torch.cuda.device(x2.device):
+        check(L.l32_swiglu_backward(_ptr(ga), _ptr(x2), _ptr(wg), _ptr(wu), _ptr(gate_cache.contiguous()),
+                                    _ptr(up_cache.contiguous()), _ptr(dx), _ptr(dwg), _ptr(dwu), _ptr(ws), ws_bytes,
+                                    tokens, hidden, inter, _dtype_code(x2), _stream(x2)), "l32_swiglu_backward")
+    part = ws_bytes // 2
+    n = tokens * inter
+    d_gate = ws[:n * 2].view(x2.dtype).view(tokens, inter)
+    d_up = ws[part:part + n * 2].view(x2.dtype).view(tokens, inter)
+    return (dx.view(x.shape) if dx is not None else None), dwg, dwu, d_gate, d_up
+
+
+def linear_forward(a, weight, bias=None):
+    """y = a weight^T + bias with weight [out_features, in_features] (nn.Linear layout)."""
+    _check_cuda(a, weight, bias)
+    a2, tokens = _flat_tokens(a)
+    w = weight.contiguous()
+    out_f, in_f = w.shape
+    if a2.shape[1] != in_f or w.dtype != a2.dtype:
+        raise L32Error(f"linear: a[..., {a2.shape[1]}] {a2.dtype} vs weight{tuple(w.shape)} {w.dtype}")
+    y = torch.empty(tokens, out_f, dtype=a2.dtype, device=a2.device)
+    b = None if bias is None else bias.contiguous().to(a2.dtype)
+    with torch.cuda.device(a2.device):
+        check(lib().l32_linear_forward(_ptr(a2), _ptr(w), _ptr(b), _ptr(y), tokens, in_f, out_f, _dtype_code(a2),
+                                       _stream(a2)), "l32_linear_forward")
+    return y.view(*a.shape[:-1], out_f)
+
+
+def ffn_forward(x, w_gate, w_up, w_down, b_gate=None, b_up=None, b_down=None, *, want_cache=False):
+    """y = (silu(x w_gate^T) * (x w_up^T)) w_down^T.  Returns (y, gate_cache|None, up_cache|None)."""
+    _check_cuda(x, w_gate, w_up, w_down, b_gate, b_up, b_down)
+    x2, tokens = _flat_tokens(x)
+    wg, wu, wd = w_gate.contiguous(), w_up.contiguous(), w_down.contiguous()
+    hidden, inter = _check_ffn_weights(x2, wg, wu, wd)
+    y = torch.empty(tokens, hidden, dtype=x2.dtype, device=x2.device)
+    act = torch.empty(tokens, inter, dtype=x2.dtype, device=x2.device)
+    gate = torch.empty_like(act) if want_cache else None
+    up = torch.empty_like(act) if want_cache else None
+    cast = lambda b: None if b is None else b.contiguous().to(x2.dtype)
+    bg, bu, bd = cast(b_gate), cast(b_up), cast(b_down)
+    with torch.cuda.device(x2.device):
+        check(lib().l32_ffn_forward(_ptr(x2), _ptr(wg), _ptr(wu), _ptr(wd), _ptr(bg), _ptr(bu), _ptr(bd), _ptr(y),
+                                    _ptr(act), _ptr(gate), _ptr(up), tokens, hidden, inter, _dtype_code(x2), _stream(x2)),
+              "l32_ffn_forward")
+    return y.view(x.shape), gate, up
+
+
+def ffn_backward(grad_y, x, w_gate, w_up, w_down, gate_cache, up_cache, *, want_dx=True, want_dw_gate_up=True,
+                 want_dw_down=True):
+    """(dx|None, dw_gate|None, dw_up|None, dw_down|None, d_gate, d_up) for the whole feed-forward."""
+    _check_cuda(grad_y, x, w_gate, w_up, w_down, gate_cache, up_cache)
+    x2, tokens = _flat_tokens(x)
+    wg, wu, wd = w_gate.contiguous(), w_up.contiguous(), w_down.contiguous()
+    hidden, inter = _check_ffn_weights(x2, wg, wu, wd)
+    gy = grad_y.contiguous().view(-1, hidden)
+    if gy.dtype != x2.dtype:
+        gy = gy.to(x2.dtype)
+    dx = torch.empty_like(x2) if want_dx else None
+    dwg = torch.empty_like(wg) if want_dw_gate_up else None
+    dwu = torch.empty_like(wu) if want_dw_gate_up else None
+    dwd = torch.empty_like(wd) if want_dw_down else None
+    L = lib()
+    ws_bytes = L.l32_ffn_backward_workspace_bytes(tokens, inter)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x2.device)
+    with torch.cuda.device(x2.device):
+        check(L.l32_ffn_backward(_ptr(gy), _ptr(x2), _ptr(wg), _ptr(wu), _ptr(wd), _ptr(gate_cache.contiguous()),
+                                 _ptr(up_cache.contiguous()), _ptr(dx), _ptr(dwg), _ptr(dwu), _ptr(dwd), _ptr(ws), ws_bytes,
+                                 tokens, hidden, inter, _dtype_code(x2), _stream(x2)), "l32_ffn_backward")
+    part = ws_bytes // 3
+    n = tokens * inter
+    d_gate = ws[:n * 2].view(x2.dtype).view(tokens, inter)
+    d_up = ws[part:part + n * 2].view(x2.dtype).view(tokens, inter)
+    return (dx.view(x.shape) if dx is not None else None), dwg, dwu, dwd, d_gate, d_up
+
+
+def gemm(a, b, *, a_mn_major=False, b_mn_major=False, a1=None, b1=None, cta_group=0, max_ctas=0):
+    """D[m,n] = A B^T (+ A1 B1^T).  K-major operand: tensor [rows, k]; MN-major operand: tensor [k, rows]."""
+    _check_cuda(a, b, a1, b1)
+    m, k = (a.shape[1], a.shape[0]) if a_mn_major else (a.shape[0], a.shape[1])
+    n, kb = (b.shape[1], b.shape[0]) if b_mn_major else (b.shape[0], b.shape[1])
+    if k != kb:
+        raise L32Error(f"gemm: reduction lengths differ ({k} vs {kb})")
+    k1 = 0
+    if a1 is not None:
+        k1 = a1.shape[0] if a_mn_major else a1.shape[1]
+    for t in (a, b, a1, b1):
+        if t is not None and (t.stride(-1) != 1 or t.dtype != a.dtype):
+            raise L32Error("gemm operands must share a dtype and be contiguous along the last dimension")
+    d = torch.empty(m, n, dtype=a.dtype, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().l32_gemm(_ptr(a), a.stride(0), int(a_mn_major), _ptr(b), b.stride(0), int(b_mn_major), _ptr(a1),
+                             0 if a1 is None else a1.stride(0), _ptr(b1), 0 if b1 is None else b1.stride(0), _ptr(d), n,
+                             m, n, k, k1, _dtype_code(a), cta_group, max_ctas, _stream(a)), "l32_gemm")
+    return d
+
+
+def swiglu_act(gate, up):
+    """Unfused act = silu(gate) * up (benchmark reference point for the fusion saving)."""
+    _check_cuda(gate, up)
+    g, u = gate.contiguous(), up.contiguous()
+    act = torch.empty_like(g)
+    with torch.cuda.device(g.device):
+        check(lib().l32_swiglu_act(_ptr(g), _ptr(u), _ptr(act), g.numel(), _dtype_code(g), _stream(g)), "l32_swiglu_act")
+    return act
