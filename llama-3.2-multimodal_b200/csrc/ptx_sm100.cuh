@@ -71,12 +71,15 @@ L32_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
                  : "memory");
 }
 // Arrive on the barrier that lives at the same smem offset in CTA `cta_rank` of this cluster.
+// Deliberately the default (.release.cta) form, like CUTLASS' ClusterBarrier::arrive(cta_id): a
+// `.release.cluster` arrive compiles to MEMBAR.ALL + ERRBAR, which also waits for this thread's
+// outstanding TMA loads and serialised the peer CTA's producer (one k-block per TMA latency, measured).
 L32_DEVICE void mbar_arrive_remote(uint64_t* bar, uint32_t cta_rank) {
     asm volatile(
         "{\n\t"
         ".reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
         "}\n" ::"r"(smem_u32(bar)),
         "r"(cta_rank)
         : "memory");
