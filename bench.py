@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Benchmark of the decoder-block hot path (fused residual Add-RMSNorm -> SwiGLU feed-forward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 11b|90b] [--mode ...]
+
+One "step" = one pass of the hot path over one batch of synthetic activations: norm2(attn_out, residual) ->
+ff(normed) (reference Model/model.py:271-272) at BASELINE.json configs[1] (Llama-3.2-11B text block, hidden 4096,
+hidden_dim 14336, bf16 prefill, 4 x 2048 tokens).  Prints ONE JSON line on rank 0 (contract in the task statement):
+  value   : whole-job tokens/s with inputs resident in HBM (CUDA events, barrier + synchronize on both sides,
+            max over ranks);
+  e2e     : the same metric through the public module API with HOST (pinned) input buffers and a host copy of
+            the result, host<->device copies inside the timed region (double-buffered on copy streams);
+  roofline: dominant kernel = the fused gate/up tcgen05 GEMM, achieved TFLOP/s from CUDA events recorded around
+            that launch inside the timed region, against MEASURED_PEAKS.json;
+  cpu_baseline: the reference's own CPU path (PyTorch fp32 expressions, oracle port) on this box's host cores.
+--impl reference times that CPU path alone (rank 0 only) and prints the same line with "impl": "reference".
+N > 1: tensor-parallel FFN (column-sharded gate/up, row-sharded down, NCCL reduce-scatter + all-gather overlapped
+with the GEMMs by token chunks), same total batch -> "scaling": "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (hidden, inter, batch, seq, label)
+    "11b": (4096, 14336, 4, 2048, "llama-3.2-11b-vision text block: add-rmsnorm + swiglu ffn, bf16 prefill 4x2048 tokens"),
+    "90b": (8192, 28672, 4, 2048, "llama-3.2-90b-vision text block: add-rmsnorm + swiglu ffn, bf16 prefill 4x2048 tokens"),
+}
+METRIC = "ffn_block_tokens_per_sec"
+UNIT = "tokens/s"
+EPS = 1e-5
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p.get("bf16_tflops_sustained"), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0,
+                source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+
+        def parse(rows):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, line in rows:
+                f = [v.strip() for v in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, pw, reasons
+
+        inside = [r for r in self.rows if t0 is None or (t0 <= r[0] <= t1 + 0.15)]
+        note = None
+        sm, mx, pw, reasons = parse(inside)
+        if not sm:
+            sm, mx, pw, reasons = parse(self.rows)
+            note = "timed region shorter than one 100 ms sample; all samples of the run used"
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+               "reasons": sorted(reasons)}
+        if note:
+            out["note"] = note
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def cpu_reference(hidden, inter, sample_tokens, steps, warmup, min_seconds=0.0, max_seconds=60.0):
+    """The reference's live CPU path for this hot path (PyTorch fp32: Model/model.py:166-171 +
+    Tools/swiglu/FusedSwiglu.py:18-20 + model.py:217), restated in oracle/ffn_oracle.py, on all host cores.
+    Each step processes `sample_tokens` tokens of the workload.  Returns (tokens_per_s, ms_per_step, cores, steps)."""
+    from oracle import ffn_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(sample_tokens, hidden, generator=g)
+    res = torch.randn(sample_tokens, hidden, generator=g)
+    gamma = 1 + 0.1 * torch.randn(hidden, generator=g)
+    wg = (torch.rand(inter, hidden, generator=g) * 2 - 1) / hidden ** 0.5
+    wu = (torch.rand(inter, hidden, generator=g) * 2 - 1) / hidden ** 0.5
+    wd = (torch.rand(hidden, inter, generator=g) * 2 - 1) / inter ** 0.5
+
+    def step():
+        with torch.no_grad():
+            return O.feedforward(O.add_rmsnorm(x, gamma, EPS, res), wg, wu, wd)
+
+    for _ in range(max(1, warmup)):
+        step()
+    done, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        done += 1
+        el = time.perf_counter() - t0
+        if (done >= steps and el >= min_seconds) or el >= max_seconds:
+            break
+    return sample_tokens * done / el, el / done * 1e3, torch.get_num_threads(), done
+
+
+def run_reference(args):
+    hidden, inter, batch, seq, label = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 256 if args.workload == "11b" else 128
+    tps, ms, cores, done = cpu_reference(hidden, inter, sample, args.steps, args.warmup, max_seconds=150.0)
+    sample_txt = (f"{sample} of the workload's {batch * seq} tokens per step, fp32, torch CPU (MKL) with {cores} threads; "
+                  "oracle port of reference Model/model.py:166-171,217 + Tools/swiglu/FusedSwiglu.py:18-20")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": label, "hidden": hidden, "hidden_dim": inter, "tokens_per_step": sample,
+                   "note": "reference CPU path on host cores (the reference has no working accelerated FFN)"},
+        "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_txt},
+        "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    import llama32_b200 as L
+    from llama32_b200 import _lib, ops
+    from llama32_b200.tp import TensorParallelFFN
+
+    hidden, inter, batch, seq, label = WORKLOADS[args.workload]
+    tokens = batch * seq
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    dt = torch.bfloat16
+    train = args.mode == "train"
+    if train and world > 1:
+        raise SystemExit("--mode train is a single-GPU measurement (the tensor-parallel path is forward only)")
+
+    # synthetic inputs and random-init weights exactly as the modules initialise them; same seed
+    # on every rank so the replicated tensors agree
+    torch.manual_seed(0)
+    norm = L.LLAMARMSNorm(hidden, eps=EPS)
+    ffn = L.FusedFeedforward(hidden, inter)           # kaiming_uniform(a=sqrt 5) == U(+-1/sqrt(fan_in))
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.1 * torch.randn(hidden))
+    norm = norm.to(dev, dt)
+    ffn = ffn.to(dev, dt)
+    nbuf = 2                                           # rotate input buffers; footprint per step >> 126 MB L2
+    gen = torch.Generator(device=dev).manual_seed(1)
+    xs = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)]
+    rs = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)]
+    dys = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)] if train else None
+    tp = TensorParallelFFN(ffn, chunks=args.tp_chunks) if world > 1 else None
+    if tp is not None:
+        ffn = None                                     # the unsharded copy is not needed any more
+        torch.cuda.empty_cache()
+    if train:
+        for p in list(norm.parameters()) + list(ffn.parameters()):
+            p.requires_grad_(True)
+
+    k_ev = []                                          # (start, end) events around the dominant kernel
+
+    def step(i, instrument=False):
+        x, r = xs[i % nbuf], rs[i % nbuf]
+        if train:
+            x = x.detach().requires_grad_(True)
+            normed = norm(x, residual=r)
+            y = ffn(normed)
+            y.backward(dys[i % nbuf])
+            return y
+        with torch.no_grad():
+            normed = norm(x, residual=r)
+            if tp is not None:
+                return tp(normed)
+            if instrument:
+                # same three launches as ffn(normed), with events around the fused gate/up GEMM
+                n2 = normed.view(-1, hidden)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                act, _, _ = ops.swiglu_forward(n2, ffn.swiglu.w_gate, ffn.swiglu.w_up)
+                e1.record()
+                k_ev.append((e0, e1))
+                return ops.linear_forward(act, ffn.w_down.weight).view(batch, seq, hidden)
+            return ffn(normed)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    # ---- timed region 1: device-resident inputs
+    launches0 = _lib.lib().l32_kernel_launch_count()
+    barrier()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i, instrument=(world == 1 and not train))
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = _lib.lib().l32_kernel_launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = tokens / (ms_step * 1e-3)
+
+    # ---- timed region 2: end to end through the module API with pinned host buffers
+    h_x = [torch.randn(batch, seq, hidden).to(dt).pin_memory() for _ in range(nbuf)]
+    h_r = [torch.randn(batch, seq, hidden).to(dt).pin_memory() for _ in range(nbuf)]
+    h_y = [torch.empty(batch, seq, hidden, dtype=dt).pin_memory() for _ in range(nbuf)]
+    d_x = [torch.empty(batch, seq, hidden, device=dev, dtype=dt) for _ in range(nbuf)]
+    d_r = [torch.empty(batch, seq, hidden, device=dev, dtype=dt) for _ in range(nbuf)]
+    s_h2d, s_d2h, s_cmp = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
+    ev_in = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_cmp = [torch.cuda.Event() for _ in range(nbuf)]
+    ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+
+    def e2e_steps(n):
+        for i in range(n):
+            b = i % nbuf
+            with torch.cuda.stream(s_h2d):
+                s_h2d.wait_event(ev_cmp[b])            # the compute that last read d_x[b] / d_r[b] is done
+                d_x[b].copy_(h_x[b], non_blocking=True)
+                d_r[b].copy_(h_r[b], non_blocking=True)
+                ev_in[b].record(s_h2d)
+            s_cmp.wait_event(ev_in[b])
+            with torch.no_grad():
+                normed = norm(d_x[b], residual=d_r[b])
+                y = tp(normed) if tp is not None else ffn(normed)
+            ev_cmp[b].record(s_cmp)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(ev_cmp[b])
+                s_d2h.wait_event(ev_out[b])
+                h_y[b].copy_(y, non_blocking=True)
+                y.record_stream(s_d2h)
+                ev_out[b].record(s_d2h)
+
+    e2e = None
+    if not train:
+        e2e_steps(max(3, args.warmup))
+        barrier()
+        e0.record()
+        e2e_steps(args.steps)
+        s_cmp.wait_stream(s_d2h)
+        s_cmp.wait_stream(s_h2d)
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+        per_tensor = tokens * hidden * 2
+        e2e = {"value": tokens / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+               "h2d_bytes_per_step": 2 * per_tensor, "d2h_bytes_per_step": per_tensor,
+               "api": "llama32_b200.LLAMARMSNorm + FusedFeedforward modules; pinned host buffers, copies on side "
+                      "streams double-buffered against compute"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    flops_step = 6.0 * tokens * hidden * inter * (3.0 if train else 1.0)
+    roofline = None
+    if k_ev:
+        torch.cuda.synchronize()
+        k_ms = statistics.mean(a.elapsed_time(b) for a, b in k_ev)
+        alg_flops = 4.0 * tokens * hidden * inter          # gate + up GEMMs: 4*H*I flop per token
+        achieved = alg_flops / (k_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "gemm_kernel<cta_group 2, EPI_SWIGLU, bf16> (fused gate/up + SiLU*mul)",
+                    "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + ", burst figure",
+                    "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
+                    "frac_of_sustained_peak": (achieved / peaks["bf16_tflops_sustained"]) if peaks["bf16_tflops_sustained"] else None,
+                    "traffic": None, "traffic_note": "see profiles/ for dram__bytes of this kernel from ncu --set full"}
+    step_tflops = flops_step / (ms_step * 1e-3) / 1e12
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample = 256 if args.workload == "11b" else 128
+        tps, ms, cores, done = cpu_reference(hidden, inter, sample, steps=3, warmup=1, min_seconds=10.0, max_seconds=30.0)
+        cpu = {"value": tps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{done} steps x {sample} tokens of the workload, fp32 torch CPU path of the reference "
+                         f"(oracle port), {ms:.1f} ms/step"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": label + (" fwd+bwd (all weights trainable)" if train else " forward"),
+                   "hidden": hidden, "hidden_dim": inter, "global_batch_tokens": tokens,
+                   "parallelism": f"tp{world}" if world > 1 else "single-gpu",
+                   "l2_policy": "inputs larger than L2: ~0.85 GB touched per step, 2 rotating activation buffers",
+                   "step_tflops": step_tflops, "step_frac_of_bf16_peak": step_tflops * (1 if world == 1 else 1.0 / world) / peaks["bf16_tflops"]},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="11b")
+    ap.add_argument("--mode", choices=["prefill", "train"], default="prefill")
+    ap.add_argument("--tp-chunks", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (the CUDA path has no CPU fallback); "
+                             "use --impl reference for the CPU reference arm")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,8 @@ extern "C" {
 
 /* ABI version of this header (bumped on any signature change). */
 L32_API int l32_abi_version(void);
+/* Number of CUDA kernels this library has launched in the calling process so far (monotonic). */
+L32_API unsigned long long l32_kernel_launch_count(void);
 /* Human-readable text for a return code of this library (static storage). */
 L32_API const char* l32_error_string(int code);
 

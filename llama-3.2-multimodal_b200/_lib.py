@@ -24,6 +24,7 @@ c_void_p, c_int, c_int64, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, cty
 # name -> (restype, argtypes); mirrors include/l32_ffn.h one to one (tests/test_abi.py checks the header).
 SIGNATURES = {
     "l32_abi_version": (c_int, []),
+    "l32_kernel_launch_count": (ctypes.c_ulonglong, []),
     "l32_error_string": (ctypes.c_char_p, [c_int]),
     "l32_add_rmsnorm_forward": (c_int, [c_void_p] * 6 + [c_int64, c_int, c_float, c_int, c_void_p]),
     "l32_rmsnorm_backward_workspace_bytes": (c_size_t, [c_int64, c_int]),

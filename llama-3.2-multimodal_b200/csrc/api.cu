@@ -3,7 +3,15 @@
 #include "../../include/l32_ffn.h"
 #include "l32_internal.cuh"
 
+#include <atomic>
+
 using namespace l32;
+
+namespace l32 {
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+}  // namespace l32
 
 namespace {
 
@@ -66,6 +74,8 @@ bool shapes_ok(int64_t tokens, int hidden, int inter) {
 extern "C" {
 
 int l32_abi_version(void) { return 1; }
+
+unsigned long long l32_kernel_launch_count(void) { return launch_count(); }
 
 const char* l32_error_string(int code) {
     switch (code) {

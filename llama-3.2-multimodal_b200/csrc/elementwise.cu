@@ -75,6 +75,7 @@ cudaError_t swiglu_bwd_elementwise(const void* d_act, const void* gate, const vo
     else
         swiglu_bwd_kernel<__half><<<ew_grid(nvec), 256, 0, s>>>((const __half*)d_act, (const __half*)gate, (const __half*)up,
                                                                 (__half*)d_gate, (__half*)d_up, nvec);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -86,6 +87,7 @@ cudaError_t swiglu_act_elementwise(const void* gate, const void* up, void* act, 
                                                                        (__nv_bfloat16*)act, nvec);
     else
         swiglu_act_kernel<__half><<<ew_grid(nvec), 256, 0, s>>>((const __half*)gate, (const __half*)up, (__half*)act, nvec);
+    count_launch();
     return cudaGetLastError();
 }
 

@@ -418,6 +418,7 @@ int launch(const GemmKernelParams& kp, int num_tiles, int max_ctas, cudaStream_t
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, kp);
+    if (e == cudaSuccess) count_launch();
     return static_cast<int>(e);
 }
 

@@ -8,6 +8,10 @@ namespace l32 {
 
 enum : int { L32_BF16 = 0, L32_FP16 = 1 };
 
+// Process-wide count of kernels this library has launched (reported by bench.py as `gpu_launches`).
+void count_launch(int n = 1);
+unsigned long long launch_count();
+
 inline bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 int num_sms();
 

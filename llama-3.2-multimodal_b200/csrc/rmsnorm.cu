@@ -357,6 +357,7 @@ static cudaError_t launch_fwd_fast(const T* x, const T* residual, const T* weigh
         else
             add_rmsnorm_fwd_kernel<T, RT, VPT, false, false><<<grid, block, 0, s>>>(x, residual, weight, y, h_out, rms, rows, C, eps);
     }
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -374,6 +375,7 @@ static cudaError_t add_rmsnorm_fwd_t(const T* x, const T* residual, const T* wei
         return launch_fwd_fast<T, 512, 4>(x, residual, weight, y, h_out, rms, rows, C, eps, s);
     }
     add_rmsnorm_fwd_generic_kernel<T><<<static_cast<unsigned>(rows), 256, 0, s>>>(x, residual, weight, y, h_out, rms, rows, C, eps);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -394,6 +396,7 @@ static cudaError_t launch_bwd_fast(const T* dy, const T* h, const T* weight, con
         if (e != cudaSuccess) return e;
     }
     k<<<grid, 512, smem, s>>>(dy, h, weight, rms, dx, partial, rows, C);
+    count_launch();
     return cudaGetLastError();
 }
 
@@ -422,11 +425,13 @@ static cudaError_t rmsnorm_bwd_t(const T* dy, const T* h, const T* weight, const
     } else {
         grid = bwd_grid(rows, 1);
         rmsnorm_bwd_generic_kernel<T><<<grid, 256, 0, s>>>(dy, h, weight, rms, dx, workspace, rows, C);
+        count_launch();
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e;
     if (dw != nullptr) {
         rmsnorm_dw_reduce_kernel<T><<<(C + 127) / 128, 128, 0, s>>>(workspace, dw, grid, C);
+        count_launch();
         e = cudaGetLastError();
     }
     return e;

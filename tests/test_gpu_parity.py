@@ -1,0 +1,385 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against
+  (1) the reference's own fp32 outputs (tests/golden, produced by oracle/make_golden.py from the real reference),
+  (2) the CPU oracle on seeded bf16-representable inputs, forward and every gradient,
+  (3) at BASELINE.json's full sizes: row/column subsets against the oracle plus size-independent properties.
+Tolerances (bf16/fp16 storage, fp32 accumulation; SURVEY.md section 8c / BASELINE.md section 6):
+  forward  : rel-L2 <= 1e-2 and max-abs <= 2^-6 * max|ref|
+  gradients: rel-L2 <= 1e-2 and max-abs <= 2^-5 * max|ref|
+"""
+import math
+
+import pytest
+import torch
+
+import llama32_b200 as L
+from conftest import load_golden
+from llama32_b200 import ops
+from oracle import ffn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+FWD = (1e-2, 2.0 ** -6)
+BWD = (1e-2, 2.0 ** -5)
+
+
+def close(got, ref, tol, what=""):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert torch.isfinite(got).all(), what
+    r, m = O.rel_l2(got, ref), O.max_abs_over_max_ref(got, ref)
+    assert r <= tol[0] and m <= tol[1], f"{what}: rel-L2 {r:.3e} (<= {tol[0]}), max-abs/max|ref| {m:.3e} (<= {tol[1]:.3e})"
+
+
+def dev(t, dtype=torch.bfloat16):
+    return t.to(DEV, dtype)
+
+
+# ----------------------------------------------------------------------------------------------- goldens
+@pytest.mark.parametrize("tag", ["small", "odd", "cfg1"])
+def test_rmsnorm_vs_reference_outputs(tag):
+    g = load_golden(f"rmsnorm_{tag}.npz")
+    w = dev(g["weight"])
+    wr = w.float().cpu()      # gamma is not bf16-representable in the fixture: compare on what the kernel saw
+    for res_key, res in (("nores", None), ("res", g["residual"])):
+        x = dev(g["x"]).requires_grad_(True)
+        r = None if res is None else dev(res).requires_grad_(True)
+        wp = w.clone().requires_grad_(True)
+        y = L.RMSNormFunction.apply(x, wp, g["eps"], r)
+        y.backward(dev(g["grad_out"]))
+        yr, dxr, dwr, drr = O.add_rmsnorm_grads(g["x"], wr, g["eps"], res, g["grad_out"])
+        close(y, yr, FWD, f"y {tag} {res_key}")
+        close(x.grad, dxr, BWD, "dx")
+        close(wp.grad, dwr, BWD, "dweight")
+        if r is not None:
+            close(r.grad, drr, BWD, "dresidual")
+        # and directly against the reference's numbers (gamma rounding included in the tolerance)
+        close(y, g[f"y_{res_key}"], FWD, "y vs reference fixture")
+        close(x.grad, g[f"dx_{res_key}"], BWD, "dx vs reference fixture")
+
+
+@pytest.mark.parametrize("tag", ["small", "cfg1"])
+def test_ffn_vs_reference_outputs(tag):
+    g = load_golden(f"ffn_{tag}.npz")
+    hidden, inter = g["w_gate"].shape[1], g["w_gate"].shape[0]
+    ff = L.FusedFeedforward(hidden, inter).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        ff.swiglu.w_gate.copy_(dev(g["w_gate"])); ff.swiglu.w_up.copy_(dev(g["w_up"])); ff.w_down.weight.copy_(dev(g["w_down"]))
+    x = dev(g["x"]).requires_grad_(True)
+    act = ff.swiglu(x)
+    y = ff(x)
+    close(act, g["act"], FWD, "act")
+    close(y, g["y"], FWD, "y")
+    y.backward(dev(g["grad_out"]))
+    close(x.grad, g["dx"], BWD, "dx")
+    if "dw_gate" in g:
+        close(ff.swiglu.w_gate.grad, g["dw_gate"], BWD, "dw_gate")
+        close(ff.swiglu.w_up.grad, g["dw_up"], BWD, "dw_up")
+        close(ff.w_down.weight.grad, g["dw_down"], BWD, "dw_down")
+
+
+def test_ffn_bias_vs_reference_outputs():
+    g = load_golden("ffn_bias.npz")
+    ff = L.FusedFeedforward(64, 104, bias=True).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        ff.swiglu.w_gate.copy_(dev(g["w_gate"])); ff.swiglu.w_up.copy_(dev(g["w_up"])); ff.w_down.weight.copy_(dev(g["w_down"]))
+        ff.swiglu.b_gate.copy_(dev(g["b_gate"])); ff.swiglu.b_up.copy_(dev(g["b_up"])); ff.w_down.bias.copy_(dev(g["b_down"]))
+    bg, bu, bd = (ff.swiglu.b_gate.float().cpu(), ff.swiglu.b_up.float().cpu(), ff.w_down.bias.float().cpu())
+    x = dev(g["x"]).requires_grad_(True)
+    y = ff(x)
+    yr = O.feedforward(g["x"], g["w_gate"], g["w_up"], g["w_down"], bg, bu, bd)
+    close(y, yr, FWD, "y (bias)")
+    y.backward(dev(g["grad_out"]))
+    close(x.grad, g["dx"], BWD, "dx (bias)")
+    assert ff.swiglu.b_gate.grad is not None and ff.w_down.bias.grad is not None
+
+
+def test_block_hot_path_vs_reference_outputs():
+    g = load_golden("block_cfg1.npz")
+    norm2 = L.LLAMARMSNorm(256, eps=g["eps"]).to(DEV, torch.bfloat16)
+    ff = L.FusedFeedforward(256, 688).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        norm2.weight.copy_(dev(g["norm2_weight"]))
+        ff.swiglu.w_gate.copy_(dev(g["w_gate"])); ff.swiglu.w_up.copy_(dev(g["w_up"])); ff.w_down.weight.copy_(dev(g["w_down"]))
+    attn = dev(g["attn_out"])
+    hidden_before = dev(g["hidden"])
+    keep = hidden_before.clone()
+    normed = norm2(attn, residual=hidden_before)
+    out = attn + ff(normed)
+    assert torch.equal(hidden_before, keep), "the shipped wrapper must not mutate the residual (SURVEY.md 0.5)"
+    close(normed, g["normed"], FWD, "normed")
+    close(out, g["block_out"], FWD, "block_out")
+
+
+def test_lora_vs_reference_outputs():
+    g = load_golden("lora_small.npz")
+    lin = L.Linear_LORA(176, 64, rank=16, alpha=32.0, dropout=0.0).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        lin.linear.weight.copy_(dev(g["w"])); lin.lora_a.weight.copy_(dev(g["lora_a"])); lin.lora_b.weight.copy_(dev(g["lora_b"]))
+    close(lin(dev(g["x"])), g["y"], (2e-2, 2.0 ** -5), "lora y")   # rank-16 side path runs in bf16 torch
+
+
+# ----------------------------------------------------------------------------------------------- oracle, seeded
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rows,c", [(1, 256), (3, 8), (17, 4096), (127, 1000), (5, 8192), (2, 16384), (9, 250), (4, 20000)])
+def test_add_rmsnorm_shapes(dtype, rows, c):
+    torch.manual_seed(rows * 131 + c)
+    rnd = O.bf16_representable if dtype == torch.bfloat16 else O.fp16_representable
+    x, r, g = rnd(torch.randn(rows, c)), rnd(torch.randn(rows, c)), rnd(torch.randn(rows, c))
+    w = rnd(1 + 0.1 * torch.randn(c))
+    for res in (None, r):
+        y, rms, h = ops.add_rmsnorm_forward(dev(x, dtype), dev(w, dtype), None if res is None else dev(res, dtype), 1e-5,
+                                            want_h=True)
+        close(y, O.add_rmsnorm(x, w, 1e-5, res), FWD, "y")
+        close(rms, O.rms_of(x, 1e-5, res), (1e-5, 1e-5), "rms")
+        hh = x if res is None else x + res
+        if res is not None:
+            close(h, hh, FWD, "h")
+        hq = hh.to(dtype).float()
+        dx, dw = ops.rmsnorm_backward(dev(g, dtype), dev(hq, dtype), dev(w, dtype), rms)
+        cdx, cdw = O.add_rmsnorm_grads_closed_form(hq, w, 1e-5, g)
+        close(dx, cdx, BWD, "dx")
+        close(dw, cdw, BWD, "dw")
+
+
+def test_rmsnorm_edge_cases():
+    w = torch.ones(64, device=DEV, dtype=torch.bfloat16)
+    y, rms, _ = ops.add_rmsnorm_forward(torch.zeros(0, 64, device=DEV, dtype=torch.bfloat16), w, None, 1e-5)
+    assert y.shape == (0, 64) and rms.shape == (0,)
+    y, rms, _ = ops.add_rmsnorm_forward(torch.zeros(3, 64, device=DEV, dtype=torch.bfloat16), w, None, 1e-5)
+    assert torch.isfinite(y).all() and (y == 0).all()
+    assert torch.allclose(rms, torch.full((3,), math.sqrt(1e-5), device=DEV))
+    # 3-D input, non-contiguous input, fp32 weight (default-constructed module) all accepted
+    x = torch.randn(2, 5, 128, device=DEV).to(torch.bfloat16)
+    n = L.LLAMARMSNorm(128).to(DEV)            # fp32 weight
+    close(n(x), O.add_rmsnorm(x.float().cpu(), torch.ones(128), 1e-6), FWD, "3-D")
+    xt = torch.randn(128, 6, device=DEV).to(torch.bfloat16).t()
+    close(n(xt), O.add_rmsnorm(xt.float().cpu(), torch.ones(128), 1e-6), FWD, "non-contiguous")
+
+
+def test_raw_rmsnorm_extension_abi():
+    """rmsnorm.forward/backward keep the reference signature, including the in-place residual update."""
+    import rmsnorm
+    x = torch.randn(6, 256, device=DEV).to(torch.float16)
+    r = torch.randn(6, 256, device=DEV).to(torch.float16)
+    w = torch.randn(256, device=DEV).to(torch.float16)
+    r0 = r.clone()
+    out, rms = rmsnorm.forward(x, w, r, 1e-5)
+    assert out.dtype == torch.float16 and rms.dtype == torch.float32 and rms.shape == (6,)
+    close(r, x.float() + r0.float(), FWD, "residual := x + residual")
+    close(out, O.add_rmsnorm(x.float().cpu(), w.float().cpu(), 1e-5, r0.float().cpu()), FWD, "out")
+    dx, dw = rmsnorm.backward(torch.ones_like(x), r, w, rms)
+    assert dx.shape == x.shape and dw.shape == (256,) and dw.dtype == torch.float16
+
+
+SHAPES = [(1, 64, 104), (3, 256, 688), (100, 256, 688), (128, 128, 256), (129, 512, 264), (300, 1024, 2048), (520, 328, 776)]
+
+
+@pytest.mark.parametrize("tokens,hidden,inter", SHAPES)
+def test_ffn_forward_backward_vs_oracle(tokens, hidden, inter):
+    s = O.synthetic_ffn(tokens, hidden, inter, seed=tokens + hidden)
+    x, wg, wu, wd, dy = (dev(s[k]) for k in ("x", "w_gate", "w_up", "w_down", "dy"))
+    y, gate, up = ops.ffn_forward(x, wg, wu, wd, want_cache=True)
+    gr, ur = O.gate_up(s["x"], s["w_gate"], s["w_up"])
+    close(gate, gr, FWD, "gate cache")
+    close(up, ur, FWD, "up cache")
+    ref = O.feedforward_grads(s["x"], s["w_gate"], s["w_up"], s["w_down"], s["dy"])
+    close(y, ref["y"], FWD, "y")
+    y2, _, _ = ops.ffn_forward(x, wg, wu, wd, want_cache=False)
+    assert torch.equal(y, y2), "cache flag must not change the result"
+    dx, dwg, dwu, dwd, _, _ = ops.ffn_backward(dy, x, wg, wu, wd, gate, up)
+    close(dx, ref["dx"], BWD, "dx")
+    close(dwg, ref["dw_gate"], BWD, "dw_gate")
+    close(dwu, ref["dw_up"], BWD, "dw_up")
+    close(dwd, ref["dw_down"], BWD, "dw_down")
+
+
+@pytest.mark.parametrize("tokens,hidden,inter", [(5, 64, 104), (260, 256, 688)])
+def test_swiglu_extension_abi_vs_oracle(tokens, hidden, inter):
+    """swiglu_fused.forward / backward / forward_down with the reference's signatures (3-D x, None biases)."""
+    import swiglu_fused
+    s = O.synthetic_ffn(tokens, hidden, inter, seed=11)
+    x = dev(s["x"]).view(1, tokens, hidden)
+    wg, wu, wd = dev(s["w_gate"]), dev(s["w_up"]), dev(s["w_down"])
+    out, gc, uc = swiglu_fused.forward(x, wg, wu, None, None)
+    assert out.shape == (1, tokens, inter) and gc.shape == out.shape and uc.shape == out.shape
+    ga = O.bf16_representable(torch.randn(1, tokens, inter))
+    ref = O.swiglu_grads(s["x"].view(1, tokens, hidden), s["w_gate"], s["w_up"], ga)
+    close(out, ref["act"], FWD, "act")
+    gx, gwg, gwu = swiglu_fused.backward(dev(ga), x, wg, wu, gc, uc)
+    close(gx, ref["dx"], BWD, "grad_x")
+    close(gwg, ref["dw_gate"], BWD, "grad_w_gate")
+    close(gwu, ref["dw_up"], BWD, "grad_w_up")
+    yd = swiglu_fused.forward_down(x, wg, wu, wd)
+    close(yd, O.feedforward(s["x"].view(1, tokens, hidden), s["w_gate"], s["w_up"], s["w_down"]), FWD, "forward_down")
+
+
+def test_fp16_ffn():
+    s = O.synthetic_ffn(200, 256, 512, seed=5)
+    h = {k: O.fp16_representable(v) for k, v in s.items()}
+    y, _, _ = ops.ffn_forward(*(dev(h[k], torch.float16) for k in ("x", "w_gate", "w_up", "w_down")))
+    close(y, O.feedforward(h["x"], h["w_gate"], h["w_up"], h["w_down"]), (2e-3, 2.0 ** -9), "fp16 y")
+
+
+def test_ffn_edge_cases():
+    wg = torch.randn(104, 64, device=DEV).to(torch.bfloat16)
+    wu, wd = torch.randn_like(wg), torch.randn(64, 104, device=DEV).to(torch.bfloat16)
+    y, _, _ = ops.ffn_forward(torch.zeros(0, 64, device=DEV, dtype=torch.bfloat16), wg, wu, wd)
+    assert y.shape == (0, 64)
+    y, _, _ = ops.ffn_forward(torch.zeros(7, 64, device=DEV, dtype=torch.bfloat16), wg, wu, wd)
+    assert (y == 0).all()
+    with pytest.raises(RuntimeError):   # hidden not a multiple of 8: loud error, no silent fallback
+        ops.swiglu_forward(torch.zeros(4, 60, device=DEV, dtype=torch.bfloat16),
+                           torch.zeros(104, 60, device=DEV, dtype=torch.bfloat16),
+                           torch.zeros(104, 60, device=DEV, dtype=torch.bfloat16))
+    with pytest.raises(RuntimeError):   # fp32 tensors never reach the kernels
+        ops.swiglu_forward(torch.zeros(4, 64, device=DEV), wg.float(), wu.float())
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_operand_layouts(cta_group, a_mn, b_mn):
+    torch.manual_seed(0)
+    m, n, k = 392, 520, 328
+    a = O.bf16_representable(torch.randn(m, k))
+    b = O.bf16_representable(torch.randn(n, k))
+    a1 = O.bf16_representable(torch.randn(m, 200))
+    b1 = O.bf16_representable(torch.randn(n, 200))
+    lay = lambda t, mn: dev(t.t().contiguous() if mn else t)
+    d = ops.gemm(lay(a, a_mn), lay(b, b_mn), a_mn_major=a_mn, b_mn_major=b_mn, cta_group=cta_group)
+    close(d, a @ b.t(), (5e-3, 2.0 ** -7), "single phase")
+    d2 = ops.gemm(lay(a, a_mn), lay(b, b_mn), a_mn_major=a_mn, b_mn_major=b_mn, a1=lay(a1, a_mn), b1=lay(b1, b_mn),
+                  cta_group=cta_group)
+    close(d2, a @ b.t() + a1 @ b1.t(), (5e-3, 2.0 ** -7), "two phase")
+
+
+def test_module_autograd_end_to_end_and_lora():
+    s = O.synthetic_ffn(384, 256, 688, seed=21)
+    norm = L.LLAMARMSNorm(256, eps=1e-5).to(DEV, torch.bfloat16)
+    ff = L.FusedFeedforward(256, 688).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        norm.weight.copy_(dev(s["gamma"]))
+        ff.swiglu.w_gate.copy_(dev(s["w_gate"])); ff.swiglu.w_up.copy_(dev(s["w_up"])); ff.w_down.weight.copy_(dev(s["w_down"]))
+    # LoRA surgery on w_down (reference README.md:179-188): frozen base on the tcgen05 GEMM, dX-only through it
+    lo = L.Linear_LORA(688, 256, rank=16, alpha=32.0, dropout=0.0).to(DEV, torch.bfloat16)
+    la = O.bf16_representable(torch.randn(16, 688) / 688 ** 0.5)
+    lb = O.bf16_representable(0.05 * torch.randn(256, 16))
+    with torch.no_grad():
+        lo.linear.weight.copy_(ff.w_down.weight); lo.lora_a.weight.copy_(dev(la)); lo.lora_b.weight.copy_(dev(lb))
+    ff.w_down = lo
+    x = dev(s["x"]).requires_grad_(True)
+    r = dev(s["residual"]).requires_grad_(True)
+    y = ff(norm(x, residual=r))
+    y.backward(dev(s["dy"]))
+    xs, rs = s["x"].clone().requires_grad_(True), s["residual"].clone().requires_grad_(True)
+    gm, wg, wu = (s[k].clone().requires_grad_(True) for k in ("gamma", "w_gate", "w_up"))
+    las, lbs = la.clone().requires_grad_(True), lb.clone().requires_grad_(True)
+    act = O.swiglu(O.add_rmsnorm(xs, gm, 1e-5, rs), wg, wu)
+    yr = O.linear_lora(act, s["w_down"], las, lbs, 32.0, 16)
+    yr.backward(s["dy"])
+    tol_f, tol_b = (1.5e-2, 2.0 ** -5), (2e-2, 2.0 ** -4)     # the rank-16 side path is plain bf16 torch
+    close(y, yr, tol_f, "lora y")
+    close(x.grad, xs.grad, tol_b, "dx"); close(r.grad, rs.grad, tol_b, "dresidual")
+    close(norm.weight.grad, gm.grad, tol_b, "dgamma")
+    close(ff.swiglu.w_gate.grad, wg.grad, tol_b, "dw_gate"); close(ff.swiglu.w_up.grad, wu.grad, tol_b, "dw_up")
+    close(lo.lora_a.weight.grad, las.grad, tol_b, "dlora_a"); close(lo.lora_b.weight.grad, lbs.grad, tol_b, "dlora_b")
+    assert lo.linear.weight.grad is None
+
+
+# ----------------------------------------------------------------------------------------------- full size
+@pytest.mark.parametrize("hidden,inter", [(4096, 14336), (8192, 28672)])
+def test_full_size_prefill_subsets_and_properties(hidden, inter):
+    """BASELINE configs 2 / 5 (4 x 2048 tokens): the oracle checks a row subset (the FFN is row-independent) and
+    a column subset of the weight gradients; properties cover the rest."""
+    tokens = 8192
+    gen = torch.Generator(device=DEV).manual_seed(hidden)
+    rn = lambda *sh: torch.randn(*sh, device=DEV, generator=gen)
+    ru = lambda *sh: torch.rand(*sh, device=DEV, generator=gen) * 2 - 1
+    x, res, dy = rn(tokens, hidden).bfloat16(), rn(tokens, hidden).bfloat16(), rn(tokens, hidden).bfloat16()
+    wg, wu = (ru(inter, hidden) / hidden ** 0.5).bfloat16(), (ru(inter, hidden) / hidden ** 0.5).bfloat16()
+    wd = (ru(hidden, inter) / inter ** 0.5).bfloat16()
+    gamma = (1 + 0.1 * rn(hidden)).bfloat16()
+    normed, rms, h = ops.add_rmsnorm_forward(x, gamma, res, 1e-5, want_h=True)
+    y, gate, up = ops.ffn_forward(normed, wg, wu, wd, want_cache=True)
+    rows = torch.randperm(tokens, generator=torch.Generator().manual_seed(1))[:96].sort().values
+    c = lambda t: t.float().cpu()
+    close(normed[rows], O.add_rmsnorm(c(x[rows]), c(gamma), 1e-5, c(res[rows])), FWD, "normed rows")
+    nr = c(normed[rows])
+    ref = O.feedforward_grads(nr, c(wg), c(wu), c(wd), c(dy[rows]))
+    close(y[rows], ref["y"], FWD, "y rows")
+    dx, dwg, dwu, dwd, d_gate, d_up = ops.ffn_backward(dy, normed, wg, wu, wd, gate, up)
+    close(dx[rows], ref["dx"], BWD, "dx rows")
+    # weight-gradient column subset: dw_gate[cols, :] = d_gate[:, cols]^T normed  (full reduction over 8192 tokens)
+    cols = torch.arange(0, inter, inter // 24)[:24]
+    dgc = O.swiglu_grads_closed_form  # noqa: F841  (closed form documented in the oracle)
+    g_c, u_c = c(normed) @ c(wg[cols]).t(), c(normed) @ c(wu[cols]).t()
+    dact_c = c(dy) @ c(wd[:, cols])
+    sg = torch.sigmoid(g_c)
+    dg_c = dact_c * u_c * (sg * (1 + g_c * (1 - sg)))
+    du_c = dact_c * (g_c * sg)
+    close(dwg[cols], dg_c.t() @ c(normed), BWD, "dw_gate rows")
+    close(dwu[cols], du_c.t() @ c(normed), BWD, "dw_up rows")
+    close(dwd[:, cols], c(dy).t() @ (torch.nn.functional.silu(g_c) * u_c), BWD, "dw_down cols")
+    # properties: row independence (a permutation of tokens permutes the output) and determinism
+    perm = torch.randperm(tokens, device=DEV, generator=gen)
+    y_p, _, _ = ops.ffn_forward(normed[perm].contiguous(), wg, wu, wd)
+    assert torch.equal(y_p, y[perm]), "FFN rows must be independent of their position / tile"
+    y_again, _, _ = ops.ffn_forward(normed, wg, wu, wd)
+    assert torch.equal(y_again, y), "bitwise run-to-run determinism"
+    # weight gradients are additive over token chunks (checksum of checksums)
+    half = tokens // 2
+    _, a_g, _, a_d, _, _ = ops.ffn_backward(dy[:half], normed[:half], wg, wu, wd, gate[:half], up[:half], want_dx=False)
+    _, b_g, _, b_d, _, _ = ops.ffn_backward(dy[half:], normed[half:], wg, wu, wd, gate[half:], up[half:], want_dx=False)
+    close(a_g.float() + b_g.float(), dwg, (6e-3, 2.0 ** -6), "dw_gate additivity")
+    close(a_d.float() + b_d.float(), dwd, (6e-3, 2.0 ** -6), "dw_down additivity")
+    # RMSNorm backward at full size against the closed form on the row subset (+ dgamma via a 1024-row slice)
+    dxn, dgam = ops.rmsnorm_backward(dy, h, gamma, rms)
+    cdx, _ = O.add_rmsnorm_grads_closed_form(c(h[rows]), c(gamma), 1e-5, c(dy[rows]))
+    close(dxn[rows], cdx, BWD, "rmsnorm dx rows")
+    _, dgam_slice = ops.rmsnorm_backward(dy[:1024], h[:1024], gamma, rms[:1024])
+    _, cdw = O.add_rmsnorm_grads_closed_form(c(h[:1024]), c(gamma), 1e-5, c(dy[:1024]))
+    close(dgam_slice, cdw, BWD, "dgamma 1024 rows")
+    assert torch.isfinite(dgam.float()).all()
+
+
+@pytest.mark.parametrize("batch", [1, 2, 8, 33, 64])
+def test_decode_shapes_11b(batch):
+    """BASELINE config 3: KV-cached decode, x [B, 1, 4096]; whole-matrix check against the oracle."""
+    hidden, inter = 4096, 14336
+    gen = torch.Generator(device=DEV).manual_seed(batch)
+    x = torch.randn(batch, 1, hidden, device=DEV, generator=gen).bfloat16()
+    wg = ((torch.rand(inter, hidden, device=DEV, generator=gen) * 2 - 1) / 64).bfloat16()
+    wu = ((torch.rand(inter, hidden, device=DEV, generator=gen) * 2 - 1) / 64).bfloat16()
+    wd = ((torch.rand(hidden, inter, device=DEV, generator=gen) * 2 - 1) / 120).bfloat16()
+    y, _, _ = ops.ffn_forward(x, wg, wu, wd)
+    assert y.shape == (batch, 1, hidden)
+    ref = torch.nn.functional.linear(
+        torch.nn.functional.silu(x.float() @ wg.float().t()) * (x.float() @ wu.float().t()), wd.float())
+    close(y, ref, FWD, "decode y")   # fp32 on the device: same expression as the oracle (FusedSwiglu.py:18-20)
+    yo = O.feedforward(x[:1].float().cpu(), wg.float().cpu(), wu.float().cpu(), wd.float().cpu())
+    close(y[:1], yo, FWD, "decode y[0] vs CPU oracle")
+
+
+def test_reference_cuda_rmsnorm_ab():
+    """A/B against the one reference CUDA kernel that builds (oracle/_ref, fp16 only)."""
+    import glob
+    import importlib.util
+    import os
+    so = glob.glob(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "rmsnorm_ref*.so"))
+    if not so:
+        pytest.skip("oracle/_ref not built")
+    spec = importlib.util.spec_from_file_location("rmsnorm_ref", so[0])
+    ref_ext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_ext)
+    torch.manual_seed(0)
+    x = torch.randn(512, 4096, device=DEV).half()
+    r = torch.randn(512, 4096, device=DEV).half()
+    w = (1 + 0.1 * torch.randn(4096, device=DEV)).half()
+    out_ref, rms_ref = ref_ext.forward(x, w, r.clone(), 1e-5)
+    y, rms, _ = ops.add_rmsnorm_forward(x, w, r, 1e-5)
+    oracle = O.add_rmsnorm(x.float().cpu(), w.float().cpu(), 1e-5, r.float().cpu())
+    close(y, oracle, (2e-3, 2.0 ** -9), "ours vs oracle (fp16)")
+    close(out_ref, oracle, (4e-3, 2.0 ** -8), "reference kernel vs oracle (fp16, it rounds the add)")
+    close(y, out_ref, (4e-3, 2.0 ** -8), "ours vs reference kernel")
+    close(rms, rms_ref, (1e-3, 1e-3), "rms")
+    assert O.rel_l2(y.float().cpu(), oracle) <= O.rel_l2(out_ref.float().cpu(), oracle) * 1.05
