@@ -502,7 +502,7 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
 
     const int b_box_rows = (g.epilogue == EPI_SWIGLU) ? 128 : kAccCols / cta_group;
     for (int ph = 0; ph < g.num_phases; ++ph) {
-        if (g.k[ph] <= 0 || (g.k[ph] % 8) != 0) return L32_ERR_BAD_SHAPE;
+        if (g.k[ph] <= 0) return L32_ERR_BAD_SHAPE;   // any K: TMA zero-fills the ragged last k-block
         if (g.a[ph].mn_major != g.a[0].mn_major || g.b[ph].mn_major != g.b[0].mn_major) return L32_ERR_BAD_SHAPE;
         kp.k[ph] = g.k[ph];
         int rc;

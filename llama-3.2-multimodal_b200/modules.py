@@ -27,17 +27,28 @@ __all__ = [
 ]
 
 
+def _wants_grad(*tensors) -> bool:
+    """True when autograd will record this call.  Function.forward always runs with grad mode off and
+    ctx.needs_input_grad ignores an enclosing torch.no_grad(), so the decision is taken in `apply`."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 # ------------------------------------------------------------------------------------------------ RMSNorm
 class RMSNormFunction(torch.autograd.Function):
     """y = rmsnorm(x + residual) * weight on the sm_100a kernels (reference Model/model.py:135-155)."""
 
+    @classmethod
+    def apply(cls, x, weight, eps, residual=None):
+        if not _wants_grad(x, weight, residual):
+            # inference: 3 streams (x, residual, y) -- no h, no rms
+            return ops.add_rmsnorm_forward(x, weight, residual, eps, want_h=False, want_rms=False)[0]
+        return super().apply(x, weight, eps, residual)
+
     @staticmethod
     def forward(ctx, x, weight, eps, residual=None):
-        need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 3))
-        y, rms, h = ops.add_rmsnorm_forward(x, weight, residual, eps, want_h=need_grad, want_rms=need_grad)
-        if need_grad:
-            # without a residual the normalised input is x itself: nothing extra is written
-            ctx.save_for_backward(h if h is not None else x, weight, rms)
+        y, rms, h = ops.add_rmsnorm_forward(x, weight, residual, eps, want_h=True, want_rms=True)
+        # without a residual the normalised input is x itself: nothing extra is written
+        ctx.save_for_backward(h if h is not None else x, weight, rms)
         ctx.has_residual = residual is not None
         return y
 
@@ -82,6 +93,12 @@ class SwiGLUFunction(torch.autograd.Function):
     Differentiable on every path (the reference's fallback branch saved nothing and its CUDA backward was
     never defined); bias gradients are returned when biases exist.
     """
+
+    @classmethod
+    def apply(cls, x, w_gate, w_up, b_gate=None, b_up=None):
+        if ops.supported(x) and not _wants_grad(x, w_gate, w_up, b_gate, b_up):
+            return ops.swiglu_forward(x, w_gate, w_up, b_gate, b_up, want_cache=False)[0]
+        return super().apply(x, w_gate, w_up, b_gate, b_up)
 
     @staticmethod
     def forward(ctx, x, w_gate, w_up, b_gate=None, b_up=None):
@@ -149,6 +166,12 @@ class FusedSwiGLU(nn.Module):
 class LinearFunction(torch.autograd.Function):
     """y = a w^T + b on the tcgen05 GEMM; backward = two more GEMMs with MN-major operands (no transposes)."""
 
+    @classmethod
+    def apply(cls, a, weight, bias=None):
+        if not _wants_grad(a, weight, bias):
+            return ops.linear_forward(a, weight, bias)
+        return super().apply(a, weight, bias)
+
     @staticmethod
     def forward(ctx, a, weight, bias=None):
         ctx.save_for_backward(a, weight)
@@ -206,6 +229,12 @@ class Linear_LORA(nn.Module):
 class FFNFunction(torch.autograd.Function):
     """Whole feed-forward y = w_down(silu(x w_gate^T) * (x w_up^T)) with a hand-written backward:
     d_act GEMM whose epilogue recomputes SiLU' in registers, two-phase dX GEMM, three wgrad GEMMs."""
+
+    @classmethod
+    def apply(cls, x, w_gate, w_up, w_down, b_gate=None, b_up=None, b_down=None):
+        if not _wants_grad(x, w_gate, w_up, w_down, b_gate, b_up, b_down):
+            return ops.ffn_forward(x, w_gate, w_up, w_down, b_gate, b_up, b_down, want_cache=False)[0]
+        return super().apply(x, w_gate, w_up, w_down, b_gate, b_up, b_down)
 
     @staticmethod
     def forward(ctx, x, w_gate, w_up, w_down, b_gate=None, b_up=None, b_down=None):
