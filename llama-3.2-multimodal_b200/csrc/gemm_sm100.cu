@@ -25,6 +25,8 @@
 // (dgrad through W^T, wgrad through X^T) without any explicit transpose.
 #include "l32_internal.cuh"
 
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 namespace l32 {
@@ -493,6 +495,10 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
     kp.tiles_m = (g.m + tile_m - 1) / tile_m;
     kp.tiles_n = (g.n + tile_n_out - 1) / tile_n_out;
     kp.raster_group = g.raster_group > 0 ? g.raster_group : 16 / cta_group;
+    if (const char* env = getenv("L32_RASTER_GROUP")) {   // tuning knob for experiments only
+        const int v = atoi(env);
+        if (v > 0) kp.raster_group = v;
+    }
     kp.idesc = make_idesc_f16(g.dtype == L32_BF16, static_cast<uint32_t>(tile_m), kAccCols, g.a[0].mn_major != 0,
                               g.b[0].mn_major != 0);
     for (int i = 0; i < 3; ++i) kp.d[i] = g.d[i];

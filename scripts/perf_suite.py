@@ -1,0 +1,120 @@
+"""Timing suite for the GPU box: decode, training step, 90B shape, raster sweep (numbers for DESIGN.md)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from llama32_b200 import ops
+import llama32_b200 as L
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def weights(H, I, n=1):
+    dt = torch.bfloat16
+    out = []
+    for _ in range(n):
+        out.append(((torch.rand(I, H, device="cuda") * 2 - 1) / H ** 0.5).to(dt))
+        out.append(((torch.rand(I, H, device="cuda") * 2 - 1) / H ** 0.5).to(dt))
+        out.append(((torch.rand(H, I, device="cuda") * 2 - 1) / I ** 0.5).to(dt))
+    return out
+
+
+def decode(H, I, nsets=3):
+    # rotate weight sets so every step streams weights from HBM (3 x 352 MB > 126 MB L2)
+    ws = weights(H, I, nsets)
+    for B in (1, 4, 16, 64, 128):
+        x = torch.randn(B, 1, H, device="cuda").bfloat16()
+        state = {"i": 0}
+
+        def f():
+            i = state["i"] % nsets
+            state["i"] += 1
+            ops.ffn_forward(x, ws[3 * i], ws[3 * i + 1], ws[3 * i + 2])
+
+        def g():
+            i = state["i"] % nsets
+            state["i"] += 1
+            ops.swiglu_forward(x, ws[3 * i], ws[3 * i + 1])
+        t = timeit(f, iters=30)
+        tg = timeit(g, iters=30)
+        gb = 3.0 * H * I * 2 / 1e9
+        print(f"decode H={H} I={I} B={B}: ffn {t * 1e3:.1f} us ({gb / t * 1e3:.0f} GB/s)  gate/up {tg * 1e3:.1f} us "
+              f"({gb * 2 / 3 / tg * 1e3:.0f} GB/s)  down {(t - tg) * 1e3:.1f} us ({gb / 3 / (t - tg) * 1e3:.0f} GB/s)", flush=True)
+
+
+def train(H, I, T):
+    dt = torch.bfloat16
+    norm = L.LLAMARMSNorm(H, eps=1e-5).to("cuda", dt)
+    ffn = L.FusedFeedforward(H, I).to("cuda", dt)
+    x = torch.randn(T, H, device="cuda").to(dt)
+    r = torch.randn(T, H, device="cuda").to(dt)
+    dy = torch.randn(T, H, device="cuda").to(dt)
+
+    def step():
+        xx = x.detach().requires_grad_(True)
+        y = ffn(norm(xx, residual=r))
+        y.backward(dy)
+    t = timeit(step, iters=10)
+    fl = 18.0 * T * H * I
+    print(f"train H={H} I={I} T={T}: fwd+bwd {t:.3f} ms  {fl / t / 1e9:.0f} TF/s  {T / t * 1e3:.0f} tok/s", flush=True)
+    wg, wu, wd = ffn.swiglu.w_gate.detach(), ffn.swiglu.w_up.detach(), ffn.w_down.weight.detach()
+    xn = x
+    y, g, u = ops.ffn_forward(xn, wg, wu, wd, want_cache=True)
+    t_f = timeit(lambda: ops.ffn_forward(xn, wg, wu, wd, want_cache=True), iters=10)
+    t_b = timeit(lambda: ops.ffn_backward(dy, xn, wg, wu, wd, g, u), iters=10)
+    print(f"   ffn fwd(+caches) {t_f:.3f} ms ({6.0 * T * H * I / t_f / 1e9:.0f} TF/s)   ffn bwd {t_b:.3f} ms ({12.0 * T * H * I / t_b / 1e9:.0f} TF/s)")
+    # individual backward GEMMs
+    dg = torch.randn(T, I, device="cuda").to(dt)
+    t1 = timeit(lambda: ops.gemm(dy, wd, b_mn_major=True), iters=10)                      # d_act
+    t2 = timeit(lambda: ops.gemm(dg, wg, b_mn_major=True, a1=dg, b1=wu), iters=10)         # dx two-phase
+    t3 = timeit(lambda: ops.gemm(dg, xn, a_mn_major=True, b_mn_major=True), iters=10)      # wgrad
+    f2 = 2.0 * T * H * I
+    print(f"   d_act gemm {t1:.3f} ms ({f2 / t1 / 1e9:.0f} TF/s)  dx 2-phase {t2:.3f} ms ({2 * f2 / t2 / 1e9:.0f} TF/s)  wgrad {t3:.3f} ms ({f2 / t3 / 1e9:.0f} TF/s)")
+    hh = x
+    rms = torch.ones(T, device="cuda")
+    w = torch.ones(H, device="cuda", dtype=dt)
+    tb = timeit(lambda: ops.rmsnorm_backward(dy, hh, w, rms), iters=30)
+    tf = timeit(lambda: ops.add_rmsnorm_forward(x, w, r, 1e-5, want_h=True), iters=30)
+    tf3 = timeit(lambda: ops.add_rmsnorm_forward(x, w, r, 1e-5, want_h=False, want_rms=False), iters=30)
+    tf2 = timeit(lambda: ops.add_rmsnorm_forward(x, w, None, 1e-5, want_h=False, want_rms=False), iters=30)
+    b = T * H * 2
+    print(f"   rmsnorm fwd(no res) {tf2 * 1e3:.1f} us {2 * b / tf2 / 1e6:.0f} GB/s | add-rmsnorm fwd {tf3 * 1e3:.1f} us {3 * b / tf3 / 1e6:.0f} GB/s | "
+          f"+h {tf * 1e3:.1f} us {4 * b / tf / 1e6:.0f} GB/s | bwd {tb * 1e3:.1f} us {3 * b / tb / 1e6:.0f} GB/s")
+
+
+def prefill(H, I, T):
+    wg, wu, wd = weights(H, I)
+    x = torch.randn(T, H, device="cuda").bfloat16()
+    act = torch.randn(T, I, device="cuda").bfloat16()
+    for rg in (0, 2, 4, 8, 16, 32):
+        if rg:
+            os.environ["L32_RASTER_GROUP"] = str(rg)
+        else:
+            os.environ.pop("L32_RASTER_GROUP", None)
+        t1 = timeit(lambda: ops.swiglu_forward(x, wg, wu), iters=10)
+        t2 = timeit(lambda: ops.linear_forward(act, wd), iters=10)
+        print(f"prefill H={H} I={I} T={T} raster={rg or 'default'}: swiglu {t1:.3f} ms ({4.0 * T * H * I / t1 / 1e9:.0f} TF/s) "
+              f"down {t2:.3f} ms ({2.0 * T * H * I / t2 / 1e9:.0f} TF/s)", flush=True)
+    os.environ.pop("L32_RASTER_GROUP", None)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1]
+    if what == "decode":
+        decode(4096, 14336)
+        decode(8192, 28672, nsets=2)
+    elif what == "train":
+        train(4096, 14336, 8192)
+    elif what == "prefill":
+        prefill(4096, 14336, 8192)
+        prefill(8192, 28672, 8192)
