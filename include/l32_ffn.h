@@ -91,7 +91,7 @@ L32_API int l32_rmsnorm_backward(const void* dy, const void* h, const void* weig
  *   pre-activation gate / up projections, needed by l32_swiglu_backward).
  * One tcgen05 kernel: the gate/up accumulators live in TMEM and SiLU*mul is applied in the epilogue,
  * so gate and up never touch HBM unless the caches are requested.  tokens <= 128 takes the
- * weight-streaming small-M kernel (caches not available there -> falls through to the tiled kernel).
+ * weight-streaming small-M kernel (weights as the UMMA M operand, cluster split-K; same fused epilogue).
  */
 L32_API int l32_swiglu_forward(const void* x, const void* w_gate, const void* w_up, const void* b_gate,
                        const void* b_up, void* act, void* gate_cache, void* up_cache, int64_t tokens,

@@ -4,6 +4,7 @@
 #include "l32_internal.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 using namespace l32;
 
@@ -18,6 +19,14 @@ namespace {
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 inline bool dtype_ok(int dtype) { return dtype == L32_BF16 || dtype == L32_FP16; }
 inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+// Largest token count routed to the weight-streaming small-M kernels (ffn_decode.cu); above it the tiled
+// tcgen05 GEMM is used.  L32_DECODE_MAX_TOKENS overrides it for experiments (0 disables the small-M path).
+int decode_max_tokens() {
+    const char* v = getenv("L32_DECODE_MAX_TOKENS");
+    if (v != nullptr && *v != '\0') return atoi(v);
+    return 128;
+}
 
 GemmOperand op(const void* p, int64_t ld, int mn_major) {
     GemmOperand o;
@@ -126,8 +135,9 @@ int l32_swiglu_forward(const void* x, const void* w_gate, const void* w_up, cons
     if (tokens == 0) return L32_OK;
     if (x == nullptr || w_gate == nullptr || w_up == nullptr || act == nullptr) return L32_ERR_NULL;
     if ((gate_cache == nullptr) != (up_cache == nullptr)) return L32_ERR_NULL;
-    if (tokens <= 128 && gate_cache == nullptr && b_gate == nullptr && b_up == nullptr) {
-        const int rc = ffn_decode_swiglu(x, w_gate, w_up, act, static_cast<int>(tokens), hidden, inter, dtype, as_stream(stream));
+    if (tokens <= decode_max_tokens()) {
+        const int rc = ffn_decode_swiglu(x, w_gate, w_up, b_gate, b_up, act, gate_cache, up_cache, static_cast<int>(tokens),
+                                         hidden, inter, dtype, as_stream(stream));
         if (rc != L32_ERR_BAD_SHAPE) return rc;   // shape outside the small-M kernel's envelope: use the tiled kernel
     }
     GemmProblem g = blank(static_cast<int>(tokens), inter, dtype);
@@ -151,8 +161,9 @@ int l32_linear_forward(const void* a, const void* w, const void* bias, void* y, 
     if (!shapes_ok(tokens, in_features, out_features)) return L32_ERR_BAD_SHAPE;
     if (tokens == 0) return L32_OK;
     if (a == nullptr || w == nullptr || y == nullptr) return L32_ERR_NULL;
-    if (tokens <= 128 && bias == nullptr) {
-        const int rc = ffn_decode_linear(a, w, y, static_cast<int>(tokens), in_features, out_features, dtype, as_stream(stream));
+    if (tokens <= decode_max_tokens()) {
+        const int rc = ffn_decode_linear(a, w, bias, y, static_cast<int>(tokens), in_features, out_features, dtype,
+                                         as_stream(stream));
         if (rc != L32_ERR_BAD_SHAPE) return rc;
     }
     GemmProblem g = blank(static_cast<int>(tokens), out_features, dtype);

@@ -1,12 +1,451 @@
-// K5: weight-streaming small-M (KV-cached decode) FFN kernels.  Under construction: until the kernel lands the
-// entry points report "outside envelope" so the C-ABI uses the tiled tcgen05 kernel for every token count.
+// K5: weight-streaming small-M (KV-cached decode) feed-forward kernels for sm_100a.
+//
+// For tokens <= 128 the feed-forward is HBM-bound: every step has to stream 3*H*I 16-bit weights (352 MB at the
+// 11B shape) while the activations are a few hundred KB.  Replaces, for that regime, the reference's scalar
+// kernels swiglu_forward_kernel / swiglu_down_forward_kernel (reference Tools/swiglu/swiglu.cu:58-100, :228-272)
+// and the two F.linear + F.silu calls of the live path (reference Tools/swiglu/FusedSwiglu.py:18-20,
+// Model/model.py:217).
+//
+// Design ("swap-AB" on tcgen05): the WEIGHT rows are the UMMA M operand (128 rows per CTA), the tokens are the
+// UMMA N operand (padded to 16/32/64/128), the accumulator D[weight row, token] lives in TMEM.
+//   * one CTA = one block of 128 weight rows x one K split; a cluster of `splits` CTAs shares a row block and
+//     reduces its fp32 partials through distributed shared memory (no atomics, no workspace, deterministic);
+//   * the host sizes the grid so that ALL CTAs are co-resident (2-4 per SM): equal work per CTA and a fair
+//     share of HBM bandwidth means no wave-quantisation tail although 224 or 256 units never divide by 148 SMs;
+//   * warp 0 streams weight tiles (TMA, evict-first) and activation tiles (TMA, evict-last) through a deep
+//     shared-memory ring, warp 1 issues tcgen05.mma, all four warps run the epilogue;
+//   * gate and up rows of the same 64 act columns sit in one 128-row A tile (two 64-row TMA boxes), so
+//     SiLU(g)*u is applied on chip and gate / up never exist in HBM;
+//   * programmatic dependent launch: the kernel prefetches its first weight stages BEFORE waiting for the
+//     previous kernel of the stream (weights never depend on it), so the down projection starts pulling HBM
+//     while the gate/up kernel drains, and the gate/up kernel while the Add-RMSNorm drains.
 #include "l32_internal.cuh"
 
-namespace l32 {
+#include <cstdlib>
+#include <cstring>
 
-int ffn_decode_swiglu(const void*, const void*, const void*, void*, int, int, int, int, cudaStream_t) {
-    return L32_ERR_BAD_SHAPE;
+namespace l32 {
+namespace {
+
+constexpr int kBlockK = 64;                 // one 128-byte swizzle atom of 16-bit elements
+constexpr int kUmmaK = 16;
+constexpr int kRowsA = 128;                 // UMMA M: weight rows per CTA
+constexpr int kThreads = 128;
+constexpr int kABytes = kRowsA * kBlockK * 2;   // 16 KiB weight tile per stage
+constexpr int kMaxStages = 12;
+constexpr int kBarrierBytes = (2 * kMaxStages + 1) * 8 + 16;
+
+enum : int { DEC_LINEAR = 0, DEC_SWIGLU = 1 };
+
+struct DecodeParams {
+    CUtensorMap map_w[2];   // weight matrices [rows, K]: [0] = gate (or the only matrix), [1] = up
+    CUtensorMap map_x;      // activations [tokens, K]
+    void* out;              // [tokens, rows_out]
+    const void* bias[2];    // optional per-output-row bias ([0] gate / linear, [1] up)
+    void* cache[2];         // SwiGLU only, optional: pre-activation gate / up projections [tokens, rows_out]
+    int tokens, n_pad;      // n_pad = UMMA N in {16, 32, 64, 128}
+    int rows_out;           // inter (SwiGLU) or out_features (linear)
+    int k;                  // reduction length
+    int splits;             // K splits = cluster size
+    int stages;             // shared-memory ring depth
+    int rotate;             // 1: every row block starts its K loop at a different k-block (spreads the L2 reads of
+                            // the shared activation tiles over time instead of all CTAs hitting the same lines)
+    long long ldo;          // row pitch of out, elements
+    uint32_t idesc;
+    uint32_t tmem_cols;
+};
+
+L32_DEVICE float ld_dsmem_f32(uint32_t local_addr, uint32_t cta_rank) {
+    float v;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %1, %2;\n\t"
+        "ld.shared::cluster.f32 %0, [ra];\n\t"
+        "}\n"
+        : "=f"(v)
+        : "r"(local_addr), "r"(cta_rank)
+        : "memory");
+    return v;
 }
-int ffn_decode_linear(const void*, const void*, void*, int, int, int, int, cudaStream_t) { return L32_ERR_BAD_SHAPE; }
+
+template <int kEpi, typename T>
+__global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_constant__ DecodeParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int stages = p.stages;
+    const uint32_t b_bytes = static_cast<uint32_t>(p.n_pad) * 128u;
+    const uint32_t stage_bytes = kABytes + b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const uint32_t lane = lane_id();
+    const int split = static_cast<int>(cluster_ctarank());
+    const int row_block = blockIdx.x / p.splits;
+
+    // this CTA's slice of the reduction
+    const int nkb = (p.k + kBlockK - 1) / kBlockK;
+    const int kb_base = nkb / p.splits, kb_rem = nkb % p.splits;
+    const int kb0 = split * kb_base + min(split, kb_rem);
+    const int cnt = kb_base + (split < kb_rem ? 1 : 0);
+    const int rot = (p.rotate && cnt > 0) ? static_cast<int>((static_cast<uint32_t>(row_block) * 40503u) % static_cast<uint32_t>(cnt)) : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.map_w[0]);
+        if constexpr (kEpi == DEC_SWIGLU) tma_prefetch_desc(&p.map_w[1]);
+        tma_prefetch_desc(&p.map_x);
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tfull_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc<1>(tmem_slot, p.tmem_cols);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    // Let the next kernel of the stream get scheduled as soon as SM resources free up; it orders itself
+    // behind this grid with griddepcontrol.wait.
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- TMA producer
+            auto load_w = [&](int kb) {
+                const int s = kb % stages;
+                uint8_t* sa = smem + s * stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                int kr = kb + rot;
+                if (kr >= cnt) kr -= cnt;
+                const int kcol = (kb0 + kr) * kBlockK;
+                if constexpr (kEpi == DEC_SWIGLU) {
+                    tma_load_2d(sa, &p.map_w[0], &full_bar[s], kcol, row_block * 64, kEvictFirst);
+                    tma_load_2d(sa + kABytes / 2, &p.map_w[1], &full_bar[s], kcol, row_block * 64, kEvictFirst);
+                } else {
+                    tma_load_2d(sa, &p.map_w[0], &full_bar[s], kcol, row_block * kRowsA, kEvictFirst);
+                }
+            };
+            auto load_x = [&](int kb) {
+                const int s = kb % stages;
+                int kr = kb + rot;
+                if (kr >= cnt) kr -= cnt;
+                tma_load_2d(smem + s * stage_bytes + kABytes, &p.map_x, &full_bar[s], (kb0 + kr) * kBlockK, 0, kEvictLast);
+            };
+            const int pre = min(stages, cnt);
+            for (int kb = 0; kb < pre; ++kb) load_w(kb);        // weights do not depend on the previous kernel
+            pdl_wait_prior_grid();                              // activations do
+            for (int kb = 0; kb < cnt; ++kb) {
+                if (kb >= pre) {
+                    mbar_wait(&empty_bar[kb % stages], ((kb / stages) & 1u) ^ 1u);
+                    load_w(kb);
+                }
+                load_x(kb);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- MMA issuer
+            uint32_t accumulate = 0;
+            for (int kb = 0; kb < cnt; ++kb) {
+                const int s = kb % stages;
+                mbar_wait(&full_bar[s], (kb / stages) & 1u);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                    const uint64_t adesc = make_smem_desc_sw128(a_addr + k * kUmmaK * 2, 0, 1024);
+                    const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * kUmmaK * 2, 0, 1024);
+                    umma_f16<1>(tmem_base, adesc, bdesc, p.idesc, accumulate);
+                    accumulate = 1;
+                }
+                umma_commit<1>(&empty_bar[s]);
+            }
+            umma_commit<1>(tfull_bar);
+        }
+    }
+    __syncwarp();
+
+    // -------------------------------------------------------------------- epilogue (all four warps)
+    // TMEM lane = weight row of this block, TMEM column = token.  Shared memory is reused as exchange space (the
+    // ring is idle: every TMA load has landed and every MMA that read it has retired once tfull fires).
+    pdl_wait_prior_grid();   // `out` may still be read by the previous kernel of the stream
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    float* part = reinterpret_cast<float*>(smem);
+    const int row = static_cast<int>(warp * 32 + lane);
+    const uint32_t taddr = tmem_base + ((warp * 32u) << 16);
+    const int nchunks = (p.tokens + 15) >> 4;
+    T* out = static_cast<T*>(p.out);
+
+    if (p.splits == 1) {
+        // ---- fast path: the whole reduction ran in this CTA
+        if constexpr (kEpi == DEC_SWIGLU) {
+            // lanes 0-63 hold gate rows, lanes 64-127 the up rows of the same 64 act columns.  Token chunks of 16
+            // alternate between the two halves: the gate warps finish the even chunks (up values through shared
+            // memory), the up warps the odd ones (gate values through shared memory).
+            const bool is_gate = warp < 2;
+            const int r = row & 63;
+            const int col = row_block * 64 + r;
+            const bool col_ok = col < p.rows_out;
+            float bg = 0.f, bu = 0.f;
+            if (col_ok) {
+                if (p.bias[0] != nullptr) bg = static_cast<float>(static_cast<const T*>(p.bias[0])[col]);
+                if (p.bias[1] != nullptr) bu = static_cast<float>(static_cast<const T*>(p.bias[1])[col]);
+            }
+            for (int c = is_gate ? 1 : 0; c < nchunks; c += 2) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(taddr + c * 16, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) part[(c * 16 + j) * 64 + r] = __uint_as_float(v[j]);
+            }
+            __syncthreads();
+            for (int c = is_gate ? 0 : 1; c < nchunks; c += 2) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(taddr + c * 16, v);
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = part[(c * 16 + j) * 64 + r];
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float mine = __uint_as_float(v[j]);
+                    const float g = (is_gate ? mine : o[j]) + bg;
+                    const float u = (is_gate ? o[j] : mine) + bu;
+                    const int n = c * 16 + j;
+                    if (col_ok && n < p.tokens) {
+                        const size_t o_idx = static_cast<size_t>(n) * p.ldo + col;
+                        out[o_idx] = static_cast<T>(silu_f32(g) * u);
+                        if (p.cache[0] != nullptr) {
+                            static_cast<T*>(p.cache[0])[o_idx] = static_cast<T>(g);
+                            static_cast<T*>(p.cache[1])[o_idx] = static_cast<T>(u);
+                        }
+                    }
+                }
+            }
+        } else {
+            const int col = row_block * kRowsA + row;
+            const bool col_ok = col < p.rows_out;
+            float b = 0.f;
+            if (col_ok && p.bias[0] != nullptr) b = static_cast<float>(static_cast<const T*>(p.bias[0])[col]);
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(taddr + c * 16, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = c * 16 + j;
+                    if (col_ok && n < p.tokens) out[static_cast<size_t>(n) * p.ldo + col] = static_cast<T>(__uint_as_float(v[j]) + b);
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 1) {
+            tc_fence_after();
+            tmem_dealloc<1>(tmem_base, p.tmem_cols);
+        }
+        return;
+    }
+
+    // ---- split-K path: park the fp32 partial as part[token][row], reduce across the cluster through DSMEM
+    if (cnt > 0) {
+        for (int c = 0; c < nchunks; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(taddr + c * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) part[(c * 16 + j) * kRowsA + row] = __uint_as_float(v[j]);
+        }
+    } else {
+        for (int n = 0; n < nchunks * 16; ++n) part[n * kRowsA + row] = 0.f;
+    }
+    tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();   // partials of every split visible cluster-wide
+
+    // each CTA of the cluster finishes a slice of the tokens: sum the splits (fixed order), fused epilogue, store
+    const int per = (p.tokens + p.splits - 1) / p.splits;
+    const int n_lo = split * per;
+    const int n_hi = min(p.tokens, n_lo + per);
+    const uint32_t part_addr = smem_u32(part);
+    auto sum_splits = [&](uint32_t addr) {
+        float v[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) v[s] = (s < p.splits) ? ld_dsmem_f32(addr, s) : 0.f;
+        return ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    };
+    if constexpr (kEpi == DEC_SWIGLU) {
+        const int r = row & 63;
+        const int col = row_block * 64 + r;
+        const bool col_ok = col < p.rows_out;
+        float bg = 0.f, bu = 0.f;
+        if (col_ok) {
+            if (p.bias[0] != nullptr) bg = static_cast<float>(static_cast<const T*>(p.bias[0])[col]);
+            if (p.bias[1] != nullptr) bu = static_cast<float>(static_cast<const T*>(p.bias[1])[col]);
+        }
+        for (int n = n_lo + (row >> 6); n < n_hi; n += 2) {
+            const float g = sum_splits(part_addr + (n * kRowsA + r) * 4) + bg;
+            const float u = sum_splits(part_addr + (n * kRowsA + 64 + r) * 4) + bu;
+            if (col_ok) {
+                const size_t o_idx = static_cast<size_t>(n) * p.ldo + col;
+                out[o_idx] = static_cast<T>(silu_f32(g) * u);
+                if (p.cache[0] != nullptr) {
+                    static_cast<T*>(p.cache[0])[o_idx] = static_cast<T>(g);
+                    static_cast<T*>(p.cache[1])[o_idx] = static_cast<T>(u);
+                }
+            }
+        }
+    } else {
+        const int col = row_block * kRowsA + row;
+        const bool col_ok = col < p.rows_out;
+        float b = 0.f;
+        if (col_ok && p.bias[0] != nullptr) b = static_cast<float>(static_cast<const T*>(p.bias[0])[col]);
+        int n = n_lo;
+        for (; n + 2 <= n_hi; n += 2) {
+            const float a0 = sum_splits(part_addr + (n * kRowsA + row) * 4);
+            const float a1 = sum_splits(part_addr + ((n + 1) * kRowsA + row) * 4);
+            if (col_ok) {
+                out[static_cast<size_t>(n) * p.ldo + col] = static_cast<T>(a0 + b);
+                out[static_cast<size_t>(n + 1) * p.ldo + col] = static_cast<T>(a1 + b);
+            }
+        }
+        if (n < n_hi) {
+            const float a0 = sum_splits(part_addr + (n * kRowsA + row) * 4);
+            if (col_ok) out[static_cast<size_t>(n) * p.ldo + col] = static_cast<T>(a0 + b);
+        }
+    }
+    __syncwarp();
+    cluster_sync_all();   // nobody leaves while a peer may still read its partial
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, p.tmem_cols);
+    }
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    if (v == nullptr || *v == '\0') return dflt;
+    return atoi(v);
+}
+
+template <int kEpi, typename T>
+int launch_decode(const DecodeParams& p, int grid, size_t smem_bytes, cudaStream_t s) {
+    auto* kernel = ffn_decode_kernel<kEpi, T>;
+    static size_t configured = 0;   // per instantiation: largest dynamic smem opted into so far
+    if (smem_bytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        configured = 227 * 1024;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(p.splits);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = env_int("L32_DECODE_PDL", 1) ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    if (e == cudaSuccess) count_launch();
+    return static_cast<int>(e);
+}
+
+// Common host path.  rows_per_block = output rows one CTA produces (64 for SwiGLU: 64 gate + 64 up weight rows).
+template <int kEpi>
+int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0, const void* bias1, void* out, void* cache0,
+                void* cache1, int tokens, int k, int rows_out, int dtype, cudaStream_t s) {
+    if (tokens <= 0 || tokens > 128 || k <= 0 || rows_out <= 0) return L32_ERR_BAD_SHAPE;
+    if ((k % 8) != 0 || (rows_out % 8) != 0) return L32_ERR_BAD_SHAPE;
+    if (!is_aligned16(x) || !is_aligned16(w0) || (w1 != nullptr && !is_aligned16(w1))) return L32_ERR_BAD_ALIGN;
+    constexpr int rows_per_block = (kEpi == DEC_SWIGLU) ? 64 : kRowsA;
+
+    DecodeParams p;
+    memset(&p, 0, sizeof(p));
+    p.tokens = tokens;
+    p.n_pad = tokens <= 16 ? 16 : tokens <= 32 ? 32 : tokens <= 64 ? 64 : 128;
+    p.rows_out = rows_out;
+    p.k = k;
+    p.ldo = rows_out;
+    p.out = out;
+    p.bias[0] = bias0;
+    p.bias[1] = bias1;
+    p.cache[0] = cache0;
+    p.cache[1] = cache1;
+    p.idesc = make_idesc_f16(dtype == L32_BF16, kRowsA, static_cast<uint32_t>(p.n_pad), false, false);
+    p.tmem_cols = p.n_pad < 32 ? 32u : static_cast<uint32_t>(p.n_pad);
+
+    const int row_blocks = (rows_out + rows_per_block - 1) / rows_per_block;
+    const int nkb = (k + kBlockK - 1) / kBlockK;
+    const int sms = num_sms();
+    // K splits (cluster size): enough CTAs to keep every SM streaming, each with at least 4 k-blocks.
+    int splits = 1;
+    while (splits < 8 && row_blocks * splits < sms && nkb / (splits * 2) >= 4) splits *= 2;
+    if (const int v = env_int("L32_DECODE_SPLITS", 0)) splits = v;
+    if (splits < 1 || splits > 8 || (splits & (splits - 1)) != 0 || splits > nkb) return L32_ERR_BAD_SHAPE;
+    p.splits = splits;
+    p.rotate = env_int("L32_DECODE_ROTATE", 1);
+    const int grid = row_blocks * splits;
+
+    // Ring depth: all CTAs co-resident (up to 4 per SM), shared memory split evenly between them.
+    int per_sm = (grid + sms - 1) / sms;
+    if (per_sm > 4) per_sm = 4;
+    if (const int v = env_int("L32_DECODE_CTAS_PER_SM", 0)) per_sm = v;
+    const int stage_bytes = kABytes + p.n_pad * 128;
+    const int budget = (228 * 1024) / per_sm - 1024 /* driver-reserved */ - 1024 /* alignment slack */ - kBarrierBytes;
+    int stages = budget / stage_bytes;
+    const int kb_per_cta = (nkb + splits - 1) / splits;
+    if (stages > kb_per_cta) stages = kb_per_cta;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) stages = 2;
+    if (const int v = env_int("L32_DECODE_STAGES", 0)) stages = v < kMaxStages ? v : kMaxStages;
+    // the fp32 partial [n_pad][128] of the epilogue reuses the ring
+    while (stages * stage_bytes < p.n_pad * kRowsA * 4) ++stages;
+    if (stages < 1 || stages > kMaxStages) return L32_ERR_BAD_SHAPE;
+    p.stages = stages;
+    const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + kBarrierBytes + 1024;
+    if (smem_bytes > 227 * 1024) return L32_ERR_BAD_SHAPE;
+
+    int rc = make_tensor_map_2d(&p.map_x, x, static_cast<uint64_t>(tokens), static_cast<uint64_t>(k), static_cast<uint64_t>(k),
+                                static_cast<uint32_t>(p.n_pad), kBlockK, dtype);
+    if (rc != L32_OK) return rc;
+    rc = make_tensor_map_2d(&p.map_w[0], w0, static_cast<uint64_t>(rows_out), static_cast<uint64_t>(k), static_cast<uint64_t>(k),
+                            rows_per_block, kBlockK, dtype);
+    if (rc != L32_OK) return rc;
+    if constexpr (kEpi == DEC_SWIGLU) {
+        rc = make_tensor_map_2d(&p.map_w[1], w1, static_cast<uint64_t>(rows_out), static_cast<uint64_t>(k),
+                                static_cast<uint64_t>(k), rows_per_block, kBlockK, dtype);
+        if (rc != L32_OK) return rc;
+    }
+    if (dtype == L32_BF16) return launch_decode<kEpi, __nv_bfloat16>(p, grid, smem_bytes, s);
+    return launch_decode<kEpi, __half>(p, grid, smem_bytes, s);
+}
+
+}  // namespace
+
+int ffn_decode_swiglu(const void* x, const void* w_gate, const void* w_up, const void* b_gate, const void* b_up, void* act,
+                      void* gate_cache, void* up_cache, int tokens, int hidden, int inter, int dtype, cudaStream_t s) {
+    return decode_gemm<DEC_SWIGLU>(x, w_gate, w_up, b_gate, b_up, act, gate_cache, up_cache, tokens, hidden, inter, dtype, s);
+}
+
+int ffn_decode_linear(const void* a, const void* w, const void* bias, void* y, int tokens, int in_features,
+                      int out_features, int dtype, cudaStream_t s) {
+    return decode_gemm<DEC_LINEAR>(a, w, nullptr, bias, nullptr, y, nullptr, nullptr, tokens, in_features, out_features, dtype, s);
+}
 
 }  // namespace l32

@@ -60,10 +60,11 @@ cudaError_t swiglu_bwd_elementwise(const void* d_act, const void* gate, const vo
 cudaError_t swiglu_act_elementwise(const void* gate, const void* up, void* act, int64_t n, int dtype, cudaStream_t s);
 
 // ---- ffn_decode.cu : weight-streaming small-M FFN (tokens <= 128)
-int ffn_decode_swiglu(const void* x, const void* w_gate, const void* w_up, void* act, int tokens, int hidden, int inter,
-                      int dtype, cudaStream_t s);
-int ffn_decode_linear(const void* a, const void* w, void* y, int tokens, int in_features, int out_features, int dtype,
-                      cudaStream_t s);
+//      return L32_ERR_BAD_SHAPE when the problem is outside the kernel's envelope (the caller then uses the tiled GEMM)
+int ffn_decode_swiglu(const void* x, const void* w_gate, const void* w_up, const void* b_gate, const void* b_up, void* act,
+                      void* gate_cache, void* up_cache, int tokens, int hidden, int inter, int dtype, cudaStream_t s);
+int ffn_decode_linear(const void* a, const void* w, const void* bias, void* y, int tokens, int in_features,
+                      int out_features, int dtype, cudaStream_t s);
 
 // ---- tensor-map helper (gemm_sm100.cu): 2-D row-major [rows, cols] 16-bit tensor, 128-byte swizzled box
 int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,

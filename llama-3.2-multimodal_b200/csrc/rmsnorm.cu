@@ -82,6 +82,15 @@ __global__ void __launch_bounds__(RT) add_rmsnorm_fwd_kernel(
     const size_t base = static_cast<size_t>(row) * C;
 
     uint4 xv[VPT], rv[VPT], wv[VPT];
+    // Programmatic dependent launch: the next kernel of the stream may be scheduled now (it orders itself with
+    // griddepcontrol.wait); the weight does not depend on the previous kernel, x / residual do.
+    pdl_launch_dependents();
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int v = tid + i * RT;
+        if (v < nvec) wv[i] = __ldg(reinterpret_cast<const uint4*>(weight) + v);
+    }
+    pdl_wait_prior_grid();
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
         const int v = tid + i * RT;
@@ -94,11 +103,6 @@ __global__ void __launch_bounds__(RT) add_rmsnorm_fwd_kernel(
             // h_out may alias residual (raw reference ABI updates residual in place): coherent load.
             if (v < nvec) rv[i] = ld_v4(residual + base + (size_t)v * 8);
         }
-    }
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-        const int v = tid + i * RT;
-        if (v < nvec) wv[i] = __ldg(reinterpret_cast<const uint4*>(weight) + v);
     }
 
     float h[VPT][8];
@@ -169,122 +173,195 @@ __global__ void __launch_bounds__(256) add_rmsnorm_fwd_generic_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// Backward, fast path: C % 8 == 0, C <= RT * VPT * 8. CTA = 512 threads = (512/RT) row groups.
+// Backward, fast path: C % 8 == 0, C <= RT * VPT * 8.  Persistent, one CTA per SM.
 //   rstd = 1/rms; xhat = h*rstd; wdy = dy*w; c1 = mean(xhat*wdy)
 //   dx = (wdy - xhat*c1) * rstd;   dw[c] = sum_rows dy*xhat
 // (same algebra as reference rmsnorm.cuh:124-152 with inp := h, minus its extra 1e-6 and atomics)
+//
+// HBM-bound (3*C*2 B per row).  A producer warp streams whole rows of dy and h into a shared-memory ring with
+// 1-D bulk copies (cp.async.bulk, mbarrier completion), so up to ~190 KB of loads per SM are in flight
+// independently of the register file.  512 consumer threads form G = 512/RT row groups that work on alternate
+// ring stages; the row reduction is one shuffle tree + one named barrier per row.  d_weight is accumulated in
+// registers over all rows of the CTA and leaves as ONE fp32 partial row per CTA (deterministic, no atomics).
 // ------------------------------------------------------------------------------------------------
+constexpr int kBwdConsumers = 512;
+constexpr int kBwdThreads = kBwdConsumers + 32;
+constexpr int kBwdMaxStages = 12;
+constexpr int kBwdBarrierBytes = 2 * kBwdMaxStages * 8;
+constexpr int kBwdRedBytes = 2 * 16 * 16 * 4;   // [parity][group][warp of the group]
+
+L32_DEVICE void bulk_load_row(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(kEvictFirst)
+        : "memory");
+}
+L32_DEVICE uint4 lds_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
+    return r;
+}
+
 template <typename T, int RT, int VPT>
-__global__ void __launch_bounds__(512) rmsnorm_bwd_kernel(
+__global__ void __launch_bounds__(kBwdThreads, 1) rmsnorm_bwd_kernel(
     const T* __restrict__ dy, const T* __restrict__ h, const T* __restrict__ weight, const float* __restrict__ rms,
-    T* __restrict__ dx, float* __restrict__ dw_partial, int64_t rows, int C) {
-    constexpr int G = 512 / RT;
-    __shared__ float red[G][16];
-    extern __shared__ float dw_smem[];   // [G-1][C] when G > 1
+    T* __restrict__ dx, float* __restrict__ dw_partial, int64_t rows, int C, int stages) {
+    constexpr int G = kBwdConsumers / RT;
+    extern __shared__ __align__(128) uint8_t bwd_smem[];
+    const uint32_t row_bytes = static_cast<uint32_t>(C) * sizeof(T);
+    const uint32_t stage_bytes = 2 * row_bytes;
+    uint8_t* ring = bwd_smem;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(stages) * stage_bytes);
+    uint64_t* empty_bar = full_bar + kBwdMaxStages;
+    float* red = reinterpret_cast<float*>(empty_bar + kBwdMaxStages);
+
     const int tid = threadIdx.x;
+    const int nvec = C >> 3;
+    const int64_t n_local = rows > blockIdx.x ? (rows - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid == 0) {
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(&full_bar[i], 1);          // the producer's arrive.expect_tx
+            mbar_init(&empty_bar[i], RT / 32);   // one arrival per consumer warp of the owning row group
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_launch_dependents();   // the d_weight column reduce may be scheduled; it waits for this grid to finish
+
+    if (tid >= kBwdConsumers) {
+        // ------------------------------------------------------------------ producer warp
+        if (tid == kBwdConsumers) {
+            for (int64_t i = 0; i < n_local; ++i) {
+                const int s = static_cast<int>(i % stages);
+                const uint32_t use = static_cast<uint32_t>(i / stages);
+                if (use > 0) mbar_wait(&empty_bar[s], (use & 1u) ^ 1u);
+                const size_t base = static_cast<size_t>(i * gridDim.x + blockIdx.x) * C;
+                uint8_t* dst = ring + static_cast<size_t>(s) * stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+                bulk_load_row(dst, dy + base, row_bytes, &full_bar[s]);
+                bulk_load_row(dst + row_bytes, h + base, row_bytes, &full_bar[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
     const int g = tid / RT;
     const int t = tid % RT;
-    const int nvec = C >> 3;
-
-    float w[VPT][8], dwacc[VPT][8];
+    uint4 wv[VPT];
+    float dwacc[VPT][8];
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
         const int v = t + i * RT;
-        if (v < nvec) {
-            uint4 wv = __ldg(reinterpret_cast<const uint4*>(weight) + v);
-            unpack8<T>(wv, w[i]);
-        }
+        wv[i] = make_uint4(0, 0, 0, 0);
+        if (v < nvec) wv[i] = __ldg(reinterpret_cast<const uint4*>(weight) + v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) dwacc[i][j] = 0.f;
     }
-
     const float invC = 1.0f / static_cast<float>(C);
-    // Uniform trip count per CTA so the group barriers inside group_sum stay convergent.
-    const int64_t rows_per_iter = static_cast<int64_t>(gridDim.x) * G;
-    const int64_t iters = (rows + rows_per_iter - 1) / rows_per_iter;
-    for (int64_t it = 0; it < iters; ++it) {
-        const int64_t row = it * rows_per_iter + static_cast<int64_t>(blockIdx.x) * G + g;
-        const bool active = row < rows;
-        const size_t base = static_cast<size_t>(active ? row : 0) * C;
+    float rms_next = (g < n_local) ? rms[static_cast<int64_t>(g) * gridDim.x + blockIdx.x] : 1.f;
+
+    for (int64_t i = g; i < n_local; i += G) {
+        const int s = static_cast<int>(i % stages);
+        const uint32_t use = static_cast<uint32_t>(i / stages);
+        const int64_t row = i * gridDim.x + blockIdx.x;
+        const float rstd = 1.0f / rms_next;
+        if (i + G < n_local) rms_next = rms[(i + G) * gridDim.x + blockIdx.x];   // prefetch for the next turn
+        mbar_wait(&full_bar[s], use & 1u);
+        const uint8_t* src = ring + static_cast<size_t>(s) * stage_bytes;
         uint4 gv[VPT], hv[VPT];
 #pragma unroll
-        for (int i = 0; i < VPT; ++i) {
-            const int v = t + i * RT;
-            if (active && v < nvec) {
-                gv[i] = ld_stream_v4(dy + base + (size_t)v * 8);
-                hv[i] = ld_stream_v4(h + base + (size_t)v * 8);
+        for (int k = 0; k < VPT; ++k) {
+            const int v = t + k * RT;
+            if (v < nvec) {
+                gv[k] = lds_v4(src + static_cast<size_t>(v) * 16);
+                hv[k] = lds_v4(src + row_bytes + static_cast<size_t>(v) * 16);
             }
         }
-        const float rstd = active ? 1.0f / rms[row] : 0.f;
-        float wdy[VPT][8], xh[VPT][8];
+        __syncwarp();
+        if ((t & 31) == 0) mbar_arrive(&empty_bar[s]);   // stage may be refilled
+
         float dot = 0.f;
 #pragma unroll
-        for (int i = 0; i < VPT; ++i) {
-            const int v = t + i * RT;
-            if (active && v < nvec) {
-                float gg[8], hh[8];
-                unpack8<T>(gv[i], gg);
-                unpack8<T>(hv[i], hh);
+        for (int k = 0; k < VPT; ++k) {
+            const int v = t + k * RT;
+            if (v < nvec) {
+                float gg[8], hh[8], w[8];
+                unpack8<T>(gv[k], gg);
+                unpack8<T>(hv[k], hh);
+                unpack8<T>(wv[k], w);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    xh[i][j] = hh[j] * rstd;
-                    wdy[i][j] = gg[j] * w[i][j];
-                    dot = fmaf(xh[i][j], wdy[i][j], dot);
-                    dwacc[i][j] = fmaf(gg[j], xh[i][j], dwacc[i][j]);
+                    const float xh = hh[j] * rstd;
+                    dot = fmaf(xh, gg[j] * w[j], dot);
+                    dwacc[k][j] = fmaf(gg[j], xh, dwacc[k][j]);
                 }
             }
         }
-        dot = group_sum<RT>(dot, red[g], t, 1 + g);
+        dot = warp_sum(dot);
+        if constexpr (RT > 32) {
+            float* slot = red + ((static_cast<int>(i / G) & 1) * 16 + g) * 16;   // double-buffered: one barrier per row
+            if ((t & 31) == 0) slot[t >> 5] = dot;
+            named_bar_sync(1 + g, RT);
+            dot = 0.f;
+#pragma unroll
+            for (int k = 0; k < RT / 32; ++k) dot += slot[k];
+        }
         const float c1 = dot * invC;
+        const size_t base = static_cast<size_t>(row) * C;
 #pragma unroll
-        for (int i = 0; i < VPT; ++i) {
-            const int v = t + i * RT;
-            if (active && v < nvec) {
-                float o[8];
+        for (int k = 0; k < VPT; ++k) {
+            const int v = t + k * RT;
+            if (v < nvec) {
+                float gg[8], hh[8], w[8], o[8];
+                unpack8<T>(gv[k], gg);
+                unpack8<T>(hv[k], hh);
+                unpack8<T>(wv[k], w);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = (wdy[i][j] - xh[i][j] * c1) * rstd;
+                for (int j = 0; j < 8; ++j) o[j] = (gg[j] * w[j] - hh[j] * rstd * c1) * rstd;
                 st_v4(dx + base + (size_t)v * 8, pack8<T>(o));
             }
         }
-        if constexpr (RT > 32) {
-            // red[g] is rewritten next iteration: make sure every thread of the group has read it.
-            if constexpr (RT == 512) __syncthreads(); else named_bar_sync(1 + g, RT);
-        }
     }
 
-    // Fold the G row groups of this CTA, then one fp32 partial row per CTA.
+    // Fold the G row groups of this CTA through the (now idle) ring, then one fp32 partial row per CTA.
+    float* fold = reinterpret_cast<float*>(ring);
     if constexpr (G > 1) {
+        named_bar_sync(15, kBwdConsumers);   // every consumer is done reading the ring
         if (g > 0) {
 #pragma unroll
-            for (int i = 0; i < VPT; ++i) {
-                const int v = t + i * RT;
+            for (int k = 0; k < VPT; ++k) {
+                const int v = t + k * RT;
                 if (v < nvec) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) dw_smem[(size_t)(g - 1) * C + v * 8 + j] = dwacc[i][j];
+                    float4* dst = reinterpret_cast<float4*>(fold + (size_t)(g - 1) * C + (size_t)v * 8);
+                    dst[0] = make_float4(dwacc[k][0], dwacc[k][1], dwacc[k][2], dwacc[k][3]);
+                    dst[1] = make_float4(dwacc[k][4], dwacc[k][5], dwacc[k][6], dwacc[k][7]);
                 }
             }
         }
-        __syncthreads();
+        named_bar_sync(15, kBwdConsumers);
     }
     if (g == 0) {
 #pragma unroll
-        for (int i = 0; i < VPT; ++i) {
-            const int v = t + i * RT;
+        for (int k = 0; k < VPT; ++k) {
+            const int v = t + k * RT;
             if (v < nvec) {
-                float4 lo, hi;
-                float s[8];
+                float sacc[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    s[j] = dwacc[i][j];
-                    if constexpr (G > 1) {
-                        for (int gg = 1; gg < G; ++gg) s[j] += dw_smem[(size_t)(gg - 1) * C + v * 8 + j];
+                for (int j = 0; j < 8; ++j) sacc[j] = dwacc[k][j];
+                if constexpr (G > 1) {
+                    for (int gg = 1; gg < G; ++gg) {
+                        const float4* src = reinterpret_cast<const float4*>(fold + (size_t)(gg - 1) * C + (size_t)v * 8);
+                        const float4 a = src[0], b = src[1];
+                        sacc[0] += a.x; sacc[1] += a.y; sacc[2] += a.z; sacc[3] += a.w;
+                        sacc[4] += b.x; sacc[5] += b.y; sacc[6] += b.z; sacc[7] += b.w;
                     }
                 }
-                lo = make_float4(s[0], s[1], s[2], s[3]);
-                hi = make_float4(s[4], s[5], s[6], s[7]);
                 float4* dst = reinterpret_cast<float4*>(dw_partial + (size_t)blockIdx.x * C + (size_t)v * 8);
-                dst[0] = lo;
-                dst[1] = hi;
+                dst[0] = make_float4(sacc[0], sacc[1], sacc[2], sacc[3]);
+                dst[1] = make_float4(sacc[4], sacc[5], sacc[6], sacc[7]);
             }
         }
     }
@@ -320,23 +397,37 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_generic_kernel(
     }
 }
 
-// dw[c] = sum_p partial[p][c], cast to T. One thread per column; consecutive threads read
-// consecutive columns (coalesced).
+// dw[c] = sum_p partial[p][c], cast to T.  CTA = 32 columns x 8 partial groups: a warp reads 32 consecutive
+// columns of one partial row (coalesced 128 B), the 8 groups split the partial rows so ~20 independent loads per
+// thread cover all partials; fixed summation order (deterministic).
 template <typename T>
-__global__ void __launch_bounds__(128) rmsnorm_dw_reduce_kernel(const float* __restrict__ partial, T* __restrict__ dw,
+__global__ void __launch_bounds__(256) rmsnorm_dw_reduce_kernel(const float* __restrict__ partial, T* __restrict__ dw,
                                                                 int nparts, int C) {
-    const int c = blockIdx.x * 128 + threadIdx.x;
-    if (c >= C) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int p = 0;
-    for (; p + 4 <= nparts; p += 4) {
-        s0 += partial[(size_t)(p + 0) * C + c];
-        s1 += partial[(size_t)(p + 1) * C + c];
-        s2 += partial[(size_t)(p + 2) * C + c];
-        s3 += partial[(size_t)(p + 3) * C + c];
+    __shared__ float sm[8][33];
+    const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    pdl_wait_prior_grid();   // partial rows come from the backward kernel launched just before
+    float s = 0.f;
+    if (c < C) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int p = pg;
+        for (; p + 24 < nparts; p += 32) {
+            a0 += partial[(size_t)p * C + c];
+            a1 += partial[(size_t)(p + 8) * C + c];
+            a2 += partial[(size_t)(p + 16) * C + c];
+            a3 += partial[(size_t)(p + 24) * C + c];
+        }
+        for (; p < nparts; p += 8) a0 += partial[(size_t)p * C + c];
+        s = (a0 + a1) + (a2 + a3);
     }
-    for (; p < nparts; ++p) s0 += partial[(size_t)p * C + c];
-    dw[c] = static_cast<T>((s0 + s1) + (s2 + s3));
+    sm[pg][cl] = s;
+    __syncthreads();
+    if (pg == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][cl];
+        dw[c] = static_cast<T>(t);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -345,20 +436,26 @@ __global__ void __launch_bounds__(128) rmsnorm_dw_reduce_kernel(const float* __r
 template <typename T, int RT, int VPT>
 static cudaError_t launch_fwd_fast(const T* x, const T* residual, const T* weight, T* y, T* h_out, float* rms,
                                    int64_t rows, int C, float eps, cudaStream_t s) {
-    dim3 grid(static_cast<unsigned>(rows)), block(RT);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(rows));
+    cfg.blockDim = dim3(RT);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const T* rc = residual;
+    cudaError_t e;
     if (residual != nullptr) {
-        if (h_out != nullptr)
-            add_rmsnorm_fwd_kernel<T, RT, VPT, true, true><<<grid, block, 0, s>>>(x, residual, weight, y, h_out, rms, rows, C, eps);
-        else
-            add_rmsnorm_fwd_kernel<T, RT, VPT, true, false><<<grid, block, 0, s>>>(x, residual, weight, y, h_out, rms, rows, C, eps);
+        if (h_out != nullptr) e = cudaLaunchKernelEx(&cfg, add_rmsnorm_fwd_kernel<T, RT, VPT, true, true>, x, rc, weight, y, h_out, rms, rows, C, eps);
+        else e = cudaLaunchKernelEx(&cfg, add_rmsnorm_fwd_kernel<T, RT, VPT, true, false>, x, rc, weight, y, h_out, rms, rows, C, eps);
     } else {
-        if (h_out != nullptr)
-            add_rmsnorm_fwd_kernel<T, RT, VPT, false, true><<<grid, block, 0, s>>>(x, residual, weight, y, h_out, rms, rows, C, eps);
-        else
-            add_rmsnorm_fwd_kernel<T, RT, VPT, false, false><<<grid, block, 0, s>>>(x, residual, weight, y, h_out, rms, rows, C, eps);
+        if (h_out != nullptr) e = cudaLaunchKernelEx(&cfg, add_rmsnorm_fwd_kernel<T, RT, VPT, false, true>, x, rc, weight, y, h_out, rms, rows, C, eps);
+        else e = cudaLaunchKernelEx(&cfg, add_rmsnorm_fwd_kernel<T, RT, VPT, false, false>, x, rc, weight, y, h_out, rms, rows, C, eps);
     }
-    count_launch();
-    return cudaGetLastError();
+    if (e == cudaSuccess) count_launch();
+    return e;
 }
 
 template <typename T>
@@ -379,23 +476,28 @@ static cudaError_t add_rmsnorm_fwd_t(const T* x, const T* residual, const T* wei
     return cudaGetLastError();
 }
 
-static int bwd_grid(int64_t rows, int rows_per_cta) {
-    const int64_t want = (rows + rows_per_cta - 1) / rows_per_cta;
-    const int64_t cap = static_cast<int64_t>(num_sms()) * 2;
-    return static_cast<int>(want < cap ? (want < 1 ? 1 : want) : cap);
+static int bwd_grid(int64_t rows) {
+    const int64_t cap = num_sms();
+    return static_cast<int>(rows < cap ? (rows < 1 ? 1 : rows) : cap);
 }
 
 template <typename T, int RT, int VPT>
 static cudaError_t launch_bwd_fast(const T* dy, const T* h, const T* weight, const float* rms, T* dx, float* partial,
                                    int64_t rows, int C, int grid, cudaStream_t s) {
-    constexpr int G = 512 / RT;
-    const size_t smem = (G > 1) ? static_cast<size_t>(G - 1) * C * sizeof(float) : 0;
+    constexpr int G = kBwdConsumers / RT;
+    const size_t stage_bytes = 2 * static_cast<size_t>(C) * sizeof(T);
+    int stages = static_cast<int>((200 * 1024) / stage_bytes);
+    if (stages > kBwdMaxStages) stages = kBwdMaxStages;
+    if (stages < 2 || stages < G - 1) return cudaErrorInvalidConfiguration;   // the d_weight fold reuses the ring
+    const size_t smem = stages * stage_bytes + kBwdBarrierBytes + kBwdRedBytes;
     auto* k = rmsnorm_bwd_kernel<T, RT, VPT>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
+        configured = true;
     }
-    k<<<grid, 512, smem, s>>>(dy, h, weight, rms, dx, partial, rows, C);
+    k<<<grid, kBwdThreads, smem, s>>>(dy, h, weight, rms, dx, partial, rows, C, stages);
     count_launch();
     return cudaGetLastError();
 }
@@ -416,23 +518,33 @@ static cudaError_t rmsnorm_bwd_t(const T* dy, const T* h, const T* weight, const
     const bool aligned = (C % 8 == 0) && is_aligned16(dy) && is_aligned16(h) && is_aligned16(weight) && is_aligned16(dx);
     int grid;
     cudaError_t e;
-    if (aligned && C <= 8192) {
-        if (C <= 32 * 2 * 8) { grid = bwd_grid(rows, 16); e = launch_bwd_fast<T, 32, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s); }
-        else if (C <= 64 * 2 * 8) { grid = bwd_grid(rows, 8); e = launch_bwd_fast<T, 64, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s); }
-        else if (C <= 128 * 2 * 8) { grid = bwd_grid(rows, 4); e = launch_bwd_fast<T, 128, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s); }
-        else if (C <= 256 * 2 * 8) { grid = bwd_grid(rows, 2); e = launch_bwd_fast<T, 256, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s); }
-        else { grid = bwd_grid(rows, 1); e = launch_bwd_fast<T, 512, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s); }
+    if (aligned && C <= 16384) {
+        grid = bwd_grid(rows);
+        if (C <= 64 * 2 * 8) e = launch_bwd_fast<T, 64, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s);
+        else if (C <= 128 * 2 * 8) e = launch_bwd_fast<T, 128, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s);
+        else if (C <= 256 * 2 * 8) e = launch_bwd_fast<T, 256, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s);
+        else if (C <= 512 * 2 * 8) e = launch_bwd_fast<T, 512, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s);
+        else e = launch_bwd_fast<T, 512, 4>(dy, h, weight, rms, dx, workspace, rows, C, grid, s);
     } else {
-        grid = bwd_grid(rows, 1);
+        grid = 2 * bwd_grid(rows);
         rmsnorm_bwd_generic_kernel<T><<<grid, 256, 0, s>>>(dy, h, weight, rms, dx, workspace, rows, C);
         count_launch();
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return e;
     if (dw != nullptr) {
-        rmsnorm_dw_reduce_kernel<T><<<(C + 127) / 128, 128, 0, s>>>(workspace, dw, grid, C);
-        count_launch();
-        e = cudaGetLastError();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(static_cast<unsigned>((C + 31) / 32));
+        cfg.blockDim = dim3(256);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const float* part = workspace;
+        e = cudaLaunchKernelEx(&cfg, rmsnorm_dw_reduce_kernel<T>, part, dw, grid, C);
+        if (e == cudaSuccess) count_launch();
     }
     return e;
 }

@@ -29,27 +29,49 @@ def weights(H, I, n=1):
     return out
 
 
-def decode(H, I, nsets=3):
+def decode(H, I, nsets=3, batches=(1, 4, 16, 32, 64, 128), knobs=({},)):
     # rotate weight sets so every step streams weights from HBM (3 x 352 MB > 126 MB L2)
     ws = weights(H, I, nsets)
-    for B in (1, 4, 16, 64, 128):
-        x = torch.randn(B, 1, H, device="cuda").bfloat16()
-        state = {"i": 0}
+    gamma = torch.ones(H, device="cuda", dtype=torch.bfloat16)
+    for kn in knobs:
+        for k in list(os.environ):
+            if k.startswith("L32_DECODE_"):
+                del os.environ[k]
+        os.environ.update({k: str(v) for k, v in kn.items()})
+        for B in batches:
+            x = torch.randn(B, 1, H, device="cuda").bfloat16()
+            r = torch.randn(B, 1, H, device="cuda").bfloat16()
+            act = torch.randn(B, 1, I, device="cuda").bfloat16()
+            state = {"i": 0}
 
-        def f():
-            i = state["i"] % nsets
-            state["i"] += 1
-            ops.ffn_forward(x, ws[3 * i], ws[3 * i + 1], ws[3 * i + 2])
+            def nxt():
+                i = state["i"] % nsets
+                state["i"] += 1
+                return ws[3 * i], ws[3 * i + 1], ws[3 * i + 2]
 
-        def g():
-            i = state["i"] % nsets
-            state["i"] += 1
-            ops.swiglu_forward(x, ws[3 * i], ws[3 * i + 1])
-        t = timeit(f, iters=30)
-        tg = timeit(g, iters=30)
-        gb = 3.0 * H * I * 2 / 1e9
-        print(f"decode H={H} I={I} B={B}: ffn {t * 1e3:.1f} us ({gb / t * 1e3:.0f} GB/s)  gate/up {tg * 1e3:.1f} us "
-              f"({gb * 2 / 3 / tg * 1e3:.0f} GB/s)  down {(t - tg) * 1e3:.1f} us ({gb / 3 / (t - tg) * 1e3:.0f} GB/s)", flush=True)
+            def f():
+                wg, wu, wd = nxt()
+                ops.ffn_forward(x, wg, wu, wd)
+
+            def g():
+                wg, wu, wd = nxt()
+                ops.swiglu_forward(x, wg, wu)
+
+            def d():
+                wg, wu, wd = nxt()
+                ops.linear_forward(act, wd)
+
+            def blk():
+                wg, wu, wd = nxt()
+                ops.ffn_forward(ops.add_rmsnorm_forward(x, gamma, r, 1e-5, want_rms=False)[0], wg, wu, wd)
+            t, tg, td, tb = (timeit(fn, iters=60, warm=6) for fn in (f, g, d, blk))
+            gb = 3.0 * H * I * 2 / 1e9
+            print(f"decode H={H} I={I} B={B} {kn}: ffn {t * 1e3:.1f} us ({gb / t * 1e3:.0f} GB/s)  gate/up {tg * 1e3:.1f} us "
+                  f"({gb * 2 / 3 / tg * 1e3:.0f} GB/s)  down {td * 1e3:.1f} us ({gb / 3 / td * 1e3:.0f} GB/s)  "
+                  f"norm+ffn {tb * 1e3:.1f} us", flush=True)
+    for k in list(os.environ):
+        if k.startswith("L32_DECODE_"):
+            del os.environ[k]
 
 
 def train(H, I, T):
@@ -80,16 +102,29 @@ def train(H, I, T):
     t3 = timeit(lambda: ops.gemm(dg, xn, a_mn_major=True, b_mn_major=True), iters=10)      # wgrad
     f2 = 2.0 * T * H * I
     print(f"   d_act gemm {t1:.3f} ms ({f2 / t1 / 1e9:.0f} TF/s)  dx 2-phase {t2:.3f} ms ({2 * f2 / t2 / 1e9:.0f} TF/s)  wgrad {t3:.3f} ms ({f2 / t3 / 1e9:.0f} TF/s)")
-    hh = x
-    rms = torch.ones(T, device="cuda")
-    w = torch.ones(H, device="cuda", dtype=dt)
-    tb = timeit(lambda: ops.rmsnorm_backward(dy, hh, w, rms), iters=30)
-    tf = timeit(lambda: ops.add_rmsnorm_forward(x, w, r, 1e-5, want_h=True), iters=30)
-    tf3 = timeit(lambda: ops.add_rmsnorm_forward(x, w, r, 1e-5, want_h=False, want_rms=False), iters=30)
-    tf2 = timeit(lambda: ops.add_rmsnorm_forward(x, w, None, 1e-5, want_h=False, want_rms=False), iters=30)
+
+
+def norm(H, T, nbuf=6):
+    """Add-RMSNorm / RMSNorm backward HBM bandwidth; nbuf rotating buffer sets (> 126 MB L2) so nothing is L2-resident."""
+    dt = torch.bfloat16
+    xs = [torch.randn(T, H, device="cuda").to(dt) for _ in range(nbuf)]
+    rs = [torch.randn(T, H, device="cuda").to(dt) for _ in range(nbuf)]
+    dys = [torch.randn(T, H, device="cuda").to(dt) for _ in range(nbuf)]
+    rms = torch.rand(T, device="cuda") + 0.5
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).to(dt)
+    st = {"i": 0}
+
+    def nx():
+        st["i"] += 1
+        return st["i"] % nbuf
+    tb = timeit(lambda: ops.rmsnorm_backward(dys[nx()], xs[nx()], w, rms), iters=60, warm=6)
+    tf = timeit(lambda: ops.add_rmsnorm_forward(xs[nx()], w, rs[nx()], 1e-5, want_h=True), iters=60, warm=6)
+    tf3 = timeit(lambda: ops.add_rmsnorm_forward(xs[nx()], w, rs[nx()], 1e-5, want_h=False, want_rms=False), iters=60, warm=6)
+    tf2 = timeit(lambda: ops.add_rmsnorm_forward(xs[nx()], w, None, 1e-5, want_h=False, want_rms=False), iters=60, warm=6)
     b = T * H * 2
-    print(f"   rmsnorm fwd(no res) {tf2 * 1e3:.1f} us {2 * b / tf2 / 1e6:.0f} GB/s | add-rmsnorm fwd {tf3 * 1e3:.1f} us {3 * b / tf3 / 1e6:.0f} GB/s | "
-          f"+h {tf * 1e3:.1f} us {4 * b / tf / 1e6:.0f} GB/s | bwd {tb * 1e3:.1f} us {3 * b / tb / 1e6:.0f} GB/s")
+    print(f"norm H={H} T={T}: fwd(no res) {tf2 * 1e3:.1f} us {2 * b / tf2 / 1e6:.0f} GB/s | add-rmsnorm fwd {tf3 * 1e3:.1f} us "
+          f"{3 * b / tf3 / 1e6:.0f} GB/s | +h {tf * 1e3:.1f} us {4 * b / tf / 1e6:.0f} GB/s | bwd {tb * 1e3:.1f} us {3 * b / tb / 1e6:.0f} GB/s",
+          flush=True)
 
 
 def prefill(H, I, T):
@@ -113,8 +148,15 @@ if __name__ == "__main__":
     if what == "decode":
         decode(4096, 14336)
         decode(8192, 28672, nsets=2)
+    elif what == "decode_sweep":
+        decode(4096, 14336, batches=(1, 16, 32, 64, 128), knobs=({}, {"L32_DECODE_ROTATE": 0}))
+        decode(8192, 28672, nsets=2, batches=(1, 64, 128), knobs=({}, {"L32_DECODE_ROTATE": 0}))
     elif what == "train":
         train(4096, 14336, 8192)
+    elif what == "norm":
+        norm(4096, 8192)
+        norm(8192, 8192)
+        norm(4096, 64)
     elif what == "prefill":
         prefill(4096, 14336, 8192)
         prefill(8192, 28672, 8192)
