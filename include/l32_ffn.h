@@ -147,6 +147,47 @@ L32_API int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, 
              int64_t lda1, const void* b1, int64_t ldb1, void* d, int64_t ldd, int m, int n, int k, int k1, int dtype,
              int cta_group, int max_ctas, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-parallel feed-forward (one process per GPU; gate/up column-parallel, down row-parallel).
+ * No reference counterpart: the reference has no distributed code; these entry points
+ * implement the sharding of Tools/swiglu/FusedSwiglu.py:63-64 / Model/model.py:214 that BASELINE.json asks for.
+ * "peer" pointers are device pointers of OTHER ranks' buffers mapped into this process (CUDA IPC / symmetric
+ * memory); the arrays holding them are HOST arrays of `world` entries (world <= 8), entry [rank] = own buffer.
+ * Flags are uint32 step counters ("epoch", monotonic, starting at 1) living in each rank's own memory.
+ */
+
+/* flag[index] := value on every rank, after everything this stream did before is visible system-wide. */
+L32_API int l32_tp_signal(void* const* peer_flags, int world, int index, uint32_t value, void* stream);
+
+/* Fused all-gather + gate/up projection + SiLU*mul.
+ *   x_full   : this rank's [tokens, hidden] activation buffer; only rows [rank*rows_per_rank, ...) are valid on
+ *              entry.  The kernel PULLS the other ranks' rows out of peer_x[s] (NVLink loads issued by the spare
+ *              warps of the tcgen05 GEMM CTAs) while the tensor cores already work on the rows that have arrived;
+ *              tiles are visited starting at the own rows, then rank+1, rank+2, ... (the pull order).
+ *   ready    : own flags, ready[s] >= epoch once rank s has written its rows (see l32_tp_signal).
+ *   done     : own scratch counters, `world` uint32, zeroed by this call (cudaMemsetAsync on `stream`).
+ *   w_gate, w_up : this rank's shard [inter_local, hidden]; act : [tokens, inter_local].
+ */
+L32_API int l32_tp_swiglu_forward_allgather(void* x_full, const void* const* peer_x, const uint32_t* ready, uint32_t* done,
+                                            uint32_t epoch, int rank, int world, int64_t rows_per_rank, const void* w_gate,
+                                            const void* w_up, const void* b_gate, const void* b_up, void* act,
+                                            void* gate_cache, void* up_cache, int64_t tokens, int hidden, int inter_local,
+                                            int dtype, void* stream);
+
+/* Fused down projection + reduce-scatter: y_partial = a w^T is stored row by row straight into the slot of the rank
+ * that owns the row: peer_slots[o] = base of rank o's [rows_per_rank, out_features] slot for THIS rank's partial.
+ *   a : [tokens, in_local]; w : this rank's shard [out_features, in_local] (contiguous copy of w_down[:, shard]).
+ */
+L32_API int l32_tp_linear_forward_reduce_scatter(const void* a, const void* w, void* const* peer_slots, int rank, int world,
+                                                 int64_t rows_per_rank, int64_t tokens, int in_local, int out_features,
+                                                 int dtype, void* stream);
+
+/* y[rows, hidden] = sum_s slots[s][rows, hidden] (+ addend), fp32 accumulation in rank order, after waiting until
+ * flags[s] >= epoch for every s != rank.  slots : own [world, slot_rows, hidden] buffer the peers pushed into. */
+L32_API int l32_tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_t epoch, int world, int rank,
+                                   const void* addend, void* y, int64_t rows, int64_t slot_rows, int hidden, int dtype,
+                                   void* stream);
+
 /* Elementwise helpers (unfused reference points for tests / benchmarks of the fusion saving). */
 L32_API int l32_swiglu_act(const void* gate, const void* up, void* act, int64_t n, int dtype, void* stream);
 

@@ -314,6 +314,109 @@ int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t 
     return gemm_sm100(g, as_stream(stream));
 }
 
+int l32_tp_signal(void* const* peer_flags, int world, int index, uint32_t value, void* stream) {
+    if (peer_flags == nullptr) return L32_ERR_NULL;
+    if (world < 1 || world > kMaxTpWorld || index < 0) return L32_ERR_BAD_SHAPE;
+    for (int i = 0; i < world; ++i)
+        if (peer_flags[i] == nullptr) return L32_ERR_NULL;
+    return static_cast<int>(tp_signal(peer_flags, world, index, value, as_stream(stream)));
+}
+
+int l32_tp_swiglu_forward_allgather(void* x_full, const void* const* peer_x, const uint32_t* ready, uint32_t* done,
+                                    uint32_t epoch, int rank, int world, int64_t rows_per_rank, const void* w_gate,
+                                    const void* w_up, const void* b_gate, const void* b_up, void* act, void* gate_cache,
+                                    void* up_cache, int64_t tokens, int hidden, int inter_local, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, inter_local)) return L32_ERR_BAD_SHAPE;
+    if (world < 1 || world > kMaxTpWorld || rank < 0 || rank >= world || rows_per_rank <= 0 ||
+        rows_per_rank * world < tokens || rows_per_rank > 0x7fffffff)
+        return L32_ERR_BAD_SHAPE;
+    if (tokens == 0) return L32_OK;
+    if (x_full == nullptr || w_gate == nullptr || w_up == nullptr || act == nullptr) return L32_ERR_NULL;
+    if ((gate_cache == nullptr) != (up_cache == nullptr)) return L32_ERR_NULL;
+    GemmProblem g = blank(static_cast<int>(tokens), inter_local, dtype);
+    g.k[0] = hidden;
+    g.a[0] = op(x_full, hidden, 0);
+    g.b[0] = op(w_gate, hidden, 0);
+    g.b[1] = op(w_up, hidden, 0);
+    g.epilogue = EPI_SWIGLU;
+    g.d[0] = act;
+    g.d[1] = gate_cache;
+    g.d[2] = up_cache;
+    g.bias[0] = b_gate;
+    g.bias[1] = b_up;
+    g.ldd = inter_local;
+    g.cta_group = 2;
+    if (world > 1) {
+        if (peer_x == nullptr || ready == nullptr || done == nullptr) return L32_ERR_NULL;
+        cudaError_t e = cudaMemsetAsync(done, 0, sizeof(uint32_t) * kMaxTpWorld, as_stream(stream));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        g.ag.world = world;
+        g.ag.rank = rank;
+        g.ag.rows_per_rank = static_cast<int>(rows_per_rank);
+        for (int s = 0; s < world; ++s) {
+            if (peer_x[s] == nullptr) return L32_ERR_NULL;
+            g.ag.peer_src[s] = peer_x[s];
+        }
+        g.ag.local_dst = x_full;
+        g.ag.ready = ready;
+        g.ag.done = done;
+        g.ag.epoch = epoch;
+        g.ag.done_base = 0;
+        g.m_rotate_rows = static_cast<int>(rank * rows_per_rank);
+        // one raster group = the m-tiles of one rank's chunk, so tiles only ever wait for the chunk being consumed
+        const int tile_m = 256;
+        int grp = static_cast<int>(rows_per_rank / tile_m);
+        if (grp < 1) grp = 1;
+        if (grp > 8) grp = 8;
+        g.raster_group = grp;
+    }
+    return gemm_sm100(g, as_stream(stream));
+}
+
+int l32_tp_linear_forward_reduce_scatter(const void* a, const void* w, void* const* peer_slots, int rank, int world,
+                                         int64_t rows_per_rank, int64_t tokens, int in_local, int out_features, int dtype,
+                                         void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, in_local, out_features)) return L32_ERR_BAD_SHAPE;
+    if (world < 1 || world > kMaxTpWorld || rank < 0 || rank >= world || rows_per_rank <= 0 ||
+        rows_per_rank * world < tokens || rows_per_rank > 0x7fffffff)
+        return L32_ERR_BAD_SHAPE;
+    if (tokens == 0) return L32_OK;
+    if (a == nullptr || w == nullptr || peer_slots == nullptr) return L32_ERR_NULL;
+    GemmProblem g = blank(static_cast<int>(tokens), out_features, dtype);
+    g.k[0] = in_local;
+    g.a[0] = op(a, in_local, 0);
+    g.b[0] = op(w, in_local, 0);
+    g.epilogue = EPI_STORE;
+    g.ldd = out_features;
+    g.cta_group = 2;
+    g.rs.world = world;
+    g.rs.rank = rank;
+    g.rs.rows_per_rank = static_cast<int>(rows_per_rank);
+    for (int o = 0; o < world; ++o) {
+        if (peer_slots[o] == nullptr || !is_aligned16(peer_slots[o])) return L32_ERR_NULL;
+        g.rs.peer_dst[o] = peer_slots[o];
+    }
+    // start with the rows owned by the next rank so that at any moment the ranks push to different owners
+    g.m_rotate_rows = static_cast<int>(((rank + 1) % world) * rows_per_rank);
+    if (g.m_rotate_rows >= tokens) g.m_rotate_rows = 0;
+    return gemm_sm100(g, as_stream(stream));
+}
+
+int l32_tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_t epoch, int world, int rank, const void* addend,
+                           void* y, int64_t rows, int64_t slot_rows, int hidden, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (world < 1 || world > kMaxTpWorld || rank < 0 || rank >= world || rows < 0 || slot_rows < rows || hidden <= 0 ||
+        (hidden % 8) != 0)
+        return L32_ERR_BAD_SHAPE;
+    if (rows == 0) return L32_OK;
+    if (slots == nullptr || y == nullptr || (world > 1 && flags == nullptr)) return L32_ERR_NULL;
+    if (!is_aligned16(slots) || !is_aligned16(y) || !is_aligned16(addend)) return L32_ERR_BAD_ALIGN;
+    return static_cast<int>(tp_reduce_partials(slots, flags, epoch, world, rank, addend, y, rows, slot_rows, hidden, dtype,
+                                               as_stream(stream)));
+}
+
 int l32_swiglu_act(const void* gate, const void* up, void* act, int64_t n, int dtype, void* stream) {
     if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
     if (n < 0 || (n % 8) != 0) return L32_ERR_BAD_SHAPE;

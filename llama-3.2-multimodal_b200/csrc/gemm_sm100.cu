@@ -63,6 +63,9 @@ struct GemmKernelParams {
     const void* e[2];
     const void* bias[2];
     long long ldd;
+    int m_rotate;           // m-tiles are visited starting at this tile index (wrapping around)
+    TpAllGather ag;         // all-gather of A fused into the kernel (world == 0: off)
+    TpReduceScatter rs;     // reduce-scatter fused into the EPI_STORE epilogue (world == 0: off)
 };
 
 // One operand tile of `rows` x 64 (K) elements into shared memory.
@@ -82,21 +85,6 @@ L32_DEVICE void load_tile(const CUtensorMap* map, uint8_t* dst, uint64_t* full_b
     }
 }
 
-struct TileCoord {
-    int m_blk, n_blk;
-};
-L32_DEVICE TileCoord tile_coord(int t, int tiles_m, int tiles_n, int group) {
-    const int per_group = group * tiles_n;
-    const int g = t / per_group;
-    const int first_m = g * group;
-    const int gsize = min(group, tiles_m - first_m);
-    const int r = t - g * per_group;
-    TileCoord c;
-    c.m_blk = first_m + r % gsize;
-    c.n_blk = r / gsize;
-    return c;
-}
-
 L32_DEVICE void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -105,6 +93,56 @@ L32_DEVICE uint4 ld_global_nc_v4(const void* p) {
     asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+
+struct TileCoord {
+    int m_blk, n_blk;
+};
+L32_DEVICE TileCoord tile_coord(int t, int tiles_m, int tiles_n, int group, int m_rotate) {
+    const int per_group = group * tiles_n;
+    const int g = t / per_group;
+    const int first_m = g * group;
+    const int gsize = min(group, tiles_m - first_m);
+    const int r = t - g * per_group;
+    TileCoord c;
+    c.m_blk = first_m + r % gsize + m_rotate;
+    if (c.m_blk >= tiles_m) c.m_blk -= tiles_m;
+    c.n_blk = r / gsize;
+    return c;
+}
+
+// All-gather fused into the kernel: this warp's share of pulling chunk after chunk of A rows out of peer memory
+// (NVLink loads that bypass the non-coherent L1) into the local A buffer, in the order the tiles consume them.
+L32_DEVICE void ag_pull(const TpAllGather& ag, int m, size_t row_bytes, int puller, int num_pullers, uint32_t lane) {
+    constexpr int kUnroll = 8;
+    for (int j = 1; j < ag.world; ++j) {
+        const int s = (ag.rank + j) % ag.world;
+        const long long r0 = static_cast<long long>(s) * ag.rows_per_rank;
+        long long rows = static_cast<long long>(m) - r0;
+        if (rows > ag.rows_per_rank) rows = ag.rows_per_rank;
+        if (rows > 0) {
+            if (lane == 0) wait_flag_ge<true>(&ag.ready[s], ag.epoch);   // rank s has written its own rows
+            __syncwarp();
+            const long long nvec = rows * static_cast<long long>(row_bytes / 16);
+            const long long v0 = nvec * puller / num_pullers, v1 = nvec * (puller + 1) / num_pullers;
+            const uint8_t* src = static_cast<const uint8_t*>(ag.peer_src[s]) + static_cast<size_t>(r0) * row_bytes;
+            uint8_t* dst = static_cast<uint8_t*>(ag.local_dst) + static_cast<size_t>(r0) * row_bytes;
+            for (long long v = v0 + lane; v < v1; v += 32 * kUnroll) {
+                uint4 buf[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u)
+                    if (v + u * 32 < v1) buf[u] = ld_relaxed_sys_v4(src + static_cast<size_t>(v + u * 32) * 16);
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u)
+                    if (v + u * 32 < v1)
+                        st_global_v4(dst + static_cast<size_t>(v + u * 32) * 16, buf[u].x, buf[u].y, buf[u].z, buf[u].w);
+            }
+            __threadfence();
+        }
+        __syncwarp();
+        if (lane == 0) red_release_gpu_add_u32(&ag.done[s], 1u);
+    }
+}
+
 
 // Store 32 consecutive columns of one row (16 packed registers), 8 columns per 16-byte store.
 L32_DEVICE void store_row32(void* base, const uint32_t (&v)[16], int n_valid) {
@@ -178,9 +216,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-                const TileCoord tc = tile_coord(t, p.tiles_m, p.tiles_n, p.raster_group);
+                const TileCoord tc = tile_coord(t, p.tiles_m, p.tiles_n, p.raster_group, p.m_rotate);
                 const int m0 = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM;
                 const int n0 = tc.n_blk * kTileNOut;
+                if (p.ag.world > 1 && m0 < p.m) {
+                    // the A rows of this tile may belong to other ranks: wait until every puller warp has landed them
+                    const int c_lo = m0 / p.ag.rows_per_rank;
+                    const int c_hi = (min(m0 + kBlockM, p.m) - 1) / p.ag.rows_per_rank;
+                    bool waited = false;
+                    for (int c = c_lo; c <= c_hi; ++c) {
+                        if (c == p.ag.rank) continue;
+                        wait_flag_ge<false>(&p.ag.done[c], p.ag.done_base + gridDim.x * 2u);
+                        waited = true;
+                    }
+                    if (waited) fence_proxy_async_all();   // generic-proxy stores of other SMs -> TMA (async proxy) loads
+                }
                 for (int ph = 0; ph < p.num_phases; ++ph) {
                     const int num_kb = (p.k[ph] + kBlockK - 1) / kBlockK;
                     for (int kb = 0; kb < num_kb; ++kb) {
@@ -243,13 +293,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 if (acc == 0) acc_phase ^= 1u;
             }
         }
+    } else if (warp == 2 || warp == 3) {
+        // ------------------------------------------------------------------ all-gather pullers (tensor-parallel only)
+        if (p.ag.world > 1)
+            ag_pull(p.ag, p.m, static_cast<size_t>(p.k[0]) * sizeof(T), static_cast<int>(blockIdx.x * 2 + (warp - 2)),
+                    static_cast<int>(gridDim.x * 2), lane);
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
         const uint32_t q = warp - 4;                       // TMEM lane quarter owned by this warp
         uint32_t acc = 0, acc_phase = 0;
         const size_t esz = sizeof(T);
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-            const TileCoord tc = tile_coord(t, p.tiles_m, p.tiles_n, p.raster_group);
+            const TileCoord tc = tile_coord(t, p.tiles_m, p.tiles_n, p.raster_group, p.m_rotate);
             const int row = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM + q * 32 + lane;
             const int n0 = tc.n_blk * kTileNOut;
             const bool row_ok = row < p.m;
@@ -259,6 +314,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * kAccCols;
 
             if constexpr (kEpi == EPI_STORE) {
+                // reduce-scatter fused into the epilogue: the row goes to the rank that owns it (peer store)
+                uint8_t* d_row = static_cast<uint8_t*>(p.d[0]) + row_off * esz;
+                if (p.rs.world > 0 && row_ok) {
+                    int owner = row / p.rs.rows_per_rank;
+                    if (owner >= p.rs.world) owner = p.rs.world - 1;
+                    d_row = static_cast<uint8_t*>(p.rs.peer_dst[owner]) +
+                            static_cast<size_t>(row - owner * p.rs.rows_per_rank) * static_cast<size_t>(p.ldd) * esz;
+                }
 #pragma unroll 1
                 for (int c = 0; c < kAccCols / 32; ++c) {
                     const int col = n0 + c * 32;
@@ -277,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                         }
                         o[j] = Pack2<T>::pack(lo, hi);
                     }
-                    if (row_ok) store_row32(static_cast<uint8_t*>(p.d[0]) + (row_off + col) * esz, o, p.n - col);
+                    if (row_ok) store_row32(d_row + static_cast<size_t>(col) * esz, o, p.n - col);
                 }
             } else if constexpr (kEpi == EPI_SWIGLU) {
 #pragma unroll 1
@@ -472,7 +535,7 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
     if (g.epilogue == EPI_SWIGLU && (g.num_phases != 1 || g.b[0].mn_major || g.b[1].mn_major)) return L32_ERR_BAD_SHAPE;
     for (int i = 0; i < 3; ++i)
         if (g.d[i] != nullptr && !is_aligned16(g.d[i])) return L32_ERR_BAD_ALIGN;
-    if (g.d[0] == nullptr) return L32_ERR_NULL;
+    if (g.d[0] == nullptr && g.rs.world == 0) return L32_ERR_NULL;
     if (g.epilogue == EPI_SWIGLU && (g.d[1] == nullptr) != (g.d[2] == nullptr)) return L32_ERR_NULL;
     if (g.epilogue == EPI_SWIGLU_BWD) {
         if (g.d[1] == nullptr || g.e[0] == nullptr || g.e[1] == nullptr) return L32_ERR_NULL;
@@ -505,6 +568,17 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
     kp.e[0] = g.e[0]; kp.e[1] = g.e[1];
     kp.bias[0] = g.bias[0]; kp.bias[1] = g.bias[1];
     kp.ldd = g.ldd;
+    kp.m_rotate = (g.m_rotate_rows > 0) ? (g.m_rotate_rows / tile_m) % kp.tiles_m : 0;
+    kp.ag = g.ag;
+    kp.rs = g.rs;
+    if (g.ag.world > kMaxTpWorld || g.rs.world > kMaxTpWorld) return L32_ERR_BAD_SHAPE;
+    if (g.ag.world > 1) {
+        // the pulled chunk is treated as a flat byte range: A must be K-major with a dense row pitch
+        if (g.a[0].mn_major || g.num_phases != 1 || g.a[0].ld != g.k[0] || g.ag.rows_per_rank <= 0 ||
+            g.ag.local_dst != g.a[0].ptr || g.ag.ready == nullptr || g.ag.done == nullptr)
+            return L32_ERR_BAD_SHAPE;
+    }
+    if (g.rs.world > 0 && (g.epilogue != EPI_STORE || g.rs.rows_per_rank <= 0)) return L32_ERR_BAD_SHAPE;
 
     const int b_box_rows = (g.epilogue == EPI_SWIGLU) ? 128 : kAccCols / cta_group;
     for (int ph = 0; ph < g.num_phases; ++ph) {

@@ -36,6 +36,30 @@ struct GemmOperand {
                        // 1: memory is [rows = K][cols = M or N]  (M/N contiguous)
 };
 
+constexpr int kMaxTpWorld = 8;
+
+// Tensor-parallel extensions of the tiled GEMM (both optional, world == 0 disables):
+//  * all-gather fused into the A operand: the rows of A owned by other ranks are PULLED from peer memory by the
+//    otherwise idle warps of every CTA, chunk by chunk in the order the tiles consume them, while the tensor cores
+//    work on the chunks that have already arrived;
+//  * reduce-scatter fused into the epilogue: each output row is stored straight into the buffer of the rank that
+//    owns it (peer stores over NVLink), slot [this rank]; the owner sums the slots.
+struct TpAllGather {
+    int world, rank;
+    int rows_per_rank;              // A rows owned by each rank (last rank may own fewer: rows beyond m are ignored)
+    const void* peer_src[kMaxTpWorld];   // peer_src[s]: base of rank s's full-size A buffer (only its own rows are valid)
+    void* local_dst;                // this rank's full-size A buffer (the GEMM's A operand)
+    const uint32_t* ready;          // local flags, ready[s] >= epoch once rank s's own rows are final
+    uint32_t* done;                 // local counters, done[s] += 1 per puller warp that finished chunk s
+    uint32_t epoch;                 // step number (monotonic, >= 1)
+    uint32_t done_base;             // value of every done[s] before this launch
+};
+struct TpReduceScatter {
+    int world, rank;
+    int rows_per_rank;              // output rows owned by each rank
+    void* peer_dst[kMaxTpWorld];    // peer_dst[o]: rank o's slot for THIS rank's partial, [rows_per_rank, ldd]
+};
+
 struct GemmProblem {
     int m, n;               // D is [m, n]; for EPI_SWIGLU n = intermediate size (act columns)
     int num_phases;         // 1, or 2 for D = A0*B0^T + A1*B1^T (EPI_SWIGLU: must be 1)
@@ -51,6 +75,9 @@ struct GemmProblem {
     int cta_group;          // 0 = auto, 1 or 2
     int raster_group;       // 0 = auto: m-tiles per raster group
     int max_ctas;           // 0 = all SMs (testing / tuning knob)
+    int m_rotate_rows;      // visit the m-tiles starting at this row (rounded down to a tile), wrapping around
+    TpAllGather ag;         // ag.world == 0: off
+    TpReduceScatter rs;     // rs.world == 0: off (EPI_STORE only)
 };
 int gemm_sm100(const GemmProblem& p, cudaStream_t s);   // returns L32_* / cudaError_t
 
@@ -65,6 +92,12 @@ int ffn_decode_swiglu(const void* x, const void* w_gate, const void* w_up, const
                       void* gate_cache, void* up_cache, int tokens, int hidden, int inter, int dtype, cudaStream_t s);
 int ffn_decode_linear(const void* a, const void* w, const void* bias, void* y, int tokens, int in_features,
                       int out_features, int dtype, cudaStream_t s);
+
+// ---- tp.cu : tensor-parallel glue (cross-GPU flags, reduction of the partial slots)
+cudaError_t tp_signal(void* const* peer_flags, int world, int index, uint32_t value, cudaStream_t s);
+cudaError_t tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_t epoch, int world, int rank,
+                               const void* addend, void* y, int64_t rows, int64_t slot_rows, int hidden, int dtype,
+                               cudaStream_t s);
 
 // ---- tensor-map helper (gemm_sm100.cu): 2-D row-major [rows, cols] 16-bit tensor, 128-byte swizzled box
 int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,

@@ -55,6 +55,50 @@ L32_DEVICE void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: 
 L32_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
+// cross-SM / cross-GPU flags and peer-memory access (tensor-parallel kernels)
+// ------------------------------------------------------------------------------------------------
+L32_DEVICE uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+L32_DEVICE uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+L32_DEVICE void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+L32_DEVICE void red_release_gpu_add_u32(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// 16-byte load that never hits a (non-coherent) L1 line: peer memory rewritten every step by another GPU.
+L32_DEVICE uint4 ld_relaxed_sys_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+L32_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Bounded spin on a flag another SM / GPU will raise: a protocol bug traps after ~10 s instead of hanging the GPU.
+template <bool kSys>
+L32_DEVICE void wait_flag_ge(const uint32_t* flag, uint32_t target) {
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (true) {
+        const uint32_t v = kSys ? ld_acquire_sys_u32(flag) : ld_acquire_gpu_u32(flag);
+        if (static_cast<int32_t>(v - target) >= 0) return;
+        if ((++spins & 0xffu) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ull) __trap();
+            __nanosleep(64);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------------
 L32_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {

@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) rmsnorm_bwd_kernel(
     }
     __syncthreads();
     pdl_launch_dependents();   // the d_weight column reduce may be scheduled; it waits for this grid to finish
+    pdl_wait_prior_grid();     // dy / h / rms come from earlier kernels of the stream; dx may still be read by them
 
     if (tid >= kBwdConsumers) {
         // ------------------------------------------------------------------ producer warp
@@ -248,15 +249,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) rmsnorm_bwd_kernel(
     }
 
     // ---------------------------------------------------------------------- consumers
+    // Per element (p = dy*h):  dot' += p*w;  dw += p*rstd;  dx = (dy*w)*rstd - h*c2,  c2 = rstd^3 * dot' / C
+    // -- algebraically the formulas above with rstd factored out of the row sums, 6 fp32 ops per element.
     const int g = tid / RT;
     const int t = tid % RT;
-    uint4 wv[VPT];
-    float dwacc[VPT][8];
+    float w[VPT][8], dwacc[VPT][8];
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
         const int v = t + i * RT;
-        wv[i] = make_uint4(0, 0, 0, 0);
-        if (v < nvec) wv[i] = __ldg(reinterpret_cast<const uint4*>(weight) + v);
+        uint4 wv = make_uint4(0, 0, 0, 0);
+        if (v < nvec) wv = __ldg(reinterpret_cast<const uint4*>(weight) + v);
+        unpack8<T>(wv, w[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) dwacc[i][j] = 0.f;
     }
@@ -267,18 +270,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) rmsnorm_bwd_kernel(
         const int s = static_cast<int>(i % stages);
         const uint32_t use = static_cast<uint32_t>(i / stages);
         const int64_t row = i * gridDim.x + blockIdx.x;
-        const float rstd = 1.0f / rms_next;
+        const float rstd = __frcp_rn(rms_next);
         if (i + G < n_local) rms_next = rms[(i + G) * gridDim.x + blockIdx.x];   // prefetch for the next turn
         mbar_wait(&full_bar[s], use & 1u);
         const uint8_t* src = ring + static_cast<size_t>(s) * stage_bytes;
-        uint4 gv[VPT], hv[VPT];
+        float gg[VPT][8], hh[VPT][8];
 #pragma unroll
         for (int k = 0; k < VPT; ++k) {
             const int v = t + k * RT;
+            uint4 gv = make_uint4(0, 0, 0, 0), hv = make_uint4(0, 0, 0, 0);
             if (v < nvec) {
-                gv[k] = lds_v4(src + static_cast<size_t>(v) * 16);
-                hv[k] = lds_v4(src + row_bytes + static_cast<size_t>(v) * 16);
+                gv = lds_v4(src + static_cast<size_t>(v) * 16);
+                hv = lds_v4(src + row_bytes + static_cast<size_t>(v) * 16);
             }
+            unpack8<T>(gv, gg[k]);
+            unpack8<T>(hv, hh[k]);
         }
         __syncwarp();
         if ((t & 31) == 0) mbar_arrive(&empty_bar[s]);   // stage may be refilled
@@ -286,18 +292,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) rmsnorm_bwd_kernel(
         float dot = 0.f;
 #pragma unroll
         for (int k = 0; k < VPT; ++k) {
-            const int v = t + k * RT;
-            if (v < nvec) {
-                float gg[8], hh[8], w[8];
-                unpack8<T>(gv[k], gg);
-                unpack8<T>(hv[k], hh);
-                unpack8<T>(wv[k], w);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float xh = hh[j] * rstd;
-                    dot = fmaf(xh, gg[j] * w[j], dot);
-                    dwacc[k][j] = fmaf(gg[j], xh, dwacc[k][j]);
-                }
+            for (int j = 0; j < 8; ++j) {
+                const float pr = gg[k][j] * hh[k][j];
+                dot = fmaf(pr, w[k][j], dot);
+                dwacc[k][j] = fmaf(pr, rstd, dwacc[k][j]);
             }
         }
         dot = warp_sum(dot);
@@ -309,18 +308,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) rmsnorm_bwd_kernel(
 #pragma unroll
             for (int k = 0; k < RT / 32; ++k) dot += slot[k];
         }
-        const float c1 = dot * invC;
+        const float c2 = dot * invC * rstd * rstd * rstd;
         const size_t base = static_cast<size_t>(row) * C;
 #pragma unroll
         for (int k = 0; k < VPT; ++k) {
             const int v = t + k * RT;
             if (v < nvec) {
-                float gg[8], hh[8], w[8], o[8];
-                unpack8<T>(gv[k], gg);
-                unpack8<T>(hv[k], hh);
-                unpack8<T>(wv[k], w);
+                float o[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = (gg[j] * w[j] - hh[j] * rstd * c1) * rstd;
+                for (int j = 0; j < 8; ++j) o[j] = fmaf(-hh[k][j], c2, gg[k][j] * w[k][j] * rstd);
                 st_v4(dx + base + (size_t)v * 8, pack8<T>(o));
             }
         }
@@ -397,35 +393,35 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_generic_kernel(
     }
 }
 
-// dw[c] = sum_p partial[p][c], cast to T.  CTA = 32 columns x 8 partial groups: a warp reads 32 consecutive
-// columns of one partial row (coalesced 128 B), the 8 groups split the partial rows so ~20 independent loads per
-// thread cover all partials; fixed summation order (deterministic).
+// dw[c] = sum_p partial[p][c], cast to T.  Latency-bound (the partials are L2-resident), so it is laid out for one
+// round of independent loads: CTA = 32 columns x 32 partial groups (1024 threads); a warp reads 32 consecutive
+// columns of one partial row (coalesced 128 B) and every thread issues its <= 8 loads back to back.  Fixed
+// summation order (deterministic).
+constexpr int kDwGroups = 32;
+constexpr int kDwMaxPerThread = 8;   // covers up to 256 partial rows (<= 2 x SM count)
 template <typename T>
-__global__ void __launch_bounds__(256) rmsnorm_dw_reduce_kernel(const float* __restrict__ partial, T* __restrict__ dw,
-                                                                int nparts, int C) {
-    __shared__ float sm[8][33];
+__global__ void __launch_bounds__(32 * kDwGroups) rmsnorm_dw_reduce_kernel(const float* __restrict__ partial,
+                                                                           T* __restrict__ dw, int nparts, int C) {
+    __shared__ float sm[kDwGroups][33];
     const int cl = threadIdx.x & 31, pg = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
+    pdl_launch_dependents();
     pdl_wait_prior_grid();   // partial rows come from the backward kernel launched just before
-    float s = 0.f;
-    if (c < C) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int p = pg;
-        for (; p + 24 < nparts; p += 32) {
-            a0 += partial[(size_t)p * C + c];
-            a1 += partial[(size_t)(p + 8) * C + c];
-            a2 += partial[(size_t)(p + 16) * C + c];
-            a3 += partial[(size_t)(p + 24) * C + c];
-        }
-        for (; p < nparts; p += 8) a0 += partial[(size_t)p * C + c];
-        s = (a0 + a1) + (a2 + a3);
+    float v[kDwMaxPerThread];
+#pragma unroll
+    for (int k = 0; k < kDwMaxPerThread; ++k) {
+        const int p = pg + k * kDwGroups;
+        v[k] = (c < C && p < nparts) ? partial[(size_t)p * C + c] : 0.f;
     }
+    float s = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    for (int p = pg + kDwMaxPerThread * kDwGroups; p < nparts; p += kDwGroups)   // only for > 256 partial rows
+        if (c < C) s += partial[(size_t)p * C + c];
     sm[pg][cl] = s;
     __syncthreads();
     if (pg == 0 && c < C) {
         float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += sm[k][cl];
+        for (int k = 0; k < kDwGroups; ++k) t += sm[k][cl];
         dw[c] = static_cast<T>(t);
     }
 }
@@ -497,9 +493,19 @@ static cudaError_t launch_bwd_fast(const T* dy, const T* h, const T* weight, con
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k<<<grid, kBwdThreads, smem, s>>>(dy, h, weight, rms, dx, partial, rows, C, stages);
-    count_launch();
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kBwdThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, dy, h, weight, rms, dx, partial, rows, C, stages);
+    if (e == cudaSuccess) count_launch();
+    return e;
 }
 
 // workspace layout: [grid][C] fp32, grid <= 2 * num_sms
@@ -535,7 +541,7 @@ static cudaError_t rmsnorm_bwd_t(const T* dy, const T* h, const T* weight, const
     if (dw != nullptr) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(static_cast<unsigned>((C + 31) / 32));
-        cfg.blockDim = dim3(256);
+        cfg.blockDim = dim3(32 * kDwGroups);
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

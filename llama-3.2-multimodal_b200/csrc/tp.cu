@@ -1,0 +1,107 @@
+// Tensor-parallel glue kernels (one process per GPU; all buffers named "peer" are symmetric allocations mapped into
+// this process, reached over NVLink 5 / NVSwitch with plain loads and stores).
+//
+// The reference has no distributed code; these kernels serve the sharding BASELINE.json's
+// north_star asks for -- gate/up column-parallel, down row-parallel -- together with the two fused GEMM variants in
+// gemm_sm100.cu (all-gather pulled into the A operand, reduce-scatter pushed from the epilogue):
+//   tp_signal_kernel          flag[index] := value on every rank (release at system scope)
+//   tp_reduce_partials_kernel y = sum over ranks of the partial slots this rank received (+ optional addend),
+//                             after waiting until every peer has raised its "partials written" flag
+#include "l32_internal.cuh"
+
+namespace l32 {
+namespace {
+
+struct PeerFlags {
+    uint32_t* ptr[kMaxTpWorld];
+};
+
+__global__ void tp_signal_kernel(PeerFlags flags, int world, int index, uint32_t value) {
+    const int d = threadIdx.x;
+    if (d < world) {
+        __threadfence_system();   // everything this GPU wrote before (earlier kernels of the stream) is visible first
+        st_release_sys_u32(flags.ptr[d] + index, value);
+    }
+}
+
+L32_DEVICE uint4 ldg_stream_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+// slots: [world][rows_per_rank][hidden] (slot s = the partial rank s pushed for this rank's rows); y, addend: [rows][hidden].
+// HBM-bound: world reads + 1 write of rows*hidden 16-bit elements; fp32 accumulation in rank order (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(256) tp_reduce_partials_kernel(const T* slots, const uint32_t* flags, uint32_t epoch,
+                                                                 int world, int rank, const T* addend, T* __restrict__ y,
+                                                                 int64_t rows, int64_t slot_rows, int hidden) {
+    if (threadIdx.x < world && static_cast<int>(threadIdx.x) != rank) wait_flag_ge<true>(&flags[threadIdx.x], epoch);
+    __syncthreads();
+    const int64_t nvec = rows * hidden / 8;
+    const int64_t slot_vec = slot_rows * hidden / 8;
+    for (int64_t v = blockIdx.x * 256ll + threadIdx.x; v < nvec; v += gridDim.x * 256ll) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        if (addend != nullptr) {
+            const uint4 a = ldg_stream_v4(addend + v * 8);
+            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = Pack2<T>::unpack(av[j]);
+                acc[2 * j] = f.x;
+                acc[2 * j + 1] = f.y;
+            }
+        }
+        for (int s = 0; s < world; ++s) {
+            const uint4 a = ldg_stream_v4(slots + (s * slot_vec + v) * 8);
+            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = Pack2<T>::unpack(av[j]);
+                acc[2 * j] += f.x;
+                acc[2 * j + 1] += f.y;
+            }
+        }
+        uint4 o;
+        o.x = Pack2<T>::pack(acc[0], acc[1]);
+        o.y = Pack2<T>::pack(acc[2], acc[3]);
+        o.z = Pack2<T>::pack(acc[4], acc[5]);
+        o.w = Pack2<T>::pack(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(y + v * 8) = o;
+    }
+}
+
+}  // namespace
+
+cudaError_t tp_signal(void* const* peer_flags, int world, int index, uint32_t value, cudaStream_t s) {
+    PeerFlags f;
+    for (int i = 0; i < kMaxTpWorld; ++i) f.ptr[i] = i < world ? static_cast<uint32_t*>(peer_flags[i]) : nullptr;
+    tp_signal_kernel<<<1, 32, 0, s>>>(f, world, index, value);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_t epoch, int world, int rank,
+                               const void* addend, void* y, int64_t rows, int64_t slot_rows, int hidden, int dtype,
+                               cudaStream_t s) {
+    if (rows == 0) return cudaSuccess;
+    const int64_t nvec = rows * hidden / 8;
+    int64_t blocks = (nvec + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    if (dtype == L32_BF16)
+        tp_reduce_partials_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+            static_cast<const __nv_bfloat16*>(slots), flags, epoch, world, rank, static_cast<const __nv_bfloat16*>(addend),
+            static_cast<__nv_bfloat16*>(y), rows, slot_rows, hidden);
+    else
+        tp_reduce_partials_kernel<__half><<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+            static_cast<const __half*>(slots), flags, epoch, world, rank, static_cast<const __half*>(addend),
+            static_cast<__half*>(y), rows, slot_rows, hidden);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace l32

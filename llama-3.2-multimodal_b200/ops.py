@@ -47,7 +47,7 @@ def supported(x: torch.Tensor) -> bool:
 
 
 # --------------------------------------------------------------------------------------------- RMSNorm
-def add_rmsnorm_forward(x, weight, residual=None, eps=1e-5, *, want_h=False, want_rms=True, h_out=None):
+def add_rmsnorm_forward(x, weight, residual=None, eps=1e-5, *, want_h=False, want_rms=True, h_out=None, out=None):
     """y = rmsnorm(x + residual) * weight.  Returns (y, rms|None, h|None).
 
     h (= x + residual rounded to x.dtype) is produced only when `want_h` and a residual is given (without a
@@ -65,7 +65,12 @@ def add_rmsnorm_forward(x, weight, residual=None, eps=1e-5, *, want_h=False, wan
         w = w.to(xc.dtype)
     if w.numel() != hidden:
         raise L32Error(f"weight has {w.numel()} elements, expected {hidden}")
-    y = torch.empty_like(xc)
+    if out is not None:
+        if out.shape != xc.shape or out.dtype != xc.dtype or not out.is_contiguous():
+            raise L32Error("add_rmsnorm_forward: `out` must be a contiguous tensor shaped and typed like the input")
+        y = out
+    else:
+        y = torch.empty_like(xc)
     rms = torch.empty(rows, dtype=torch.float32, device=xc.device) if want_rms else None
     h = h_out
     if h is None and want_h and rc is not None:
@@ -256,3 +261,58 @@ def swiglu_act(gate, up):
     with torch.cuda.device(g.device):
         check(lib().l32_swiglu_act(_ptr(g), _ptr(u), _ptr(act), g.numel(), _dtype_code(g), _stream(g)), "l32_swiglu_act")
     return act
+
+
+# --------------------------------------------------------------------------------------------- tensor parallel
+def _ptr_array(ptrs):
+    import ctypes
+    arr = (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+    return arr
+
+
+def tp_signal(peer_flag_ptrs, index, value, device):
+    """flag[index] := value on every rank (host list of `world` device pointers to each rank's uint32 flag array)."""
+    arr = _ptr_array(peer_flag_ptrs)
+    with torch.cuda.device(device):
+        check(lib().l32_tp_signal(arr, len(peer_flag_ptrs), int(index), int(value),
+                                  torch.cuda.current_stream(device).cuda_stream), "l32_tp_signal")
+
+
+def tp_swiglu_forward_allgather(x_full, peer_x_ptrs, ready, done, epoch, rank, rows_per_rank, w_gate, w_up, out=None):
+    """Fused all-gather (pulled over NVLink inside the GEMM) + gate/up projection + SiLU*mul on this rank's shard."""
+    _check_cuda(x_full, ready, done, w_gate, w_up)
+    tokens, hidden = x_full.shape
+    inter = w_gate.shape[0]
+    act = out if out is not None else torch.empty(tokens, inter, dtype=x_full.dtype, device=x_full.device)
+    world = len(peer_x_ptrs)
+    arr = _ptr_array(peer_x_ptrs)
+    with torch.cuda.device(x_full.device):
+        check(lib().l32_tp_swiglu_forward_allgather(_ptr(x_full), arr, _ptr(ready), _ptr(done), int(epoch), int(rank), world,
+                                                    int(rows_per_rank), _ptr(w_gate), _ptr(w_up), None, None, _ptr(act), None,
+                                                    None, tokens, hidden, inter, _dtype_code(x_full), _stream(x_full)),
+              "l32_tp_swiglu_forward_allgather")
+    return act
+
+
+def tp_linear_forward_reduce_scatter(a, weight, peer_slot_ptrs, rank, rows_per_rank):
+    """Fused down projection + reduce-scatter: every output row is stored into its owner's slot for this rank."""
+    _check_cuda(a, weight)
+    tokens, in_f = a.shape
+    out_f = weight.shape[0]
+    arr = _ptr_array(peer_slot_ptrs)
+    with torch.cuda.device(a.device):
+        check(lib().l32_tp_linear_forward_reduce_scatter(_ptr(a), _ptr(weight), arr, int(rank), len(peer_slot_ptrs),
+                                                         int(rows_per_rank), tokens, in_f, out_f, _dtype_code(a), _stream(a)),
+              "l32_tp_linear_forward_reduce_scatter")
+
+
+def tp_reduce_partials(slots, flags, epoch, rank, rows, addend=None, out=None):
+    """y = sum over ranks of the partial slots [world, slot_rows, hidden] (+ addend), after every peer signalled."""
+    _check_cuda(slots, flags, addend)
+    world, slot_rows, hidden = slots.shape
+    y = out if out is not None else torch.empty(rows, hidden, dtype=slots.dtype, device=slots.device)
+    with torch.cuda.device(slots.device):
+        check(lib().l32_tp_reduce_partials(_ptr(slots), _ptr(flags), int(epoch), world, int(rank), _ptr(addend), _ptr(y),
+                                           int(rows), slot_rows, hidden, _dtype_code(slots), _stream(slots)),
+              "l32_tp_reduce_partials")
+    return y

@@ -121,3 +121,125 @@ class TensorParallelFFN(torch.nn.Module):
         for w in works:
             w.wait()
         return y.view(x.shape)
+
+
+# ======================================================================================================================
+# Fused path: the collectives live INSIDE the tcgen05 GEMM kernels (peer memory over NVLink 5 / NVSwitch), no NCCL on
+# the data path.  Sequence-parallel in, sequence-parallel out:
+#
+#   rank r holds rows [r*R, (r+1)*R) of x / residual (R = ceil(tokens / world))
+#   1. Add-RMSNorm of the own rows, written into the own full-size `normed` buffer      (K1, local)
+#      -> signal ready[r] = epoch on every rank
+#   2. gate/up GEMM + SiLU*mul on the weight shard; the other ranks' normed rows are PULLED out of peer memory by the
+#      spare warps of the GEMM CTAs while the tensor cores work on the rows already there (fused all-gather)
+#   3. down GEMM on the shard; the epilogue stores every output row straight into the slot of the rank that owns the
+#      row (fused reduce-scatter, peer stores)  -> signal rs_done[r] = epoch on every rank
+#   4. the owner sums the `world` slots (fp32, rank order) once every peer has signalled -> y rows [r*R, (r+1)*R)
+#
+# Buffer reuse across steps is safe without extra barriers: a rank can only start step i+1's norm after its own step-i
+# reduce, which waited for every peer's rs_done flag, which each peer raises after its step-i GEMMs (the pulls included).
+# ======================================================================================================================
+FLAG_READY, FLAG_RS_DONE, NUM_FLAGS = 0, 8, 64
+
+
+class TpRankBuffers:
+    """Buffers of one rank of the fused path plus the addresses of every rank's buffers (entry [rank] = own)."""
+
+    def __init__(self, rank, world, max_tokens, hidden, normed, slots, flags, peer_normed, peer_slots_base, peer_flags):
+        self.rank, self.world, self.max_tokens, self.hidden = rank, world, max_tokens, hidden
+        self.slot_rows = slots.shape[1]
+        self.normed, self.slots, self.flags = normed, slots, flags
+        self.done = torch.zeros(8, dtype=torch.int32, device=normed.device)
+        self.peer_normed = list(peer_normed)
+        self.peer_flags = list(peer_flags)
+        slot_bytes = self.slot_rows * hidden * normed.element_size()
+        # where THIS rank's partial for owner o lands: slot [rank] of rank o's slots buffer
+        self.peer_slots = [int(base) + rank * slot_bytes for base in peer_slots_base]
+
+    @staticmethod
+    def slot_rows_for(max_tokens, world):
+        return -(-max_tokens // world)
+
+    @classmethod
+    def symmetric(cls, max_tokens, hidden, dtype, device, group=None):
+        """Allocate the three buffers as symmetric memory and exchange the peer mappings (one process per GPU)."""
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        rows = cls.slot_rows_for(max_tokens, world)
+        normed = symm.empty(max_tokens, hidden, dtype=dtype, device=device)
+        slots = symm.empty(world, rows, hidden, dtype=dtype, device=device)
+        flags = symm.empty(NUM_FLAGS, dtype=torch.int32, device=device)
+        flags.zero_()
+        hn, hs, hf = (symm.rendezvous(t, group) for t in (normed, slots, flags))
+        torch.cuda.synchronize(device)
+        dist.barrier(group)   # every rank's flags are zero before anybody can signal
+        bufs = cls(rank, world, max_tokens, hidden, normed, slots, flags, hn.buffer_ptrs, hs.buffer_ptrs, hf.buffer_ptrs)
+        bufs._handles = (hn, hs, hf)   # keep the mappings alive
+        return bufs
+
+    @classmethod
+    def local_world(cls, world, max_tokens, hidden, dtype, device):
+        """All ranks' buffers on ONE device, cross-wired with plain pointers: the single-GPU emulation used by the
+        tests (the ranks' phases are then run one after another, never concurrently)."""
+        rows = cls.slot_rows_for(max_tokens, world)
+        normed = [torch.zeros(max_tokens, hidden, dtype=dtype, device=device) for _ in range(world)]
+        slots = [torch.zeros(world, rows, hidden, dtype=dtype, device=device) for _ in range(world)]
+        flags = [torch.zeros(NUM_FLAGS, dtype=torch.int32, device=device) for _ in range(world)]
+        return [cls(r, world, max_tokens, hidden, normed[r], slots[r], flags[r], [t.data_ptr() for t in normed],
+                    [t.data_ptr() for t in slots], [t.data_ptr() for t in flags]) for r in range(world)]
+
+
+class FusedTensorParallelBlock:
+    """norm2(x, residual) -> feed-forward of one rank, collectives fused into the GEMM kernels (see above)."""
+
+    def __init__(self, gamma, eps, w_gate, w_up, w_down, bufs: TpRankBuffers):
+        """gamma [H]; w_gate / w_up / w_down are the FULL matrices ([I,H], [I,H], [H,I]); the shard is taken here."""
+        self.bufs = bufs
+        self.eps = eps
+        self.gamma = gamma
+        wg, wu, wd = shard_ffn_weights(w_gate, w_up, w_down, bufs.world, bufs.rank)
+        self.w_gate, self.w_up, self.w_down = wg.contiguous(), wu.contiguous(), wd
+        self.epoch = 0
+        self._act = None
+
+    def rows_of(self, tokens, rank=None):
+        rank = self.bufs.rank if rank is None else rank
+        per = -(-tokens // self.bufs.world)
+        lo = min(rank * per, tokens)
+        return lo, min(lo + per, tokens), per
+
+    # -- the four phases (run back to back by forward(); the single-GPU emulation interleaves them across ranks)
+    def phase_norm(self, x_local, residual_local, tokens):
+        b = self.bufs
+        self.epoch += 1
+        lo, hi, _ = self.rows_of(tokens)
+        if hi > lo:
+            ops.add_rmsnorm_forward(x_local, self.gamma, residual_local, self.eps, want_rms=False, out=b.normed[lo:hi])
+        ops.tp_signal(b.peer_flags, FLAG_READY + b.rank, self.epoch, b.normed.device)
+
+    def phase_gate_up(self, tokens):
+        b = self.bufs
+        _, _, per = self.rows_of(tokens)
+        self._act = ops.tp_swiglu_forward_allgather(b.normed[:tokens], b.peer_normed, b.flags[FLAG_READY:FLAG_READY + 8],
+                                                    b.done, self.epoch, b.rank, per, self.w_gate, self.w_up)
+
+    def phase_down(self, tokens):
+        b = self.bufs
+        _, _, per = self.rows_of(tokens)
+        ops.tp_linear_forward_reduce_scatter(self._act, self.w_down, b.peer_slots, b.rank, per)
+        ops.tp_signal(b.peer_flags, FLAG_RS_DONE + b.rank, self.epoch, b.normed.device)
+
+    def phase_reduce(self, tokens, addend=None):
+        b = self.bufs
+        lo, hi, _ = self.rows_of(tokens)
+        return ops.tp_reduce_partials(b.slots, b.flags[FLAG_RS_DONE:FLAG_RS_DONE + 8], self.epoch, b.rank, hi - lo, addend=addend)
+
+    def forward(self, x_local, residual_local, tokens, addend=None):
+        """x_local / residual_local: this rank's rows [rows_local, H]; returns this rank's rows of the FFN output."""
+        if tokens > self.bufs.max_tokens:
+            raise ValueError(f"tokens {tokens} exceeds the buffers' capacity {self.bufs.max_tokens}")
+        self.phase_norm(x_local, residual_local, tokens)
+        self.phase_gate_up(tokens)
+        self.phase_down(tokens)
+        return self.phase_reduce(tokens, addend)

@@ -118,12 +118,13 @@ def norm(H, T, nbuf=6):
         st["i"] += 1
         return st["i"] % nbuf
     tb = timeit(lambda: ops.rmsnorm_backward(dys[nx()], xs[nx()], w, rms), iters=60, warm=6)
+    tb0 = timeit(lambda: ops.rmsnorm_backward(dys[nx()], xs[nx()], w, rms, want_dweight=False), iters=60, warm=6)
     tf = timeit(lambda: ops.add_rmsnorm_forward(xs[nx()], w, rs[nx()], 1e-5, want_h=True), iters=60, warm=6)
     tf3 = timeit(lambda: ops.add_rmsnorm_forward(xs[nx()], w, rs[nx()], 1e-5, want_h=False, want_rms=False), iters=60, warm=6)
     tf2 = timeit(lambda: ops.add_rmsnorm_forward(xs[nx()], w, None, 1e-5, want_h=False, want_rms=False), iters=60, warm=6)
     b = T * H * 2
     print(f"norm H={H} T={T}: fwd(no res) {tf2 * 1e3:.1f} us {2 * b / tf2 / 1e6:.0f} GB/s | add-rmsnorm fwd {tf3 * 1e3:.1f} us "
-          f"{3 * b / tf3 / 1e6:.0f} GB/s | +h {tf * 1e3:.1f} us {4 * b / tf / 1e6:.0f} GB/s | bwd {tb * 1e3:.1f} us {3 * b / tb / 1e6:.0f} GB/s",
+          f"{3 * b / tf3 / 1e6:.0f} GB/s | +h {tf * 1e3:.1f} us {4 * b / tf / 1e6:.0f} GB/s | bwd {tb * 1e3:.1f} us {3 * b / tb / 1e6:.0f} GB/s (no dweight reduce: {tb0 * 1e3:.1f} us)",
           flush=True)
 
 
