@@ -14,8 +14,10 @@ hidden_dim 14336, bf16 prefill, 4 x 2048 tokens).  Prints ONE JSON line on rank 
             that launch inside the timed region, against MEASURED_PEAKS.json;
   cpu_baseline: the reference's own CPU path (PyTorch fp32 expressions, oracle port) on this box's host cores.
 --impl reference times that CPU path alone (rank 0 only) and prints the same line with "impl": "reference".
-N > 1: tensor-parallel FFN (column-sharded gate/up, row-sharded down, NCCL reduce-scatter + all-gather overlapped
-with the GEMMs by token chunks), same total batch -> "scaling": "strong".
+N > 1: tensor-parallel FFN (column-sharded gate/up, row-sharded down), sequence-parallel Add-RMSNorm, same total batch
+-> "scaling": "strong".  Default --tp-impl fused: the all-gather is pulled over NVLink inside the gate/up tcgen05 GEMM
+and the reduce-scatter is pushed from the down-GEMM epilogue (peer memory, no NCCL on the data path); --tp-impl nccl is
+the NCCL reduce-scatter / all-gather baseline with the same sharding.
 """
 from __future__ import annotations
 
@@ -174,12 +176,106 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ secondary numbers
+def _time_cuda(fn, iters, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3   # seconds
+
+
+def extra_numbers(dev, peaks):
+    """The other headline quantities of BASELINE.json's metric, measured in the same process (single GPU): RMSNorm HBM
+    GB/s, KV-decode FFN us/step (weight streaming), the 90B-shape prefill and the 11B training step.  Every HBM-bound
+    kernel rotates >= 3 buffer sets larger than the 126 MB L2."""
+    from llama32_b200 import ops
+    import llama32_b200 as L
+    dt = torch.bfloat16
+    out = {}
+    gen = torch.Generator(device=dev).manual_seed(7)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=gen).to(dt)
+    uni = lambda r, c: ((torch.rand(r, c, device=dev, generator=gen) * 2 - 1) / c ** 0.5).to(dt)
+    hbm = peaks["hbm_gbs"]
+    # ---- Add-RMSNorm, 8192 x 4096 (config 2 activations)
+    T, H = 8192, 4096
+    xs, rs, dys = ([rnd(T, H) for _ in range(6)] for _ in range(3))
+    gamma = (1 + 0.1 * torch.randn(H, device=dev, generator=gen)).to(dt)
+    rms = torch.rand(T, device=dev, generator=gen) + 0.5
+    st = {"i": 0}
+
+    def nx():
+        st["i"] += 1
+        return st["i"] % 6
+    b = T * H * 2
+    t = _time_cuda(lambda: ops.add_rmsnorm_forward(xs[nx()], gamma, rs[nx()], EPS, want_rms=False), 100)
+    out["add_rmsnorm_fwd_8192x4096"] = {"us": t * 1e6, "GBps": 3 * b / t / 1e9, "frac_of_measured_hbm": 3 * b / t / 1e9 / hbm,
+                                        "algorithmic_bytes": 3 * b}
+    t = _time_cuda(lambda: ops.rmsnorm_backward(dys[nx()], xs[nx()], gamma, rms), 100)
+    out["rmsnorm_bwd_8192x4096"] = {"us": t * 1e6, "GBps": 3 * b / t / 1e9, "frac_of_measured_hbm": 3 * b / t / 1e9 / hbm,
+                                    "algorithmic_bytes": 3 * b}
+    del xs, rs, dys
+    # ---- KV-cached decode FFN (config 3), 11B shape, 3 rotating weight sets (1.06 GB)
+    H, I = 4096, 14336
+    ws = [(uni(I, H), uni(I, H), uni(H, I)) for _ in range(3)]
+    wbytes = 3.0 * H * I * 2
+    for B in (1, 16, 64):
+        x = rnd(B, 1, H)
+        r = rnd(B, 1, H)
+
+        def dec():
+            wg, wu, wd = ws[nx() % 3]
+            ops.ffn_forward(ops.add_rmsnorm_forward(x, gamma, r, EPS, want_rms=False)[0], wg, wu, wd)
+        t = _time_cuda(dec, 150, warm=10)
+        out[f"decode_11b_batch{B}"] = {"us_per_step": t * 1e6, "tokens_per_s": B / t, "GBps": wbytes / t / 1e9,
+                                       "frac_of_measured_hbm": wbytes / t / 1e9 / hbm, "algorithmic_bytes": wbytes,
+                                       "what": "add-rmsnorm + FFN per decode step, weights streamed from HBM"}
+    # ---- 11B training step (config 4 without the LoRA side path: all FFN weights trainable), fwd + bwd
+    norm = L.LLAMARMSNorm(H, eps=EPS).to(dev, dt)
+    ffn = L.FusedFeedforward(H, I).to(dev, dt)
+    with torch.no_grad():
+        ffn.swiglu.w_gate.copy_(ws[0][0]); ffn.swiglu.w_up.copy_(ws[0][1]); ffn.w_down.weight.copy_(ws[0][2])
+    del ws
+    T = 8192
+    x, r, dy = rnd(T, H), rnd(T, H), rnd(T, H)
+
+    def train_step():
+        xx = x.detach().requires_grad_(True)
+        ffn(norm(xx, residual=r)).backward(dy)
+    t = _time_cuda(train_step, 10, warm=3)
+    fl = 18.0 * T * H * I
+    out["train_11b_fwd_bwd_8192tok"] = {"ms": t * 1e3, "tokens_per_s": T / t, "TFLOPs": fl / t / 1e12,
+                                        "frac_of_bf16_burst_peak": fl / t / 1e12 / peaks["bf16_tflops"]}
+    del norm, ffn, x, r, dy
+    torch.cuda.empty_cache()
+    # ---- 90B shape prefill on one GPU (config 5 at p = 1)
+    H, I, T = 8192, 28672, 8192
+    wg, wu, wd = uni(I, H), uni(I, H), uni(H, I)
+    gamma = (1 + 0.1 * torch.randn(H, device=dev, generator=gen)).to(dt)
+    xs2, rs2 = [rnd(T, H) for _ in range(2)], [rnd(T, H) for _ in range(2)]
+
+    def pre90():
+        i = nx() % 2
+        ops.ffn_forward(ops.add_rmsnorm_forward(xs2[i], gamma, rs2[i], EPS, want_rms=False)[0], wg, wu, wd)
+    t = _time_cuda(pre90, 10, warm=3)
+    fl = 6.0 * T * H * I
+    out["prefill_90b_8192tok"] = {"ms": t * 1e3, "tokens_per_s": T / t, "TFLOPs": fl / t / 1e12,
+                                  "frac_of_bf16_burst_peak": fl / t / 1e12 / peaks["bf16_tflops"],
+                                  "frac_of_bf16_sustained_peak": fl / t / 1e12 / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch.distributed as dist
     import llama32_b200 as L
     from llama32_b200 import _lib, ops
-    from llama32_b200.tp import TensorParallelFFN
+    from llama32_b200.tp import FusedTensorParallelBlock, TensorParallelFFN, TpRankBuffers
 
     hidden, inter, batch, seq, label = WORKLOADS[args.workload]
     tokens = batch * seq
@@ -213,8 +309,17 @@ def run_ours(args):
     xs = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)]
     rs = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)]
     dys = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)] if train else None
-    tp = TensorParallelFFN(ffn, chunks=args.tp_chunks) if world > 1 else None
-    if tp is not None:
+    tp = fused = None
+    if world > 1 and args.tp_impl == "nccl":
+        tp = TensorParallelFFN(ffn, chunks=args.tp_chunks)
+    elif world > 1:
+        bufs = TpRankBuffers.symmetric(tokens, hidden, dt, dev)
+        fused = FusedTensorParallelBlock(norm.weight.detach(), EPS, ffn.swiglu.w_gate.detach(), ffn.swiglu.w_up.detach(),
+                                         ffn.w_down.weight.detach(), bufs)
+        lo, hi, _ = fused.rows_of(tokens)
+        xs_loc = [x.view(tokens, hidden)[lo:hi].contiguous() for x in xs]   # sequence-parallel: this rank's rows only
+        rs_loc = [r.view(tokens, hidden)[lo:hi].contiguous() for r in rs]
+    if world > 1:
         ffn = None                                     # the unsharded copy is not needed any more
         torch.cuda.empty_cache()
     if train:
@@ -232,6 +337,17 @@ def run_ours(args):
             y.backward(dys[i % nbuf])
             return y
         with torch.no_grad():
+            if fused is not None:
+                if instrument:
+                    fused.phase_norm(xs_loc[i % nbuf], rs_loc[i % nbuf], tokens)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    fused.phase_gate_up(tokens)
+                    e1.record()
+                    k_ev.append((e0, e1))
+                    fused.phase_down(tokens)
+                    return fused.phase_reduce(tokens)
+                return fused.forward(xs_loc[i % nbuf], rs_loc[i % nbuf], tokens)
             normed = norm(x, residual=r)
             if tp is not None:
                 return tp(normed)
@@ -265,7 +381,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        step(i, instrument=(world == 1 and not train))
+        step(i, instrument=((world == 1 or fused is not None) and not train))
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -280,11 +396,16 @@ def run_ours(args):
     value = tokens / (ms_step * 1e-3)
 
     # ---- timed region 2: end to end through the module API with pinned host buffers
-    h_x = [torch.randn(batch, seq, hidden).to(dt).pin_memory() for _ in range(nbuf)]
-    h_r = [torch.randn(batch, seq, hidden).to(dt).pin_memory() for _ in range(nbuf)]
-    h_y = [torch.empty(batch, seq, hidden, dtype=dt).pin_memory() for _ in range(nbuf)]
-    d_x = [torch.empty(batch, seq, hidden, device=dev, dtype=dt) for _ in range(nbuf)]
-    d_r = [torch.empty(batch, seq, hidden, device=dev, dtype=dt) for _ in range(nbuf)]
+    if fused is not None:
+        lo, hi, _ = fused.rows_of(tokens)
+        io_shape = (hi - lo, hidden)                   # every rank moves only its own rows over PCIe
+    else:
+        io_shape = (batch, seq, hidden)
+    h_x = [torch.randn(*io_shape).to(dt).pin_memory() for _ in range(nbuf)]
+    h_r = [torch.randn(*io_shape).to(dt).pin_memory() for _ in range(nbuf)]
+    h_y = [torch.empty(*io_shape, dtype=dt).pin_memory() for _ in range(nbuf)]
+    d_x = [torch.empty(*io_shape, device=dev, dtype=dt) for _ in range(nbuf)]
+    d_r = [torch.empty(*io_shape, device=dev, dtype=dt) for _ in range(nbuf)]
     s_h2d, s_d2h, s_cmp = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
     ev_in = [torch.cuda.Event() for _ in range(nbuf)]
     ev_cmp = [torch.cuda.Event() for _ in range(nbuf)]
@@ -300,8 +421,11 @@ def run_ours(args):
                 ev_in[b].record(s_h2d)
             s_cmp.wait_event(ev_in[b])
             with torch.no_grad():
-                normed = norm(d_x[b], residual=d_r[b])
-                y = tp(normed) if tp is not None else ffn(normed)
+                if fused is not None:
+                    y = fused.forward(d_x[b], d_r[b], tokens)
+                else:
+                    normed = norm(d_x[b], residual=d_r[b])
+                    y = tp(normed) if tp is not None else ffn(normed)
             ev_cmp[b].record(s_cmp)
             with torch.cuda.stream(s_d2h):
                 s_d2h.wait_event(ev_cmp[b])
@@ -325,11 +449,13 @@ def run_ours(args):
             t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t.item())
-        per_tensor = tokens * hidden * 2
+        per_tensor = h_x[0].numel() * 2
+        api = ("llama32_b200.LLAMARMSNorm + FusedFeedforward modules" if world == 1 else
+               ("llama32_b200.tp.FusedTensorParallelBlock.forward (bytes are per rank: each rank moves its own rows)"
+                if fused is not None else "llama32_b200.LLAMARMSNorm + tp.TensorParallelFFN"))
         e2e = {"value": tokens / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                "h2d_bytes_per_step": 2 * per_tensor, "d2h_bytes_per_step": per_tensor,
-               "api": "llama32_b200.LLAMARMSNorm + FusedFeedforward modules; pinned host buffers, copies on side "
-                      "streams double-buffered against compute"}
+               "api": api + "; pinned host buffers, copies on side streams double-buffered against compute"}
 
     if rank != 0:
         if world > 1:
@@ -342,15 +468,24 @@ def run_ours(args):
     if k_ev:
         torch.cuda.synchronize()
         k_ms = statistics.mean(a.elapsed_time(b) for a, b in k_ev)
-        alg_flops = 4.0 * tokens * hidden * inter          # gate + up GEMMs: 4*H*I flop per token
+        alg_flops = 4.0 * tokens * hidden * inter / world  # gate + up GEMMs: 4*H*I flop per token, per rank
         achieved = alg_flops / (k_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "gemm_kernel<cta_group 2, EPI_SWIGLU, bf16> (fused gate/up + SiLU*mul)",
+        kname = "gemm_kernel<cta_group 2, EPI_SWIGLU, bf16> (fused gate/up + SiLU*mul)"
+        if world > 1:
+            kname += f", all-gather of {(world - 1) * tokens // world} rows pulled over NVLink inside the kernel (rank 0's timing)"
+        roofline = {"bound": "tensor", "kernel": kname,
                     "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_tflops"], "peak_source": peaks["source"] + ", burst figure",
                     "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
                     "frac_of_sustained_peak": (achieved / peaks["bf16_tflops_sustained"]) if peaks["bf16_tflops_sustained"] else None,
                     "traffic": None, "traffic_note": "see profiles/ for dram__bytes of this kernel from ncu --set full"}
     step_tflops = flops_step / (ms_step * 1e-3) / 1e12
+
+    extra = None
+    if world == 1 and not train and not args.no_extra:
+        del xs, rs, d_x, d_r
+        torch.cuda.empty_cache()
+        extra = extra_numbers(dev, peaks)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -366,11 +501,13 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": label + (" fwd+bwd (all weights trainable)" if train else " forward"),
                    "hidden": hidden, "hidden_dim": inter, "global_batch_tokens": tokens,
-                   "parallelism": f"tp{world}" if world > 1 else "single-gpu",
+                   "parallelism": (f"tp{world} ({args.tp_impl}), sequence-parallel norm" if world > 1 else "single-gpu"),
                    "l2_policy": "inputs larger than L2: ~0.85 GB touched per step, 2 rotating activation buffers",
                    "step_tflops": step_tflops, "step_frac_of_bf16_peak": step_tflops * (1 if world == 1 else 1.0 / world) / peaks["bf16_tflops"]},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }
+    if extra is not None:
+        line["extra"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -385,7 +522,9 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="11b")
     ap.add_argument("--mode", choices=["prefill", "train"], default="prefill")
     ap.add_argument("--tp-chunks", type=int, default=4)
+    ap.add_argument("--tp-impl", choices=["fused", "nccl"], default="fused")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (RMSNorm GB/s, decode, 90B, train)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

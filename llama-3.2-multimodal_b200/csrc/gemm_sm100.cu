@@ -38,6 +38,7 @@ constexpr int kUmmaK = 16;
 constexpr int kAccCols = 256;  // TMEM columns per accumulator stage (= UMMA N)
 constexpr int kThreads = 256;
 constexpr int kAtomBytes = kBlockK * 128;   // 64 rows x 128 B = 8 KiB: one swizzle-atom column of a tile
+constexpr int kEpiStageBytes = 32 * 128;    // per epilogue warp: 32 rows x 128 B transpose buffer (EPI_STORE)
 
 template <int kCtaGroup>
 struct TileCfg {
@@ -47,7 +48,7 @@ struct TileCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (kCtaGroup == 2) ? 6 : 4;
     static constexpr int kNumBarriers = 2 * kStages + 4;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kNumBarriers * 8 + 16 + 1024 /* alignment slack */;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 4 * kEpiStageBytes + kNumBarriers * 8 + 16 + 1024 /* alignment slack */;
 };
 
 struct GemmKernelParams {
@@ -91,6 +92,15 @@ L32_DEVICE void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32
 L32_DEVICE uint4 ld_global_nc_v4(const void* p) {
     uint4 r;
     asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+L32_DEVICE void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+L32_DEVICE uint4 ld_shared_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)) : "memory");
     return r;
 }
 
@@ -171,7 +181,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + 4 * kEpiStageBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tfull_bar = empty_bar + kStages;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -314,33 +325,62 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * kAccCols;
 
             if constexpr (kEpi == EPI_STORE) {
-                // reduce-scatter fused into the epilogue: the row goes to the rank that owns it (peer store)
-                uint8_t* d_row = static_cast<uint8_t*>(p.d[0]) + row_off * esz;
-                if (p.rs.world > 0 && row_ok) {
-                    int owner = row / p.rs.rows_per_rank;
-                    if (owner >= p.rs.world) owner = p.rs.world - 1;
-                    d_row = static_cast<uint8_t*>(p.rs.peer_dst[owner]) +
-                            static_cast<size_t>(row - owner * p.rs.rows_per_rank) * static_cast<size_t>(p.ldd) * esz;
-                }
+                // Rows leave through a per-warp shared-memory transpose so that every store instruction writes whole
+                // 128-byte row segments (4 rows x 128 B per instruction) instead of 32 scattered 16-byte pieces: that
+                // is what NVLink needs when the reduce-scatter is fused in (the row then goes straight to the rank
+                // that owns it, a peer store), and it is friendlier to the local L2 as well.
+                uint8_t* stage = epi_stage + q * kEpiStageBytes;
+                const int warp_row0 = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM + q * 32;
+                const T* bias = static_cast<const T*>(p.bias[0]);
 #pragma unroll 1
-                for (int c = 0; c < kAccCols / 32; ++c) {
-                    const int col = n0 + c * 32;
+                for (int c = 0; c < kAccCols / 64; ++c) {
+                    const int col = n0 + c * 64;
                     if (col >= p.n) break;
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(taddr + c * 32, v);
-                    tmem_ld_wait();
-                    uint32_t o[16];
-                    const T* bias = static_cast<const T*>(p.bias[0]);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float lo = __uint_as_float(v[2 * j]), hi = __uint_as_float(v[2 * j + 1]);
-                        if (bias != nullptr) {
-                            if (col + 2 * j < p.n) lo += static_cast<float>(bias[col + 2 * j]);
-                            if (col + 2 * j + 1 < p.n) hi += static_cast<float>(bias[col + 2 * j + 1]);
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + c * 64 + half * 32, v);
+                        tmem_ld_wait();
+                        const int hcol = col + half * 32;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            uint32_t o[4];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = j4 * 4 + jj;
+                                float lo = __uint_as_float(v[2 * j]), hi = __uint_as_float(v[2 * j + 1]);
+                                if (bias != nullptr) {
+                                    if (hcol + 2 * j < p.n) lo += static_cast<float>(bias[hcol + 2 * j]);
+                                    if (hcol + 2 * j + 1 < p.n) hi += static_cast<float>(bias[hcol + 2 * j + 1]);
+                                }
+                                o[jj] = Pack2<T>::pack(lo, hi);
+                            }
+                            const uint32_t chunk = static_cast<uint32_t>(half * 4 + j4) ^ (lane & 7u);   // XOR swizzle
+                            st_shared_v4(stage + lane * 128u + chunk * 16u, o[0], o[1], o[2], o[3]);
                         }
-                        o[j] = Pack2<T>::pack(lo, hi);
                     }
-                    if (row_ok) store_row32(d_row + static_cast<size_t>(col) * esz, o, p.n - col);
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const uint32_t r = static_cast<uint32_t>(it) * 4u + (lane >> 3);
+                        const uint32_t ch = lane & 7u;
+                        const uint4 val = ld_shared_v4(stage + r * 128u + ((ch ^ (r & 7u)) * 16u));
+                        const int grow = warp_row0 + static_cast<int>(r);
+                        const int gcol = col + static_cast<int>(ch) * 8;
+                        if (grow < p.m && gcol < p.n) {
+                            uint8_t* dst;
+                            if (p.rs.world > 0) {
+                                int owner = grow / p.rs.rows_per_rank;
+                                if (owner >= p.rs.world) owner = p.rs.world - 1;
+                                dst = static_cast<uint8_t*>(p.rs.peer_dst[owner]) +
+                                      static_cast<size_t>(grow - owner * p.rs.rows_per_rank) * static_cast<size_t>(p.ldd) * esz;
+                            } else {
+                                dst = static_cast<uint8_t*>(p.d[0]) + static_cast<size_t>(grow) * static_cast<size_t>(p.ldd) * esz;
+                            }
+                            st_global_v4(dst + static_cast<size_t>(gcol) * esz, val.x, val.y, val.z, val.w);
+                        }
+                    }
+                    __syncwarp();
                 }
             } else if constexpr (kEpi == EPI_SWIGLU) {
 #pragma unroll 1

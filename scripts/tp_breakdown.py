@@ -1,0 +1,81 @@
+"""Per-phase timing of the fused tensor-parallel block (torchrun, one process per GPU).
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/tp_breakdown.py [11b|90b] [tokens]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from llama32_b200.tp import FusedTensorParallelBlock, TpRankBuffers  # noqa: E402
+
+
+def main():
+    wl = sys.argv[1] if len(sys.argv) > 1 else "11b"
+    tokens = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+    hidden, inter = (4096, 14336) if wl == "11b" else (8192, 28672)
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    dt = torch.bfloat16
+    torch.manual_seed(0)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    gamma = (1 + 0.1 * torch.randn(hidden, device=dev, generator=gen)).to(dt)
+    wg = ((torch.rand(inter, hidden, device=dev, generator=gen) * 2 - 1) / hidden ** 0.5).to(dt)
+    wu = ((torch.rand(inter, hidden, device=dev, generator=gen) * 2 - 1) / hidden ** 0.5).to(dt)
+    wd = ((torch.rand(hidden, inter, device=dev, generator=gen) * 2 - 1) / inter ** 0.5).to(dt)
+    bufs = TpRankBuffers.symmetric(tokens, hidden, dt, dev)
+    blk = FusedTensorParallelBlock(gamma, 1e-5, wg, wu, wd, bufs)
+    del wg, wu, wd
+    lo, hi, _ = blk.rows_of(tokens)
+    xs = [torch.randn(hi - lo, hidden, device=dev, generator=gen).to(dt) for _ in range(2)]
+    rs = [torch.randn(hi - lo, hidden, device=dev, generator=gen).to(dt) for _ in range(2)]
+    names = ["norm+signal", "gate/up+allgather", "down+reduce-scatter+signal", "reduce"]
+    acc = [0.0] * 4
+    iters, warm = 30, 5
+    for i in range(iters + warm):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record()
+        blk.phase_norm(xs[i % 2], rs[i % 2], tokens)
+        ev[1].record()
+        blk.phase_gate_up(tokens)
+        ev[2].record()
+        blk.phase_down(tokens)
+        ev[3].record()
+        blk.phase_reduce(tokens)
+        ev[4].record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            for k in range(4):
+                acc[k] += ev[k].elapsed_time(ev[k + 1])
+    # back-to-back steps (no barrier in between): the number bench.py reports
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        blk.forward(xs[i % 2], rs[i % 2], tokens)
+    e1.record()
+    torch.cuda.synchronize()
+    total = e0.elapsed_time(e1) / iters
+    t = torch.tensor(acc + [total], device=dev, dtype=torch.float64)
+    gathered = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    if rank == 0:
+        fl_gu = 4.0 * tokens * hidden * inter / world
+        fl_dn = 2.0 * tokens * hidden * inter / world
+        for r, g in enumerate(gathered):
+            g = g.tolist()
+            ph = [v / iters for v in g[:4]]
+            print(f"{wl} p={world} tokens={tokens} rank {r}: " + "  ".join(f"{n} {v * 1e3:.0f} us" for n, v in zip(names, ph)) +
+                  f" | gate/up {fl_gu / ph[1] / 1e9:.0f} TF/s down {fl_dn / ph[2] / 1e9:.0f} TF/s | sum {sum(ph):.3f} ms | back-to-back {g[4]:.3f} ms "
+                  f"= {tokens / g[4] / 1e3:.2f} M tok/s", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
