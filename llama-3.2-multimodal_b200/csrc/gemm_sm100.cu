@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 namespace l32 {
 namespace {
@@ -64,6 +65,7 @@ struct GemmKernelParams {
     const void* e[2];
     const void* bias[2];
     long long ldd;
+    int n_act;              // EPI_SWIGLU: act columns per tile (UMMA N = 2 * n_act), multiple of 16, <= 128
     int m_rotate;           // m-tiles are visited starting at this tile index (wrapping around)
     TpAllGather ag;         // all-gather of A fused into the kernel (world == 0: off)
     TpReduceScatter rs;     // reduce-scatter fused into the EPI_STORE epilogue (world == 0: off)
@@ -123,7 +125,7 @@ L32_DEVICE TileCoord tile_coord(int t, int tiles_m, int tiles_n, int group, int 
 // All-gather fused into the kernel: this warp's share of pulling chunk after chunk of A rows out of peer memory
 // (NVLink loads that bypass the non-coherent L1) into the local A buffer, in the order the tiles consume them.
 L32_DEVICE void ag_pull(const TpAllGather& ag, int m, size_t row_bytes, int puller, int num_pullers, uint32_t lane) {
-    constexpr int kUnroll = 8;
+    constexpr int kUnroll = 16;
     for (int j = 1; j < ag.world; ++j) {
         const int s = (ag.rank + j) % ag.world;
         const long long r0 = static_cast<long long>(s) * ag.rows_per_rank;
@@ -175,7 +177,10 @@ template <int kCtaGroup, int kEpi, typename T>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmKernelParams p) {
     using Cfg = TileCfg<kCtaGroup>;
     constexpr int kStages = Cfg::kStages;
-    constexpr int kTileNOut = (kEpi == EPI_SWIGLU) ? 128 : 256;   // output columns per tile
+    const int kTileNOut = (kEpi == EPI_SWIGLU) ? p.n_act : 256;   // output columns per tile
+    // bytes the pair's TMA loads deliver per ring stage (EPI_SWIGLU stages n_act gate + n_act up weight rows)
+    const uint32_t stage_tx = (kEpi == EPI_SWIGLU) ? static_cast<uint32_t>(kCtaGroup * Cfg::kABytes + 2 * p.n_act * 128)
+                                                   : static_cast<uint32_t>(Cfg::kStageBytes * kCtaGroup);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
                         uint8_t* sa = smem_a + stage * Cfg::kABytes;
                         uint8_t* sb = smem_b + stage * Cfg::kBBytes;
-                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCtaGroup);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
                         load_tile<kCtaGroup>(&p.map_a[ph], sa, &full_bar[stage], p.a_mn_major, m0, kBlockM, kb * kBlockK);
                         if constexpr (kEpi == EPI_SWIGLU) {
                             if constexpr (kCtaGroup == 2) {
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                                 load_tile<2>(&p.map_b[rank], sb, &full_bar[stage], 0, n0, 128, kb * kBlockK);
                             } else {
                                 load_tile<1>(&p.map_b[0], sb, &full_bar[stage], 0, n0, 128, kb * kBlockK);
-                                load_tile<1>(&p.map_b[1], sb + 128 * 128, &full_bar[stage], 0, n0, 128, kb * kBlockK);
+                                load_tile<1>(&p.map_b[1], sb + p.n_act * 128, &full_bar[stage], 0, n0, 128, kb * kBlockK);
                             }
                         } else {
                             load_tile<kCtaGroup>(&p.map_b[ph], sb, &full_bar[stage], p.b_mn_major,
@@ -383,19 +388,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     __syncwarp();
                 }
             } else if constexpr (kEpi == EPI_SWIGLU) {
-#pragma unroll 1
-                for (int c = 0; c < 128 / 32; ++c) {
-                    const int col = n0 + c * 32;
-                    if (col >= p.n) break;
-                    uint32_t g[32], u[32];
-                    tmem_ld_32x32b_x32(taddr + c * 32, g);
-                    tmem_ld_32x32b_x32(taddr + 128 + c * 32, u);
-                    tmem_ld_wait();
-                    const T* bg = static_cast<const T*>(p.bias[0]);
-                    const T* bu = static_cast<const T*>(p.bias[1]);
+                // accumulator columns [0, n_act) = gate, [n_act, 2 n_act) = up of the same act columns
+                const T* bg = static_cast<const T*>(p.bias[0]);
+                const T* bu = static_cast<const T*>(p.bias[1]);
+                auto finish = [&](auto& g, auto& u, int col, auto ncols_tag) {
+                    constexpr int kCols = decltype(ncols_tag)::value;
                     if (bg != nullptr || bu != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
+                        for (int j = 0; j < kCols; ++j) {
                             if (col + j < p.n) {
                                 if (bg != nullptr) g[j] = __float_as_uint(__uint_as_float(g[j]) + static_cast<float>(bg[col + j]));
                                 if (bu != nullptr) u[j] = __float_as_uint(__uint_as_float(u[j]) + static_cast<float>(bu[col + j]));
@@ -404,20 +404,41 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     }
                     uint32_t o[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 16; ++j) o[j] = 0;
+#pragma unroll
+                    for (int j = 0; j < kCols / 2; ++j) {
                         const float g0 = __uint_as_float(g[2 * j]), g1 = __uint_as_float(g[2 * j + 1]);
                         const float u0 = __uint_as_float(u[2 * j]), u1 = __uint_as_float(u[2 * j + 1]);
                         o[j] = Pack2<T>::pack(silu_f32(g0) * u0, silu_f32(g1) * u1);
                     }
-                    if (row_ok) store_row32(static_cast<uint8_t*>(p.d[0]) + (row_off + col) * esz, o, p.n - col);
+                    const int n_valid = min(p.n - col, kCols);
+                    if (row_ok) store_row32(static_cast<uint8_t*>(p.d[0]) + (row_off + col) * esz, o, n_valid);
                     if (p.d[1] != nullptr) {   // backward caches
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = Pack2<T>::pack(__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1]));
-                        if (row_ok) store_row32(static_cast<uint8_t*>(p.d[1]) + (row_off + col) * esz, o, p.n - col);
+                        for (int j = 0; j < kCols / 2; ++j) o[j] = Pack2<T>::pack(__uint_as_float(g[2 * j]), __uint_as_float(g[2 * j + 1]));
+                        if (row_ok) store_row32(static_cast<uint8_t*>(p.d[1]) + (row_off + col) * esz, o, n_valid);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = Pack2<T>::pack(__uint_as_float(u[2 * j]), __uint_as_float(u[2 * j + 1]));
-                        if (row_ok) store_row32(static_cast<uint8_t*>(p.d[2]) + (row_off + col) * esz, o, p.n - col);
+                        for (int j = 0; j < kCols / 2; ++j) o[j] = Pack2<T>::pack(__uint_as_float(u[2 * j]), __uint_as_float(u[2 * j + 1]));
+                        if (row_ok) store_row32(static_cast<uint8_t*>(p.d[2]) + (row_off + col) * esz, o, n_valid);
                     }
+                };
+                int c0 = 0;
+#pragma unroll 1
+                for (; c0 + 32 <= p.n_act; c0 += 32) {
+                    const int col = n0 + c0;
+                    if (col >= p.n) break;
+                    uint32_t g[32], u[32];
+                    tmem_ld_32x32b_x32(taddr + c0, g);
+                    tmem_ld_32x32b_x32(taddr + p.n_act + c0, u);
+                    tmem_ld_wait();
+                    finish(g, u, col, std::integral_constant<int, 32>{});
+                }
+                if (c0 < p.n_act && n0 + c0 < p.n) {   // n_act = 32 k + 16: one 16-column tail
+                    uint32_t g[16], u[16];
+                    tmem_ld_32x32b_x16(taddr + c0, g);
+                    tmem_ld_32x32b_x16(taddr + p.n_act + c0, u);
+                    tmem_ld_wait();
+                    finish(g, u, n0 + c0, std::integral_constant<int, 16>{});
                 }
             } else {   // EPI_SWIGLU_BWD
 #pragma unroll 1
@@ -593,17 +614,38 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
     kp.num_phases = g.num_phases;
     kp.a_mn_major = g.a[0].mn_major;
     kp.b_mn_major = g.b[0].mn_major;
-    const int tile_n_out = (g.epilogue == EPI_SWIGLU) ? 128 : 256;
     const int tile_m = kBlockM * cta_group;
     kp.tiles_m = (g.m + tile_m - 1) / tile_m;
+    // EPI_SWIGLU: pick the act-column tile width (multiple of 16) that minimises waves x tile cost -- e.g. a
+    // tensor-parallel shard of 1792 act columns is 7 waves of 112 columns instead of 7 waves of 128 (the last one
+    // nearly empty).  Ties go to the wider tile.
+    int n_act = 128;
+    if (g.epilogue == EPI_SWIGLU) {
+        int ctas = num_sms();
+        if (g.max_ctas > 0 && g.max_ctas < ctas) ctas = g.max_ctas;
+        const long long clusters = ctas / cta_group > 0 ? ctas / cta_group : 1;
+        long long best = -1;
+        for (int cand = 128; cand >= 64; cand -= 16) {
+            const long long tiles = static_cast<long long>(kp.tiles_m) * ((g.n + cand - 1) / cand);
+            const long long cost = ((tiles + clusters - 1) / clusters) * (cand + 12);   // + fixed per-tile overhead
+            if (best < 0 || cost < best) { best = cost; n_act = cand; }
+        }
+        if (const char* env = getenv("L32_SWIGLU_TILE_N")) {   // tuning knob for experiments only
+            const int v = atoi(env);
+            if (v >= 16 && v <= 128 && (v % 16) == 0) n_act = v;
+        }
+    }
+    kp.n_act = n_act;
+    const int tile_n_out = (g.epilogue == EPI_SWIGLU) ? n_act : 256;
     kp.tiles_n = (g.n + tile_n_out - 1) / tile_n_out;
     kp.raster_group = g.raster_group > 0 ? g.raster_group : 16 / cta_group;
     if (const char* env = getenv("L32_RASTER_GROUP")) {   // tuning knob for experiments only
         const int v = atoi(env);
         if (v > 0) kp.raster_group = v;
     }
-    kp.idesc = make_idesc_f16(g.dtype == L32_BF16, static_cast<uint32_t>(tile_m), kAccCols, g.a[0].mn_major != 0,
-                              g.b[0].mn_major != 0);
+    kp.idesc = make_idesc_f16(g.dtype == L32_BF16, static_cast<uint32_t>(tile_m),
+                              g.epilogue == EPI_SWIGLU ? static_cast<uint32_t>(2 * n_act) : static_cast<uint32_t>(kAccCols),
+                              g.a[0].mn_major != 0, g.b[0].mn_major != 0);
     for (int i = 0; i < 3; ++i) kp.d[i] = g.d[i];
     kp.e[0] = g.e[0]; kp.e[1] = g.e[1];
     kp.bias[0] = g.bias[0]; kp.bias[1] = g.bias[1];
@@ -637,7 +679,7 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
     }
     if (g.epilogue == EPI_SWIGLU) {
         for (int i = 0; i < 2; ++i) {
-            int rc = make_tensor_map_2d(&kp.map_b[i], g.b[i].ptr, g.n, g.k[0], g.b[i].ld, 128, kBlockK, g.dtype);
+            int rc = make_tensor_map_2d(&kp.map_b[i], g.b[i].ptr, g.n, g.k[0], g.b[i].ld, n_act, kBlockK, g.dtype);
             if (rc != L32_OK) return rc;
         }
     }

@@ -144,6 +144,22 @@ def prefill(H, I, T):
     os.environ.pop("L32_RASTER_GROUP", None)
 
 
+def tp_shapes():
+    """The per-rank GEMMs of the tensor-parallel path, run locally (no NVLink): isolates wave quantisation / short-K
+    effects from the cost of the fused collectives."""
+    T = 8192
+    for name, H, I in (("11b", 4096, 14336), ("90b", 8192, 28672)):
+        for p in (2, 4, 8):
+            Il = I // p
+            wg, wu, wd = weights(H, Il)
+            x = torch.randn(T, H, device="cuda").bfloat16()
+            act = torch.randn(T, Il, device="cuda").bfloat16()
+            t1 = timeit(lambda: ops.swiglu_forward(x, wg, wu), iters=20)
+            t2 = timeit(lambda: ops.linear_forward(act, wd), iters=20)
+            print(f"tp-shape {name} p={p} I/p={Il}: gate/up {t1 * 1e3:.0f} us ({4.0 * T * H * Il / t1 / 1e9:.0f} TF/s)  "
+                  f"down {t2 * 1e3:.0f} us ({2.0 * T * H * Il / t2 / 1e9:.0f} TF/s)", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     if what == "decode":
@@ -154,6 +170,8 @@ if __name__ == "__main__":
         decode(8192, 28672, nsets=2, batches=(1, 64, 128), knobs=({}, {"L32_DECODE_ROTATE": 0}))
     elif what == "train":
         train(4096, 14336, 8192)
+    elif what == "tp_shapes":
+        tp_shapes()
     elif what == "norm":
         norm(4096, 8192)
         norm(8192, 8192)
