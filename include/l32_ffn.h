@@ -125,6 +125,18 @@ L32_API int l32_ffn_forward(const void* x, const void* w_gate, const void* w_up,
                     const void* b_up, const void* b_down, void* y, void* act_ws, void* gate_cache, void* up_cache,
                     int64_t tokens, int hidden, int inter, int dtype, void* stream);
 
+/* Tail of the decoder block in one call: normed = rmsnorm(attn_out + residual) * norm_weight;
+ * out = attn_out + ff(normed)   -- the "+ attn_out" rides in the epilogue of the down GEMM.
+ * Replaces: TransformerBlock.forward lines norm2 / ff / return, Model/model.py:270-273 (three module calls and one
+ *           elementwise add in the reference).  The reference drops `residual` from the block output (SURVEY.md
+ *           section 0.6); so does this.  Inference only (no caches).  The sum is formed the way the reference's
+ *           16-bit path forms it: ff_out rounded to `dtype`, then added to attn_out and rounded again.
+ *   normed_ws : [tokens, hidden] scratch;  act_ws : [tokens, inter] scratch;  out may NOT alias attn_out.
+ */
+L32_API int l32_block_tail_forward(const void* attn_out, const void* residual, const void* norm_weight, float eps,
+                                   const void* w_gate, const void* w_up, const void* w_down, void* out, void* normed_ws,
+                                   void* act_ws, int64_t tokens, int hidden, int inter, int dtype, void* stream);
+
 /* Whole feed-forward backward (down projection included).
  *   dy : [tokens, hidden].  Outputs (each optional): dx [tokens, hidden], dw_gate / dw_up [inter, hidden]
  *   (both or neither), dw_down [hidden, inter].
@@ -137,6 +149,30 @@ L32_API int l32_ffn_backward(const void* dy, const void* x, const void* w_gate, 
                      const void* gate_cache, const void* up_cache, void* dx, void* dw_gate, void* dw_up,
                      void* dw_down, void* workspace, size_t workspace_bytes, int64_t tokens, int hidden, int inter,
                      int dtype, void* stream);
+
+/* Feed-forward whose down projection carries a LoRA adapter: y = act w_down^T + (act lora_a^T) lora_bs^T.
+ * Replaces: Linear_LORA.forward (Model/model.py:120-121) swapped into FusedFeedforward.w_down by the fine-tuning
+ *           recipe of README.md:179-188 (rank 16, alpha 32); the adapter rides in the down GEMM as a second
+ *           accumulation phase of K = rank, so the [tokens, hidden] LoRA term never exists in HBM.
+ *   lora_a  : [rank, inter];  lora_bs : [hidden, rank], ALREADY multiplied by alpha / rank;  rank % 8 == 0, rank <= 64.
+ *   t_out   : [tokens, rank] receives act lora_a^T (needed by the backward);  act_ws : [tokens, inter] scratch.
+ *   (LoRA dropout is the caller's business: with p > 0 in training mode the host layer uses the unfused path.)
+ */
+L32_API int l32_ffn_lora_forward(const void* x, const void* w_gate, const void* w_up, const void* w_down, const void* lora_a,
+                                 const void* lora_bs, void* y, void* act_ws, void* t_out, void* gate_cache, void* up_cache,
+                                 int64_t tokens, int hidden, int inter, int rank, int dtype, void* stream);
+
+/* Backward of l32_ffn_lora_forward with a frozen base w_down (no dw_down).
+ *   Outputs (each optional): dx, dw_gate / dw_up (both or neither), dlora_a [rank, inter], dlora_bs [hidden, rank]
+ *   (gradient w.r.t. the SCALED matrix; multiply by alpha / rank for lora_b).
+ *   workspace : l32_ffn_lora_backward_workspace_bytes(tokens, inter, rank) bytes.
+ */
+L32_API size_t l32_ffn_lora_backward_workspace_bytes(int64_t tokens, int inter, int rank);
+L32_API int l32_ffn_lora_backward(const void* dy, const void* x, const void* w_gate, const void* w_up, const void* w_down,
+                                  const void* lora_a, const void* lora_bs, const void* t, const void* gate_cache,
+                                  const void* up_cache, void* dx, void* dw_gate, void* dw_up, void* dlora_a, void* dlora_bs,
+                                  void* workspace, size_t workspace_bytes, int64_t tokens, int hidden, int inter, int rank,
+                                  int dtype, void* stream);
 
 /* General tiled GEMM used by the entry points above (exposed for tests, tuning and the tensor-parallel
  * host code):  D[m,n] = A[m,k] B[n,k]^T  (+ A1 B1^T when a1 != NULL).
@@ -158,6 +194,10 @@ L32_API int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, 
 
 /* flag[index] := value on every rank, after everything this stream did before is visible system-wide. */
 L32_API int l32_tp_signal(void* const* peer_flags, int world, int index, uint32_t value, void* stream);
+
+/* Plain SM copy between (peer) buffers: the NVLink bandwidth reference for the fused kernels (pull when src is peer
+ * memory, push when dst is).  bytes % 16 == 0; `ctas` CTAs of `warps` warps, `unroll` (4, 8 or 16) loads in flight per lane. */
+L32_API int l32_tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, void* stream);
 
 /* Fused all-gather + gate/up projection + SiLU*mul.
  *   x_full   : this rank's [tokens, hidden] activation buffer; only rows [rank*rows_per_rank, ...) are valid on

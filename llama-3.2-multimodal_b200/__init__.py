@@ -4,6 +4,7 @@ The directory name is not a Python identifier; import it as `llama32_b200` (alia
 """
 from .modules import (  # noqa: F401
     FFNFunction,
+    FFNLoRAFunction,
     FusedFeedForward,
     FusedFeedforward,
     FusedSwiGLU,
@@ -12,13 +13,14 @@ from .modules import (  # noqa: F401
     LinearFunction,
     RMSNormFunction,
     SwiGLUFunction,
+    block_tail,
     convert_feedforward_to_fused,
     convert_instances,
     patch_reference,
 )
 
 __all__ = [
-    "FFNFunction", "FusedFeedForward", "FusedFeedforward", "FusedSwiGLU", "LLAMARMSNorm", "Linear_LORA",
-    "LinearFunction", "RMSNormFunction", "SwiGLUFunction", "convert_feedforward_to_fused", "convert_instances",
+    "FFNFunction", "FFNLoRAFunction", "FusedFeedForward", "FusedFeedforward", "FusedSwiGLU", "LLAMARMSNorm", "Linear_LORA",
+    "LinearFunction", "RMSNormFunction", "SwiGLUFunction", "block_tail", "convert_feedforward_to_fused", "convert_instances",
     "patch_reference",
 ]

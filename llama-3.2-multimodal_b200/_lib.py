@@ -34,11 +34,16 @@ SIGNATURES = {
     "l32_swiglu_backward": (c_int, [c_void_p] * 10 + [c_size_t, c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_linear_forward": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_ffn_forward": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_int, c_void_p]),
+    "l32_block_tail_forward": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 6 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_ffn_backward_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "l32_ffn_backward": (c_int, [c_void_p] * 12 + [c_size_t, c_int64, c_int, c_int, c_int, c_void_p]),
+    "l32_ffn_lora_forward": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    "l32_ffn_lora_backward_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "l32_ffn_lora_backward": (c_int, [c_void_p] * 16 + [c_size_t, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "l32_gemm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p, c_int64,
                          c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "l32_swiglu_act": (c_int, [c_void_p] * 3 + [c_int64, c_int, c_void_p]),
+    "l32_tp_peer_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "l32_tp_signal": (c_int, [c_void_p, c_int, c_int, ctypes.c_uint32, c_void_p]),
     "l32_tp_swiglu_forward_allgather": (c_int, [c_void_p] * 4 + [ctypes.c_uint32, c_int, c_int, c_int64] + [c_void_p] * 7 +
                                         [c_int64, c_int, c_int, c_int, c_void_p]),

@@ -155,14 +155,41 @@ int l32_swiglu_forward(const void* x, const void* w_gate, const void* w_up, cons
     return gemm_sm100(g, as_stream(stream));
 }
 
+namespace {
+int linear_forward_add(const void* a, const void* w, const void* bias, const void* addend, void* y, int64_t tokens,
+                       int in_features, int out_features, int dtype, void* stream);
+}
+
 int l32_linear_forward(const void* a, const void* w, const void* bias, void* y, int64_t tokens, int in_features,
                        int out_features, int dtype, void* stream) {
+    return linear_forward_add(a, w, bias, nullptr, y, tokens, in_features, out_features, dtype, stream);
+}
+
+int l32_block_tail_forward(const void* attn_out, const void* residual, const void* norm_weight, float eps, const void* w_gate,
+                           const void* w_up, const void* w_down, void* out, void* normed_ws, void* act_ws, int64_t tokens,
+                           int hidden, int inter, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, inter)) return L32_ERR_BAD_SHAPE;
+    if (tokens == 0) return L32_OK;
+    if (attn_out == nullptr || norm_weight == nullptr || w_gate == nullptr || w_up == nullptr || w_down == nullptr || out == nullptr)
+        return L32_ERR_NULL;
+    if (normed_ws == nullptr || act_ws == nullptr) return L32_ERR_WORKSPACE;
+    int rc = l32_add_rmsnorm_forward(attn_out, residual, norm_weight, normed_ws, nullptr, nullptr, tokens, hidden, eps, dtype, stream);
+    if (rc != L32_OK) return rc;
+    rc = l32_swiglu_forward(normed_ws, w_gate, w_up, nullptr, nullptr, act_ws, nullptr, nullptr, tokens, hidden, inter, dtype, stream);
+    if (rc != L32_OK) return rc;
+    return linear_forward_add(act_ws, w_down, nullptr, attn_out, out, tokens, inter, hidden, dtype, stream);
+}
+
+namespace {
+int linear_forward_add(const void* a, const void* w, const void* bias, const void* addend, void* y, int64_t tokens,
+                       int in_features, int out_features, int dtype, void* stream) {
     if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
     if (!shapes_ok(tokens, in_features, out_features)) return L32_ERR_BAD_SHAPE;
     if (tokens == 0) return L32_OK;
     if (a == nullptr || w == nullptr || y == nullptr) return L32_ERR_NULL;
     if (tokens <= decode_max_tokens()) {
-        const int rc = ffn_decode_linear(a, w, bias, y, static_cast<int>(tokens), in_features, out_features, dtype,
+        const int rc = ffn_decode_linear(a, w, bias, addend, y, static_cast<int>(tokens), in_features, out_features, dtype,
                                          as_stream(stream));
         if (rc != L32_ERR_BAD_SHAPE) return rc;
     }
@@ -172,10 +199,12 @@ int l32_linear_forward(const void* a, const void* w, const void* bias, void* y, 
     g.b[0] = op(w, in_features, 0);
     g.epilogue = EPI_STORE;
     g.d[0] = y;
+    g.e[0] = addend;
     g.bias[0] = bias;
     g.ldd = out_features;
     return gemm_sm100(g, as_stream(stream));
 }
+}  // namespace
 
 int l32_ffn_forward(const void* x, const void* w_gate, const void* w_up, const void* w_down, const void* b_gate,
                     const void* b_up, const void* b_down, void* y, void* act_ws, void* gate_cache, void* up_cache,
@@ -290,6 +319,140 @@ int l32_ffn_backward(const void* dy, const void* x, const void* w_gate, const vo
     return rc;
 }
 
+int l32_ffn_lora_forward(const void* x, const void* w_gate, const void* w_up, const void* w_down, const void* lora_a,
+                         const void* lora_bs, void* y, void* act_ws, void* t_out, void* gate_cache, void* up_cache,
+                         int64_t tokens, int hidden, int inter, int rank, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, inter) || rank <= 0 || rank > 64 || (rank % 8) != 0) return L32_ERR_BAD_SHAPE;
+    if (tokens == 0) return L32_OK;
+    if (w_down == nullptr || lora_a == nullptr || lora_bs == nullptr || y == nullptr || t_out == nullptr) return L32_ERR_NULL;
+    if (act_ws == nullptr) return L32_ERR_WORKSPACE;
+    cudaStream_t s = as_stream(stream);
+    const int t = static_cast<int>(tokens);
+    // act through the tiled kernel: the small-M path has no two-phase down projection
+    GemmProblem g = blank(t, inter, dtype);
+    g.k[0] = hidden;
+    g.a[0] = op(x, hidden, 0);
+    g.b[0] = op(w_gate, hidden, 0);
+    g.b[1] = op(w_up, hidden, 0);
+    g.epilogue = EPI_SWIGLU;
+    g.d[0] = act_ws;
+    g.d[1] = gate_cache;
+    g.d[2] = up_cache;
+    g.ldd = inter;
+    if (x == nullptr || w_gate == nullptr || w_up == nullptr) return L32_ERR_NULL;
+    if ((gate_cache == nullptr) != (up_cache == nullptr)) return L32_ERR_NULL;
+    int rc = gemm_sm100(g, s);
+    if (rc != L32_OK) return rc;
+    // t = act lora_a^T  [tokens, rank]
+    g = blank(t, rank, dtype);
+    g.k[0] = inter;
+    g.a[0] = op(act_ws, inter, 0);
+    g.b[0] = op(lora_a, inter, 0);
+    g.epilogue = EPI_STORE;
+    g.d[0] = t_out;
+    g.ldd = rank;
+    rc = gemm_sm100(g, s);
+    if (rc != L32_OK) return rc;
+    // y = act w_down^T + t lora_bs^T : one kernel, two accumulation phases (K = inter, then K = rank)
+    g = blank(t, hidden, dtype);
+    g.num_phases = 2;
+    g.k[0] = inter;
+    g.k[1] = rank;
+    g.a[0] = op(act_ws, inter, 0);
+    g.b[0] = op(w_down, inter, 0);
+    g.a[1] = op(t_out, rank, 0);
+    g.b[1] = op(lora_bs, rank, 0);
+    g.epilogue = EPI_STORE;
+    g.d[0] = y;
+    g.ldd = hidden;
+    return gemm_sm100(g, s);
+}
+
+size_t l32_ffn_lora_backward_workspace_bytes(int64_t tokens, int inter, int rank) {
+    if (tokens < 0 || inter <= 0 || rank <= 0) return 0;
+    return 3 * align256(static_cast<size_t>(tokens) * inter * 2) + align256(static_cast<size_t>(tokens) * rank * 2);
+}
+
+int l32_ffn_lora_backward(const void* dy, const void* x, const void* w_gate, const void* w_up, const void* w_down,
+                          const void* lora_a, const void* lora_bs, const void* t_saved, const void* gate_cache,
+                          const void* up_cache, void* dx, void* dw_gate, void* dw_up, void* dlora_a, void* dlora_bs,
+                          void* workspace, size_t workspace_bytes, int64_t tokens, int hidden, int inter, int rank, int dtype,
+                          void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, inter) || rank <= 0 || rank > 64 || (rank % 8) != 0) return L32_ERR_BAD_SHAPE;
+    if ((dw_gate == nullptr) != (dw_up == nullptr)) return L32_ERR_NULL;
+    cudaStream_t s = as_stream(stream);
+    if (tokens == 0) {
+        cudaError_t e = cudaSuccess;
+        const size_t wbytes = static_cast<size_t>(inter) * hidden * 2;
+        if (dw_gate != nullptr) {
+            e = cudaMemsetAsync(dw_gate, 0, wbytes, s);
+            if (e == cudaSuccess) e = cudaMemsetAsync(dw_up, 0, wbytes, s);
+        }
+        if (e == cudaSuccess && dlora_a != nullptr) e = cudaMemsetAsync(dlora_a, 0, static_cast<size_t>(rank) * inter * 2, s);
+        if (e == cudaSuccess && dlora_bs != nullptr) e = cudaMemsetAsync(dlora_bs, 0, static_cast<size_t>(hidden) * rank * 2, s);
+        return static_cast<int>(e);
+    }
+    if (dy == nullptr || x == nullptr || w_gate == nullptr || w_up == nullptr || w_down == nullptr || lora_a == nullptr ||
+        lora_bs == nullptr || t_saved == nullptr || gate_cache == nullptr || up_cache == nullptr)
+        return L32_ERR_NULL;
+    if (workspace == nullptr || workspace_bytes < l32_ffn_lora_backward_workspace_bytes(tokens, inter, rank) ||
+        !is_aligned16(workspace))
+        return L32_ERR_WORKSPACE;
+    const size_t part = align256(static_cast<size_t>(tokens) * inter * 2);
+    void* d_gate = workspace;
+    void* d_up = static_cast<uint8_t*>(workspace) + part;
+    void* act = static_cast<uint8_t*>(workspace) + 2 * part;
+    void* u = static_cast<uint8_t*>(workspace) + 3 * part;
+    const int t = static_cast<int>(tokens);
+
+    // u = dy lora_bs  [tokens, rank]   (lora_bs [hidden, rank] consumed as an MN-major B operand)
+    GemmProblem g = blank(t, rank, dtype);
+    g.k[0] = hidden;
+    g.a[0] = op(dy, hidden, 0);
+    g.b[0] = op(lora_bs, rank, 1);
+    g.epilogue = EPI_STORE;
+    g.d[0] = u;
+    g.ldd = rank;
+    int rc = gemm_sm100(g, s);
+    if (rc != L32_OK) return rc;
+    // d_act = dy w_down + u lora_a (two phases), SiLU' recomputed in the epilogue -> d_gate, d_up (+ act for dlora_a)
+    g = blank(t, inter, dtype);
+    g.num_phases = 2;
+    g.k[0] = hidden;
+    g.k[1] = rank;
+    g.a[0] = op(dy, hidden, 0);
+    g.b[0] = op(w_down, inter, 1);
+    g.a[1] = op(u, rank, 0);
+    g.b[1] = op(lora_a, inter, 1);
+    g.epilogue = EPI_SWIGLU_BWD;
+    g.d[0] = d_gate;
+    g.d[1] = d_up;
+    g.d[2] = (dlora_a != nullptr) ? act : nullptr;
+    g.e[0] = gate_cache;
+    g.e[1] = up_cache;
+    g.ldd = inter;
+    rc = gemm_sm100(g, s);
+    if (rc != L32_OK) return rc;
+    if (dx != nullptr) {
+        rc = dgrad_x(d_gate, d_up, w_gate, w_up, dx, t, hidden, inter, dtype, s);
+        if (rc != L32_OK) return rc;
+    }
+    if (dw_gate != nullptr) {
+        rc = wgrad(d_gate, inter, x, hidden, dw_gate, t, dtype, s);
+        if (rc != L32_OK) return rc;
+        rc = wgrad(d_up, inter, x, hidden, dw_up, t, dtype, s);
+        if (rc != L32_OK) return rc;
+    }
+    if (dlora_bs != nullptr) {   // [hidden, rank] = dy^T t
+        rc = wgrad(dy, hidden, t_saved, rank, dlora_bs, t, dtype, s);
+        if (rc != L32_OK) return rc;
+    }
+    if (dlora_a != nullptr) rc = wgrad(u, rank, act, inter, dlora_a, t, dtype, s);   // [rank, inter] = u^T act
+    return rc;
+}
+
 int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t ldb, int b_mn_major, const void* a1,
              int64_t lda1, const void* b1, int64_t ldb1, void* d, int64_t ldd, int m, int n, int k, int k1, int dtype,
              int cta_group, int max_ctas, void* stream) {
@@ -320,6 +483,13 @@ int l32_tp_signal(void* const* peer_flags, int world, int index, uint32_t value,
     for (int i = 0; i < world; ++i)
         if (peer_flags[i] == nullptr) return L32_ERR_NULL;
     return static_cast<int>(tp_signal(peer_flags, world, index, value, as_stream(stream)));
+}
+
+int l32_tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, void* stream) {
+    if (dst == nullptr || src == nullptr) return L32_ERR_NULL;
+    if (!is_aligned16(dst) || !is_aligned16(src) || (bytes % 16) != 0) return L32_ERR_BAD_ALIGN;
+    if (ctas < 1 || warps < 1 || warps > 32) return L32_ERR_BAD_SHAPE;
+    return static_cast<int>(tp_peer_copy(dst, src, bytes, ctas, warps, unroll, as_stream(stream)));
 }
 
 int l32_tp_swiglu_forward_allgather(void* x_full, const void* const* peer_x, const uint32_t* ready, uint32_t* done,

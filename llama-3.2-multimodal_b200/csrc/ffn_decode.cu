@@ -42,6 +42,7 @@ struct DecodeParams {
     CUtensorMap map_x;      // activations [tokens, K]
     void* out;              // [tokens, rows_out]
     const void* bias[2];    // optional per-output-row bias ([0] gate / linear, [1] up)
+    const void* addend;     // linear only, optional [tokens, rows_out]: out = a w^T + bias + addend
     void* cache[2];         // SwiGLU only, optional: pre-activation gate / up projections [tokens, rows_out]
     int tokens, n_pad;      // n_pad = UMMA N in {16, 32, 64, 128}
     int rows_out;           // inter (SwiGLU) or out_features (linear)
@@ -244,7 +245,12 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int n = c * 16 + j;
-                    if (col_ok && n < p.tokens) out[static_cast<size_t>(n) * p.ldo + col] = static_cast<T>(__uint_as_float(v[j]) + b);
+                    if (col_ok && n < p.tokens) {
+                        const size_t o_idx = static_cast<size_t>(n) * p.ldo + col;
+                        float r = __uint_as_float(v[j]) + b;
+                        if (p.addend != nullptr) r = static_cast<float>(static_cast<T>(r)) + static_cast<float>(static_cast<const T*>(p.addend)[o_idx]);
+                        out[o_idx] = static_cast<T>(r);
+                    }
                 }
             }
         }
@@ -310,18 +316,23 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
         const bool col_ok = col < p.rows_out;
         float b = 0.f;
         if (col_ok && p.bias[0] != nullptr) b = static_cast<float>(static_cast<const T*>(p.bias[0])[col]);
+        auto store_out = [&](int nn, float r) {
+            const size_t o_idx = static_cast<size_t>(nn) * p.ldo + col;
+            if (p.addend != nullptr) r = static_cast<float>(static_cast<T>(r)) + static_cast<float>(static_cast<const T*>(p.addend)[o_idx]);
+            out[o_idx] = static_cast<T>(r);
+        };
         int n = n_lo;
         for (; n + 2 <= n_hi; n += 2) {
             const float a0 = sum_splits(part_addr + (n * kRowsA + row) * 4);
             const float a1 = sum_splits(part_addr + ((n + 1) * kRowsA + row) * 4);
             if (col_ok) {
-                out[static_cast<size_t>(n) * p.ldo + col] = static_cast<T>(a0 + b);
-                out[static_cast<size_t>(n + 1) * p.ldo + col] = static_cast<T>(a1 + b);
+                store_out(n, a0 + b);
+                store_out(n + 1, a1 + b);
             }
         }
         if (n < n_hi) {
             const float a0 = sum_splits(part_addr + (n * kRowsA + row) * 4);
-            if (col_ok) out[static_cast<size_t>(n) * p.ldo + col] = static_cast<T>(a0 + b);
+            if (col_ok) store_out(n, a0 + b);
         }
     }
     __syncwarp();
@@ -368,8 +379,8 @@ int launch_decode(const DecodeParams& p, int grid, size_t smem_bytes, cudaStream
 
 // Common host path.  rows_per_block = output rows one CTA produces (64 for SwiGLU: 64 gate + 64 up weight rows).
 template <int kEpi>
-int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0, const void* bias1, void* out, void* cache0,
-                void* cache1, int tokens, int k, int rows_out, int dtype, cudaStream_t s) {
+int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0, const void* bias1, const void* addend, void* out,
+                void* cache0, void* cache1, int tokens, int k, int rows_out, int dtype, cudaStream_t s) {
     if (tokens <= 0 || tokens > 128 || k <= 0 || rows_out <= 0) return L32_ERR_BAD_SHAPE;
     if ((k % 8) != 0 || (rows_out % 8) != 0) return L32_ERR_BAD_SHAPE;
     if (!is_aligned16(x) || !is_aligned16(w0) || (w1 != nullptr && !is_aligned16(w1))) return L32_ERR_BAD_ALIGN;
@@ -385,6 +396,7 @@ int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0
     p.out = out;
     p.bias[0] = bias0;
     p.bias[1] = bias1;
+    p.addend = addend;
     p.cache[0] = cache0;
     p.cache[1] = cache1;
     p.idesc = make_idesc_f16(dtype == L32_BF16, kRowsA, static_cast<uint32_t>(p.n_pad), false, false);
@@ -440,12 +452,12 @@ int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0
 
 int ffn_decode_swiglu(const void* x, const void* w_gate, const void* w_up, const void* b_gate, const void* b_up, void* act,
                       void* gate_cache, void* up_cache, int tokens, int hidden, int inter, int dtype, cudaStream_t s) {
-    return decode_gemm<DEC_SWIGLU>(x, w_gate, w_up, b_gate, b_up, act, gate_cache, up_cache, tokens, hidden, inter, dtype, s);
+    return decode_gemm<DEC_SWIGLU>(x, w_gate, w_up, b_gate, b_up, nullptr, act, gate_cache, up_cache, tokens, hidden, inter, dtype, s);
 }
 
-int ffn_decode_linear(const void* a, const void* w, const void* bias, void* y, int tokens, int in_features,
+int ffn_decode_linear(const void* a, const void* w, const void* bias, const void* addend, void* y, int tokens, int in_features,
                       int out_features, int dtype, cudaStream_t s) {
-    return decode_gemm<DEC_LINEAR>(a, w, nullptr, bias, nullptr, y, nullptr, nullptr, tokens, in_features, out_features, dtype, s);
+    return decode_gemm<DEC_LINEAR>(a, w, nullptr, bias, nullptr, addend, y, nullptr, nullptr, tokens, in_features, out_features, dtype, s);
 }
 
 }  // namespace l32

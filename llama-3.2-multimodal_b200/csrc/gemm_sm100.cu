@@ -6,11 +6,12 @@
 // swiglu_backward_kernel (reference Tools/swiglu/swiglu.cu:58-100, :228-272, :179-223) and the cuBLAS
 // F.linear calls of the live PyTorch path (reference Tools/swiglu/FusedSwiglu.py:18-20, Model/model.py:214-217).
 //
-// Structure (one CTA per SM, 256 threads; optional CTA pair = cta_group::2 with UMMA M = 256):
+// Structure (one CTA per SM, 320 threads; optional CTA pair = cta_group::2 with UMMA M = 256):
 //   warp 0   : TMA producer  (cp.async.bulk.tensor, 128-byte swizzle, ring of kStages smem slots)
 //   warp 1   : MMA issuer    (tcgen05.mma kind::f16, one elected thread of the leader CTA)
 //   warp 2   : TMEM allocator
 //   warps 4-7: epilogue      (tcgen05.ld -> registers -> fused math -> 16-byte global stores)
+//   warps 2-3, 8-9: all-gather pullers of the tensor-parallel variant (idle otherwise): NVLink loads from peer memory
 // TMEM holds two 256-column fp32 accumulator stages, so the epilogue of tile t overlaps the main loop of
 // tile t+1.  Tiles are visited in a grouped raster so concurrently running CTAs share A and B panels in L2.
 //
@@ -37,7 +38,8 @@ constexpr int kBlockM = 128;   // accumulator rows per CTA (= TMEM lanes)
 constexpr int kBlockK = 64;    // one 128-byte swizzle atom of 16-bit elements
 constexpr int kUmmaK = 16;
 constexpr int kAccCols = 256;  // TMEM columns per accumulator stage (= UMMA N)
-constexpr int kThreads = 256;
+constexpr int kThreads = 320;             // warps 0-1 TMA / MMA, 2-3 + 8-9 all-gather pullers (2 allocates TMEM), 4-7 epilogue
+constexpr int kPullWarps = 4;
 constexpr int kAtomBytes = kBlockK * 128;   // 64 rows x 128 B = 8 KiB: one swizzle-atom column of a tile
 constexpr int kEpiStageBytes = 32 * 128;    // per epilogue warp: 32 rows x 128 B transpose buffer (EPI_STORE)
 
@@ -125,7 +127,7 @@ L32_DEVICE TileCoord tile_coord(int t, int tiles_m, int tiles_n, int group, int 
 // All-gather fused into the kernel: this warp's share of pulling chunk after chunk of A rows out of peer memory
 // (NVLink loads that bypass the non-coherent L1) into the local A buffer, in the order the tiles consume them.
 L32_DEVICE void ag_pull(const TpAllGather& ag, int m, size_t row_bytes, int puller, int num_pullers, uint32_t lane) {
-    constexpr int kUnroll = 16;
+    constexpr int kUnroll = 8;   // measured (scripts/nvlink_probe.py): 4 warps/SM x 8 loads in flight saturate NVLink pulls; 16 is slower
     for (int j = 1; j < ag.world; ++j) {
         const int s = (ag.rank + j) % ag.world;
         const long long r0 = static_cast<long long>(s) * ag.rows_per_rank;
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     bool waited = false;
                     for (int c = c_lo; c <= c_hi; ++c) {
                         if (c == p.ag.rank) continue;
-                        wait_flag_ge<false>(&p.ag.done[c], p.ag.done_base + gridDim.x * 2u);
+                        wait_flag_ge<false>(&p.ag.done[c], p.ag.done_base + gridDim.x * static_cast<uint32_t>(kPullWarps));
                         waited = true;
                     }
                     if (waited) fence_proxy_async_all();   // generic-proxy stores of other SMs -> TMA (async proxy) loads
@@ -309,11 +311,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 if (acc == 0) acc_phase ^= 1u;
             }
         }
-    } else if (warp == 2 || warp == 3) {
+    } else if (warp == 2 || warp == 3 || warp >= 8) {
         // ------------------------------------------------------------------ all-gather pullers (tensor-parallel only)
-        if (p.ag.world > 1)
-            ag_pull(p.ag, p.m, static_cast<size_t>(p.k[0]) * sizeof(T), static_cast<int>(blockIdx.x * 2 + (warp - 2)),
-                    static_cast<int>(gridDim.x * 2), lane);
+        if (p.ag.world > 1) {
+            const int idx = static_cast<int>(warp >= 8 ? warp - 6 : warp - 2);   // 0..3
+            ag_pull(p.ag, p.m, static_cast<size_t>(p.k[0]) * sizeof(T), static_cast<int>(blockIdx.x) * kPullWarps + idx,
+                    static_cast<int>(gridDim.x) * kPullWarps, lane);
+        }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
         const uint32_t q = warp - 4;                       // TMEM lane quarter owned by this warp
@@ -373,6 +377,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                         const int grow = warp_row0 + static_cast<int>(r);
                         const int gcol = col + static_cast<int>(ch) * 8;
                         if (grow < p.m && gcol < p.n) {
+                            uint4 out = val;
+                            if (p.e[0] != nullptr) {   // fused "+ addend" (block tail: attn_out + ff_out, reference model.py:273)
+                                const uint4 ad = ld_global_nc_v4(static_cast<const uint8_t*>(p.e[0]) +
+                                                                 (static_cast<size_t>(grow) * static_cast<size_t>(p.ldd) + gcol) * esz);
+                                const uint32_t vi[4] = {val.x, val.y, val.z, val.w}, ai[4] = {ad.x, ad.y, ad.z, ad.w};
+                                uint32_t oi[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 a = Pack2<T>::unpack(vi[j]), b = Pack2<T>::unpack(ai[j]);
+                                    oi[j] = Pack2<T>::pack(a.x + b.x, a.y + b.y);
+                                }
+                                out = make_uint4(oi[0], oi[1], oi[2], oi[3]);
+                            }
                             uint8_t* dst;
                             if (p.rs.world > 0) {
                                 int owner = grow / p.rs.rows_per_rank;
@@ -382,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                             } else {
                                 dst = static_cast<uint8_t*>(p.d[0]) + static_cast<size_t>(grow) * static_cast<size_t>(p.ldd) * esz;
                             }
-                            st_global_v4(dst + static_cast<size_t>(gcol) * esz, val.x, val.y, val.z, val.w);
+                            st_global_v4(dst + static_cast<size_t>(gcol) * esz, out.x, out.y, out.z, out.w);
                         }
                     }
                     __syncwarp();
@@ -660,7 +677,8 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
             g.ag.local_dst != g.a[0].ptr || g.ag.ready == nullptr || g.ag.done == nullptr)
             return L32_ERR_BAD_SHAPE;
     }
-    if (g.rs.world > 0 && (g.epilogue != EPI_STORE || g.rs.rows_per_rank <= 0)) return L32_ERR_BAD_SHAPE;
+    if (g.rs.world > 0 && (g.epilogue != EPI_STORE || g.rs.rows_per_rank <= 0 || g.e[0] != nullptr)) return L32_ERR_BAD_SHAPE;
+    if (g.epilogue == EPI_STORE && g.e[0] != nullptr && !is_aligned16(g.e[0])) return L32_ERR_BAD_ALIGN;
 
     const int b_box_rows = (g.epilogue == EPI_SWIGLU) ? 128 : kAccCols / cta_group;
     for (int ph = 0; ph < g.num_phases; ++ph) {

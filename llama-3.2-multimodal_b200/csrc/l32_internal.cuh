@@ -68,7 +68,7 @@ struct GemmProblem {
     GemmOperand b[2];       // EPI_SWIGLU: b[0] = gate weights, b[1] = up weights (both K-major)
     int epilogue;           // EPI_*
     void* d[3];             // outputs, see EPI_*; optional ones may be null
-    const void* e[2];       // EPI_SWIGLU_BWD: gate / up caches [m, n]
+    const void* e[2];       // EPI_SWIGLU_BWD: gate / up caches [m, n];  EPI_STORE: e[0] = optional addend [m, n] (D += addend)
     int64_t ldd;            // row pitch of every output / epilogue input, elements
     const void* bias[2];    // optional per-column bias (bias[0] for D / gate, bias[1] for up)
     int dtype;              // L32_BF16 / L32_FP16
@@ -90,11 +90,12 @@ cudaError_t swiglu_act_elementwise(const void* gate, const void* up, void* act, 
 //      return L32_ERR_BAD_SHAPE when the problem is outside the kernel's envelope (the caller then uses the tiled GEMM)
 int ffn_decode_swiglu(const void* x, const void* w_gate, const void* w_up, const void* b_gate, const void* b_up, void* act,
                       void* gate_cache, void* up_cache, int tokens, int hidden, int inter, int dtype, cudaStream_t s);
-int ffn_decode_linear(const void* a, const void* w, const void* bias, void* y, int tokens, int in_features,
-                      int out_features, int dtype, cudaStream_t s);
+int ffn_decode_linear(const void* a, const void* w, const void* bias, const void* addend, void* y, int tokens,
+                      int in_features, int out_features, int dtype, cudaStream_t s);
 
 // ---- tp.cu : tensor-parallel glue (cross-GPU flags, reduction of the partial slots)
 cudaError_t tp_signal(void* const* peer_flags, int world, int index, uint32_t value, cudaStream_t s);
+cudaError_t tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, cudaStream_t s);
 cudaError_t tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_t epoch, int world, int rank,
                                const void* addend, void* y, int64_t rows, int64_t slot_rows, int hidden, int dtype,
                                cudaStream_t s);

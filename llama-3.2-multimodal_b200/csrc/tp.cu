@@ -74,7 +74,36 @@ __global__ void __launch_bounds__(256) tp_reduce_partials_kernel(const T* slots,
     }
 }
 
+// Plain peer copy (pull when src is peer memory, push when dst is): the NVLink bandwidth reference the fused kernels are
+// compared with.  `warps` warps per CTA, 16-byte vectors, kUnroll loads in flight per lane.
+template <int kUnroll>
+__global__ void __launch_bounds__(1024) tp_peer_copy_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
+                                                            long long nvec) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvec; v += stride * kUnroll) {
+        uint4 buf[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (v + u * stride < nvec) buf[u] = ld_relaxed_sys_v4(src + (v + u * stride) * 16);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (v + u * stride < nvec) *reinterpret_cast<uint4*>(dst + (v + u * stride) * 16) = buf[u];
+    }
+}
+
 }  // namespace
+
+cudaError_t tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, cudaStream_t s) {
+    const long long nvec = static_cast<long long>(bytes / 16);
+    if (nvec == 0) return cudaSuccess;
+    auto* d = static_cast<uint8_t*>(dst);
+    auto* sp = static_cast<const uint8_t*>(src);
+    if (unroll >= 16) tp_peer_copy_kernel<16><<<ctas, warps * 32, 0, s>>>(d, sp, nvec);
+    else if (unroll >= 8) tp_peer_copy_kernel<8><<<ctas, warps * 32, 0, s>>>(d, sp, nvec);
+    else tp_peer_copy_kernel<4><<<ctas, warps * 32, 0, s>>>(d, sp, nvec);
+    count_launch();
+    return cudaGetLastError();
+}
 
 cudaError_t tp_signal(void* const* peer_flags, int world, int index, uint32_t value, cudaStream_t s) {
     PeerFlags f;

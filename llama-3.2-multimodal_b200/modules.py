@@ -22,8 +22,8 @@ import torch.nn.functional as F
 from . import ops
 
 __all__ = [
-    "RMSNormFunction", "LLAMARMSNorm", "SwiGLUFunction", "FusedSwiGLU", "LinearFunction", "Linear_LORA", "FFNFunction",
-    "FusedFeedforward", "FusedFeedForward", "convert_feedforward_to_fused", "patch_reference", "convert_instances",
+    "RMSNormFunction", "LLAMARMSNorm", "SwiGLUFunction", "FusedSwiGLU", "LinearFunction", "Linear_LORA", "FFNFunction", "FFNLoRAFunction",
+    "FusedFeedforward", "FusedFeedForward", "convert_feedforward_to_fused", "patch_reference", "convert_instances", "block_tail",
 ]
 
 
@@ -256,6 +256,39 @@ class FFNFunction(torch.autograd.Function):
         return dx, (dwg if ng else None), (dwu if nu else None), dwd, dbg, dbu, dbd
 
 
+class FFNLoRAFunction(torch.autograd.Function):
+    """Feed-forward with a LoRA adapter on a frozen w_down (reference README.md:179-188 swaps Linear_LORA,
+    Model/model.py:107-121, into FusedFeedforward.w_down): the adapter is a second accumulation phase (K = rank) of the
+    down GEMM in forward and of the d_act GEMM in backward, so neither [tokens, hidden] nor [tokens, inter] LoRA
+    terms are materialised.  `scale` = alpha / rank."""
+
+    @classmethod
+    def apply(cls, x, w_gate, w_up, w_down, lora_a, lora_b, scale):
+        if not _wants_grad(x, w_gate, w_up, lora_a, lora_b):
+            return ops.ffn_lora_forward(x, w_gate, w_up, w_down, lora_a, lora_b * scale, want_cache=False)[0]
+        return super().apply(x, w_gate, w_up, w_down, lora_a, lora_b, scale)
+
+    @staticmethod
+    def forward(ctx, x, w_gate, w_up, w_down, lora_a, lora_b, scale):
+        lora_bs = lora_b * scale
+        y, t, gate, up = ops.ffn_lora_forward(x, w_gate, w_up, w_down, lora_a, lora_bs, want_cache=True)
+        ctx.save_for_backward(x, w_gate, w_up, w_down, lora_a, lora_bs, t, gate, up)
+        ctx.scale = scale
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x, w_gate, w_up, w_down, lora_a, lora_bs, t, gate, up = ctx.saved_tensors
+        nx, ng, nu, nd, na, nb, _ = ctx.needs_input_grad
+        if nd:
+            raise RuntimeError("FFNLoRAFunction: the base w_down is frozen under LoRA (Model/model.py:117); "
+                               "set requires_grad=False on it or use FusedFeedforward without an adapter")
+        dx, dwg, dwu, dla, dlbs = ops.ffn_lora_backward(grad_y, x, w_gate, w_up, w_down, lora_a, lora_bs, t, gate, up,
+                                                        want_dx=nx, want_dw_gate_up=(ng or nu), want_dlora=(na or nb))
+        dlb = (dlbs * ctx.scale) if (dlbs is not None and nb) else None
+        return dx, (dwg if ng else None), (dwu if nu else None), None, (dla if na else None), dlb, None
+
+
 def _is_lora(m) -> bool:
     return all(hasattr(m, a) for a in ("linear", "lora_a", "lora_b", "rank", "alpha"))
 
@@ -280,10 +313,37 @@ class FusedFeedforward(nn.Module):
             if isinstance(wd, nn.Linear) and wd.weight.dtype == x.dtype:
                 return FFNFunction.apply(x, sw.w_gate, sw.w_up, wd.weight, sw.b_gate, sw.b_up, wd.bias)
             if _is_lora(wd) and wd.linear.weight.dtype == x.dtype:
+                drop = getattr(wd, "dropout", None)
+                no_dropout = drop is None or not (self.training and getattr(drop, "p", 0.0) > 0.0)
+                if (no_dropout and sw.b_gate is None and wd.linear.bias is None and not wd.linear.weight.requires_grad and
+                        wd.lora_a.weight.dtype == x.dtype and wd.lora_b.weight.dtype == x.dtype and
+                        wd.rank % 8 == 0 and wd.rank <= 64 and x.numel() // x.shape[-1] > 0):
+                    return FFNLoRAFunction.apply(x, sw.w_gate, sw.w_up, wd.linear.weight, wd.lora_a.weight,
+                                                 wd.lora_b.weight, wd.alpha / wd.rank)
                 act = sw(x)
                 base = LinearFunction.apply(act, wd.linear.weight, wd.linear.bias)
                 return base + (wd.alpha / wd.rank) * wd.lora_b(wd.lora_a(wd.dropout(act)))
         return wd(sw(x))
+
+
+def block_tail(norm2, ff, attn_out, residual):
+    """`attn_out + ff(norm2(attn_out, residual=residual))` -- the tail of the reference's TransformerBlock.forward
+    (Model/model.py:270-273).  For inference on 16-bit CUDA tensors it is one C call (Add-RMSNorm, fused gate/up GEMM,
+    down GEMM whose epilogue adds attn_out); otherwise (training, fp32, CPU, LoRA / biases) the modules are composed
+    exactly as the reference does."""
+    sw, wd = ff.swiglu, ff.w_down
+    if (ops.supported(attn_out) and isinstance(wd, nn.Linear) and wd.bias is None and sw.b_gate is None and
+            sw.w_gate.dtype == attn_out.dtype and wd.weight.dtype == attn_out.dtype and
+            not _wants_grad(attn_out, residual, norm2.weight, sw.w_gate, sw.w_up, wd.weight)):
+        return ops.block_tail_forward(attn_out, residual, norm2.weight, norm2.eps, sw.w_gate, sw.w_up, wd.weight)
+    return attn_out + ff(norm2(attn_out, residual=residual))
+
+
+def _transformer_block_forward(self, hidden_states, attention_mask=None, position_ids=None, kv_cache=None):
+    """Same computation as the reference's TransformerBlock.forward (Model/model.py:265-273) with the tail fused."""
+    normed = self.norm1(hidden_states)
+    attn_out = self.att(normed, attention_mask=attention_mask, position_ids=position_ids, kv_cache=kv_cache)
+    return block_tail(self.norm2, self.ff, attn_out, hidden_states)
 
 
 FusedFeedForward = FusedFeedforward   # the reference spells it both ways (FusedSwiglu.py:94 vs model.py:210)
@@ -307,7 +367,7 @@ def convert_feedforward_to_fused(feedforward_module):
     return fused
 
 
-def patch_reference(model_module, swiglu_module=None):
+def patch_reference(model_module, swiglu_module=None, fuse_block_tail=True):
     """Point an imported reference `Model.model` (and `Tools.swiglu.FusedSwiglu`) at this implementation.
 
     After the call, models built from the reference's own classes (MllamaForConditionalGeneration,
@@ -320,6 +380,8 @@ def patch_reference(model_module, swiglu_module=None):
     model_module.FusedSwiGLU = FusedSwiGLU
     model_module.Linear_LORA = Linear_LORA
     model_module.HAS_RMSNORM_EXT = True
+    if fuse_block_tail and hasattr(model_module, "TransformerBlock"):
+        model_module.TransformerBlock.forward = _transformer_block_forward
     if swiglu_module is not None:
         swiglu_module.SwiGLUFunction = SwiGLUFunction
         swiglu_module.FusedSwiGLU = FusedSwiGLU

@@ -204,6 +204,29 @@ def ffn_forward(x, w_gate, w_up, w_down, b_gate=None, b_up=None, b_down=None, *,
     return y.view(x.shape), gate, up
 
 
+def block_tail_forward(attn_out, residual, norm_weight, eps, w_gate, w_up, w_down):
+    """out = attn_out + ff(rmsnorm(attn_out + residual) * norm_weight): the decoder-block tail in one C call
+    (reference Model/model.py:270-273), the final add fused into the down-GEMM epilogue.  Inference only."""
+    _check_cuda(attn_out, residual, norm_weight, w_gate, w_up, w_down)
+    a2, tokens = _flat_tokens(attn_out)
+    wg, wu, wd = w_gate.contiguous(), w_up.contiguous(), w_down.contiguous()
+    hidden, inter = _check_ffn_weights(a2, wg, wu, wd)
+    r2 = None if residual is None else residual.contiguous().view(-1, hidden)
+    if r2 is not None and r2.shape != a2.shape:
+        raise L32Error(f"residual shape {tuple(residual.shape)} != attn_out shape {tuple(attn_out.shape)}")
+    w = norm_weight.contiguous()
+    if w.dtype != a2.dtype:
+        w = w.to(a2.dtype)
+    out = torch.empty_like(a2)
+    normed = torch.empty_like(a2)
+    act = torch.empty(tokens, inter, dtype=a2.dtype, device=a2.device)
+    with torch.cuda.device(a2.device):
+        check(lib().l32_block_tail_forward(_ptr(a2), _ptr(r2), _ptr(w), float(eps), _ptr(wg), _ptr(wu), _ptr(wd), _ptr(out),
+                                           _ptr(normed), _ptr(act), tokens, hidden, inter, _dtype_code(a2), _stream(a2)),
+              "l32_block_tail_forward")
+    return out.view(attn_out.shape)
+
+
 def ffn_backward(grad_y, x, w_gate, w_up, w_down, gate_cache, up_cache, *, want_dx=True, want_dw_gate_up=True,
                  want_dw_down=True):
     """(dx|None, dw_gate|None, dw_up|None, dw_down|None, d_gate, d_up) for the whole feed-forward."""
@@ -230,6 +253,57 @@ def ffn_backward(grad_y, x, w_gate, w_up, w_down, gate_cache, up_cache, *, want_
     d_gate = ws[:n * 2].view(x2.dtype).view(tokens, inter)
     d_up = ws[part:part + n * 2].view(x2.dtype).view(tokens, inter)
     return (dx.view(x.shape) if dx is not None else None), dwg, dwu, dwd, d_gate, d_up
+
+
+def ffn_lora_forward(x, w_gate, w_up, w_down, lora_a, lora_bs, *, want_cache=False):
+    """y = act w_down^T + (act lora_a^T) lora_bs^T with the adapter fused into the down GEMM (lora_bs pre-scaled by
+    alpha / rank).  Returns (y, t [tokens, rank], gate_cache|None, up_cache|None)."""
+    _check_cuda(x, w_gate, w_up, w_down, lora_a, lora_bs)
+    x2, tokens = _flat_tokens(x)
+    wg, wu, wd = w_gate.contiguous(), w_up.contiguous(), w_down.contiguous()
+    hidden, inter = _check_ffn_weights(x2, wg, wu, wd)
+    la, lb = lora_a.contiguous(), lora_bs.contiguous()
+    rank = la.shape[0]
+    if tuple(la.shape) != (rank, inter) or tuple(lb.shape) != (hidden, rank) or la.dtype != x2.dtype or lb.dtype != x2.dtype:
+        raise L32Error(f"lora shapes/dtypes: lora_a{tuple(la.shape)} {la.dtype}, lora_b{tuple(lb.shape)} {lb.dtype}")
+    y = torch.empty(tokens, hidden, dtype=x2.dtype, device=x2.device)
+    act = torch.empty(tokens, inter, dtype=x2.dtype, device=x2.device)
+    t = torch.empty(tokens, rank, dtype=x2.dtype, device=x2.device)
+    gate = torch.empty_like(act) if want_cache else None
+    up = torch.empty_like(act) if want_cache else None
+    with torch.cuda.device(x2.device):
+        check(lib().l32_ffn_lora_forward(_ptr(x2), _ptr(wg), _ptr(wu), _ptr(wd), _ptr(la), _ptr(lb), _ptr(y), _ptr(act), _ptr(t),
+                                         _ptr(gate), _ptr(up), tokens, hidden, inter, rank, _dtype_code(x2), _stream(x2)),
+              "l32_ffn_lora_forward")
+    return y.view(x.shape), t, gate, up
+
+
+def ffn_lora_backward(grad_y, x, w_gate, w_up, w_down, lora_a, lora_bs, t, gate_cache, up_cache, *, want_dx=True,
+                      want_dw_gate_up=True, want_dlora=True):
+    """(dx|None, dw_gate|None, dw_up|None, dlora_a|None, dlora_bs|None) for ffn_lora_forward (frozen w_down)."""
+    _check_cuda(grad_y, x, w_gate, w_up, w_down, lora_a, lora_bs, t, gate_cache, up_cache)
+    x2, tokens = _flat_tokens(x)
+    wg, wu, wd = w_gate.contiguous(), w_up.contiguous(), w_down.contiguous()
+    hidden, inter = _check_ffn_weights(x2, wg, wu, wd)
+    la, lb = lora_a.contiguous(), lora_bs.contiguous()
+    rank = la.shape[0]
+    gy = grad_y.contiguous().view(-1, hidden)
+    if gy.dtype != x2.dtype:
+        gy = gy.to(x2.dtype)
+    dx = torch.empty_like(x2) if want_dx else None
+    dwg = torch.empty_like(wg) if want_dw_gate_up else None
+    dwu = torch.empty_like(wu) if want_dw_gate_up else None
+    dla = torch.empty_like(la) if want_dlora else None
+    dlb = torch.empty_like(lb) if want_dlora else None
+    L = lib()
+    ws_bytes = L.l32_ffn_lora_backward_workspace_bytes(tokens, inter, rank)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x2.device)
+    with torch.cuda.device(x2.device):
+        check(L.l32_ffn_lora_backward(_ptr(gy), _ptr(x2), _ptr(wg), _ptr(wu), _ptr(wd), _ptr(la), _ptr(lb), _ptr(t.contiguous()),
+                                      _ptr(gate_cache.contiguous()), _ptr(up_cache.contiguous()), _ptr(dx), _ptr(dwg), _ptr(dwu),
+                                      _ptr(dla), _ptr(dlb), _ptr(ws), ws_bytes, tokens, hidden, inter, rank, _dtype_code(x2),
+                                      _stream(x2)), "l32_ffn_lora_backward")
+    return (dx.view(x.shape) if dx is not None else None), dwg, dwu, dla, dlb
 
 
 def gemm(a, b, *, a_mn_major=False, b_mn_major=False, a1=None, b1=None, cta_group=0, max_ctas=0):

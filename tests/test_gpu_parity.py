@@ -111,6 +111,39 @@ def test_block_hot_path_vs_reference_outputs():
     close(out, g["block_out"], FWD, "block_out")
 
 
+def test_block_tail_fused_vs_reference_outputs():
+    """l32_block_tail_forward (norm2 -> ff -> '+ attn_out' in the down epilogue) against the reference's own block output
+    (golden from the real TransformerBlock tail; 32 tokens -> the small-M kernels)."""
+    g = load_golden("block_cfg1.npz")
+    attn, hidden = dev(g["attn_out"]), dev(g["hidden"])
+    norm = L.LLAMARMSNorm(256, eps=g["eps"]).to(DEV, torch.bfloat16)
+    ff = L.FusedFeedforward(256, 688).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        norm.weight.copy_(dev(g["norm2_weight"]))
+        ff.swiglu.w_gate.copy_(dev(g["w_gate"])); ff.swiglu.w_up.copy_(dev(g["w_up"])); ff.w_down.weight.copy_(dev(g["w_down"]))
+        out = L.block_tail(norm, ff, attn, hidden)
+        composed = attn + ff(norm(attn, residual=hidden))
+    close(out, g["block_out"], FWD, "fused block tail vs reference block output")
+    close(out, composed, (4e-3, 2.0 ** -7), "fused vs composed modules")
+    xg = attn.clone().requires_grad_(True)     # training: falls back to composing the modules, differentiable
+    L.block_tail(norm, ff, xg, hidden).sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad.float()).all()
+
+
+@pytest.mark.parametrize("tokens,hidden,inter", [(300, 256, 688), (1111, 512, 1536), (64, 1024, 2048)])
+def test_block_tail_fused_vs_oracle(tokens, hidden, inter):
+    """Same fusion through the tiled tcgen05 kernels (> 128 tokens) and the small-M kernels, against the oracle's
+    restatement of Model/model.py:270-273."""
+    s = O.synthetic_ffn(tokens, hidden, inter, seed=tokens)
+    attn, res, gamma, wg, wu, wd = (dev(s[k]) for k in ("x", "residual", "gamma", "w_gate", "w_up", "w_down"))
+    out = ops.block_tail_forward(attn, res, gamma, 1e-5, wg, wu, wd)
+    _, _, ref = O.block_hot_path(s["x"], s["residual"], s["gamma"], 1e-5, s["w_gate"], s["w_up"], s["w_down"])
+    close(out, ref, FWD, "block tail")
+    out2 = ops.block_tail_forward(attn, None, gamma, 1e-5, wg, wu, wd)     # norm without a residual (final_norm style)
+    _, _, ref2 = O.block_hot_path(s["x"], torch.zeros_like(s["x"]), s["gamma"], 1e-5, s["w_gate"], s["w_up"], s["w_down"])
+    close(out2, ref2, FWD, "block tail, no residual")
+
+
 def test_lora_vs_reference_outputs():
     g = load_golden("lora_small.npz")
     lin = L.Linear_LORA(176, 64, rank=16, alpha=32.0, dropout=0.0).to(DEV, torch.bfloat16)
@@ -284,6 +317,47 @@ def test_module_autograd_end_to_end_and_lora():
     close(ff.swiglu.w_gate.grad, wg.grad, tol_b, "dw_gate"); close(ff.swiglu.w_up.grad, wu.grad, tol_b, "dw_up")
     close(lo.lora_a.weight.grad, las.grad, tol_b, "dlora_a"); close(lo.lora_b.weight.grad, lbs.grad, tol_b, "dlora_b")
     assert lo.linear.weight.grad is None
+
+
+@pytest.mark.parametrize("tokens,hidden,inter,rank", [(300, 256, 688, 16), (64, 512, 1024, 8), (1030, 384, 1152, 64)])
+def test_ffn_lora_fused_vs_oracle(tokens, hidden, inter, rank):
+    """The LoRA adapter as a second accumulation phase of the down GEMM (forward) and of the d_act GEMM (backward),
+    against autograd over the reference's expressions (FusedSwiglu.py:18-20 + Linear_LORA.forward, model.py:120-121)."""
+    s = O.synthetic_ffn(tokens, hidden, inter, seed=rank + tokens)
+    alpha = 32.0
+    la = O.bf16_representable(torch.randn(rank, inter) / inter ** 0.5)
+    lb = O.bf16_representable(0.05 * torch.randn(hidden, rank))
+    x, wg, wu, wd, dy = (dev(s[k]) for k in ("x", "w_gate", "w_up", "w_down", "dy"))
+    scale = alpha / rank
+    lbs = dev(lb) * scale
+    y, t, gate, up = ops.ffn_lora_forward(x, wg, wu, wd, dev(la), lbs, want_cache=True)
+    xs = s["x"].clone().requires_grad_(True)
+    wgs, wus = s["w_gate"].clone().requires_grad_(True), s["w_up"].clone().requires_grad_(True)
+    las, lbs_ref = la.clone().requires_grad_(True), lb.clone().requires_grad_(True)
+    act = O.swiglu(xs, wgs, wus)
+    yr = O.linear_lora(act, s["w_down"], las, lbs_ref, alpha, rank)
+    yr.backward(s["dy"])
+    close(y, yr, FWD, "lora-fused y")
+    close(t, act.detach() @ la.t(), (1.5e-2, 2.0 ** -5), "t = act A^T")
+    dx, dwg, dwu, dla, dlbs = ops.ffn_lora_backward(dy, x, wg, wu, wd, dev(la), lbs, t, gate, up)
+    close(dx, xs.grad, BWD, "dx")
+    close(dwg, wgs.grad, BWD, "dw_gate")
+    close(dwu, wus.grad, BWD, "dw_up")
+    close(dla, las.grad, (1.5e-2, 2.0 ** -5), "dlora_a")
+    close(dlbs.float() * scale, lbs_ref.grad, (1.5e-2, 2.0 ** -5), "dlora_b")
+    # module routing: eval / p = 0 -> fused Function; training with dropout -> the unfused path (still correct in expectation)
+    ff = L.FusedFeedforward(hidden, inter).to(DEV, torch.bfloat16)
+    lo = L.Linear_LORA(inter, hidden, rank=rank, alpha=alpha, dropout=0.05).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        ff.swiglu.w_gate.copy_(wg); ff.swiglu.w_up.copy_(wu)
+        lo.linear.weight.copy_(wd); lo.lora_a.weight.copy_(dev(la)); lo.lora_b.weight.copy_(dev(lb))
+    ff.w_down = lo
+    ff.eval()
+    with torch.no_grad():
+        close(ff(x), yr, FWD, "module (eval) y")
+    ff.train()
+    yt = ff(x)
+    assert yt.shape == y.shape and torch.isfinite(yt.float()).all()
 
 
 # ----------------------------------------------------------------------------------------------- full size
