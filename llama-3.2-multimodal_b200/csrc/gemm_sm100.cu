@@ -41,7 +41,8 @@ constexpr int kAccCols = 256;  // TMEM columns per accumulator stage (= UMMA N)
 constexpr int kThreads = 320;             // warps 0-1 TMA / MMA, 2-3 + 8-9 all-gather pullers (2 allocates TMEM), 4-7 epilogue
 constexpr int kPullWarps = 4;
 constexpr int kAtomBytes = kBlockK * 128;   // 64 rows x 128 B = 8 KiB: one swizzle-atom column of a tile
-constexpr int kEpiStageBytes = 32 * 128;    // per epilogue warp: 32 rows x 128 B transpose buffer (EPI_STORE)
+constexpr int kEpiRowPitch = 272;           // 256 B of one output row + 16 B so the lanes' st.shared hit distinct banks
+constexpr int kEpiStageBytes = 32 * kEpiRowPitch;   // per epilogue warp: one row buffer per lane (EPI_STORE)
 
 template <int kCtaGroup>
 struct TileCfg {
@@ -51,7 +52,7 @@ struct TileCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (kCtaGroup == 2) ? 6 : 4;
     static constexpr int kNumBarriers = 2 * kStages + 4;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 4 * kEpiStageBytes + kNumBarriers * 8 + 16 + 1024 /* alignment slack */;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 4 * kEpiStageBytes + kNumBarriers * 8 + 16;
 };
 
 struct GemmKernelParams {
@@ -107,6 +108,14 @@ L32_DEVICE uint4 ld_shared_v4(const void* p) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)) : "memory");
     return r;
 }
+
+// Bulk async store of one contiguous row segment (shared -> global), tracked by the issuing thread's bulk group.
+L32_DEVICE void bulk_store_row(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+L32_DEVICE void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+L32_DEVICE void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 struct TileCoord {
     int m_blk, n_blk;
@@ -184,8 +193,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     const uint32_t stage_tx = (kEpi == EPI_SWIGLU) ? static_cast<uint32_t>(kCtaGroup * Cfg::kABytes + 2 * p.n_act * 128)
                                                    : static_cast<uint32_t>(Cfg::kStageBytes * kCtaGroup);
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // 128-byte-swizzled tiles need 1024-byte alignment; the kernel has no static shared memory, so the dynamic window
+    // starts aligned (checked: a misaligned base traps instead of corrupting tiles).
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kABytes;
     uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;
@@ -334,75 +346,66 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * kAccCols;
 
             if constexpr (kEpi == EPI_STORE) {
-                // Rows leave through a per-warp shared-memory transpose so that every store instruction writes whole
-                // 128-byte row segments (4 rows x 128 B per instruction) instead of 32 scattered 16-byte pieces: that
-                // is what NVLink needs when the reduce-scatter is fused in (the row then goes straight to the rank
-                // that owns it, a peer store), and it is friendlier to the local L2 as well.
-                uint8_t* stage = epi_stage + q * kEpiStageBytes;
-                const int warp_row0 = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM + q * 32;
+                // Every lane parks 128 columns (256 B) of its own row in shared memory and ships them with ONE bulk
+                // async store (cp.async.bulk shared -> global): whole 256-byte row segments on the wire, which is what
+                // NVLink needs when the reduce-scatter is fused in (the row then goes straight to the rank that owns
+                // it -- a peer store), no second pass through the LSU, and the TMEM stage is released without waiting
+                // for the stores.  Row pitch 272 B keeps the 16-byte st.shared of the 32 lanes conflict-free.
+                uint8_t* my_row = epi_stage + q * kEpiStageBytes + lane * kEpiRowPitch;
                 const T* bias = static_cast<const T*>(p.bias[0]);
+                uint8_t* d_row = nullptr;
+                if (row_ok) {
+                    if (p.rs.world > 0) {
+                        int owner = row / p.rs.rows_per_rank;
+                        if (owner >= p.rs.world) owner = p.rs.world - 1;
+                        d_row = static_cast<uint8_t*>(p.rs.peer_dst[owner]) +
+                                static_cast<size_t>(row - owner * p.rs.rows_per_rank) * static_cast<size_t>(p.ldd) * esz;
+                    } else {
+                        d_row = static_cast<uint8_t*>(p.d[0]) + row_off * esz;
+                    }
+                }
+                const uint8_t* add_row = (p.e[0] != nullptr) ? static_cast<const uint8_t*>(p.e[0]) + row_off * esz : nullptr;
 #pragma unroll 1
-                for (int c = 0; c < kAccCols / 64; ++c) {
-                    const int col = n0 + c * 64;
+                for (int c = 0; c < kAccCols / 128; ++c) {
+                    const int col = n0 + c * 128;
                     if (col >= p.n) break;
+                    bulk_store_wait_read();   // the previous store of this lane has finished reading its row buffer
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
+                    for (int part = 0; part < 4; ++part) {
+                        const int pcol = col + part * 32;
+                        if (pcol >= p.n) break;
                         uint32_t v[32];
-                        tmem_ld_32x32b_x32(taddr + c * 64 + half * 32, v);
+                        tmem_ld_32x32b_x32(taddr + c * 128 + part * 32, v);
                         tmem_ld_wait();
-                        const int hcol = col + half * 32;
+                        uint32_t o[16];
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            uint32_t o[4];
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const int j = j4 * 4 + jj;
-                                float lo = __uint_as_float(v[2 * j]), hi = __uint_as_float(v[2 * j + 1]);
-                                if (bias != nullptr) {
-                                    if (hcol + 2 * j < p.n) lo += static_cast<float>(bias[hcol + 2 * j]);
-                                    if (hcol + 2 * j + 1 < p.n) hi += static_cast<float>(bias[hcol + 2 * j + 1]);
-                                }
-                                o[jj] = Pack2<T>::pack(lo, hi);
+                        for (int j = 0; j < 16; ++j) {
+                            float lo = __uint_as_float(v[2 * j]), hi = __uint_as_float(v[2 * j + 1]);
+                            if (bias != nullptr) {
+                                if (pcol + 2 * j < p.n) lo += static_cast<float>(bias[pcol + 2 * j]);
+                                if (pcol + 2 * j + 1 < p.n) hi += static_cast<float>(bias[pcol + 2 * j + 1]);
                             }
-                            const uint32_t chunk = static_cast<uint32_t>(half * 4 + j4) ^ (lane & 7u);   // XOR swizzle
-                            st_shared_v4(stage + lane * 128u + chunk * 16u, o[0], o[1], o[2], o[3]);
+                            o[j] = Pack2<T>::pack(lo, hi);
                         }
-                    }
-                    __syncwarp();
+                        if (add_row != nullptr && row_ok) {   // fused "+ addend" (block tail: attn_out + ff_out, model.py:273)
+                            uint32_t ad[16];
+                            load_row32(add_row + static_cast<size_t>(pcol) * esz, ad, p.n - pcol);
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const uint32_t r = static_cast<uint32_t>(it) * 4u + (lane >> 3);
-                        const uint32_t ch = lane & 7u;
-                        const uint4 val = ld_shared_v4(stage + r * 128u + ((ch ^ (r & 7u)) * 16u));
-                        const int grow = warp_row0 + static_cast<int>(r);
-                        const int gcol = col + static_cast<int>(ch) * 8;
-                        if (grow < p.m && gcol < p.n) {
-                            uint4 out = val;
-                            if (p.e[0] != nullptr) {   // fused "+ addend" (block tail: attn_out + ff_out, reference model.py:273)
-                                const uint4 ad = ld_global_nc_v4(static_cast<const uint8_t*>(p.e[0]) +
-                                                                 (static_cast<size_t>(grow) * static_cast<size_t>(p.ldd) + gcol) * esz);
-                                const uint32_t vi[4] = {val.x, val.y, val.z, val.w}, ai[4] = {ad.x, ad.y, ad.z, ad.w};
-                                uint32_t oi[4];
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 a = Pack2<T>::unpack(vi[j]), b = Pack2<T>::unpack(ai[j]);
-                                    oi[j] = Pack2<T>::pack(a.x + b.x, a.y + b.y);
-                                }
-                                out = make_uint4(oi[0], oi[1], oi[2], oi[3]);
+                            for (int j = 0; j < 16; ++j) {
+                                const float2 a = Pack2<T>::unpack(o[j]), b = Pack2<T>::unpack(ad[j]);
+                                o[j] = Pack2<T>::pack(a.x + b.x, a.y + b.y);
                             }
-                            uint8_t* dst;
-                            if (p.rs.world > 0) {
-                                int owner = grow / p.rs.rows_per_rank;
-                                if (owner >= p.rs.world) owner = p.rs.world - 1;
-                                dst = static_cast<uint8_t*>(p.rs.peer_dst[owner]) +
-                                      static_cast<size_t>(grow - owner * p.rs.rows_per_rank) * static_cast<size_t>(p.ldd) * esz;
-                            } else {
-                                dst = static_cast<uint8_t*>(p.d[0]) + static_cast<size_t>(grow) * static_cast<size_t>(p.ldd) * esz;
-                            }
-                            st_global_v4(dst + static_cast<size_t>(gcol) * esz, out.x, out.y, out.z, out.w);
                         }
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4)
+                            st_shared_v4(my_row + part * 64 + j4 * 16, o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
                     }
-                    __syncwarp();
+                    fence_proxy_async_smem();   // generic-proxy st.shared -> async-proxy bulk store
+                    if (row_ok) {
+                        const int ncols = min(p.n - col, 128);
+                        bulk_store_row(d_row + static_cast<size_t>(col) * esz, my_row, static_cast<uint32_t>(ncols) * static_cast<uint32_t>(esz));
+                    }
+                    bulk_store_commit();
                 }
             } else if constexpr (kEpi == EPI_SWIGLU) {
                 // accumulator columns [0, n_act) = gate, [n_act, 2 n_act) = up of the same act columns
@@ -501,6 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             acc ^= 1u;
             if (acc == 0) acc_phase ^= 1u;
         }
+        if constexpr (kEpi == EPI_STORE) bulk_store_wait_read();   // shared memory must outlive the last bulk stores
     }
 
     __syncwarp();

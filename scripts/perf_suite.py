@@ -160,6 +160,44 @@ def tp_shapes():
                   f"down {t2 * 1e3:.0f} us ({2.0 * T * H * Il / t2 / 1e9:.0f} TF/s)", flush=True)
 
 
+def tp_emul(world=8, H=4096, I=14336, T=8192):
+    """Fused TP phases with all ranks emulated on one GPU (peer pointers = local buffers): cost of the mechanism itself
+    (rotation, raster, flag waits, pulls / pushes through local memory) without NVLink."""
+    from llama32_b200.tp import FusedTensorParallelBlock, TpRankBuffers
+    dt = torch.bfloat16
+    wg, wu, wd = weights(H, I)
+    gamma = torch.ones(H, device="cuda", dtype=dt)
+    bufs = TpRankBuffers.local_world(world, T, H, dt, "cuda")
+    blocks = [FusedTensorParallelBlock(gamma, 1e-5, wg, wu, wd, b) for b in bufs]
+    x = torch.randn(T, H, device="cuda").to(dt)
+    r = torch.randn(T, H, device="cuda").to(dt)
+    acc = [0.0, 0.0, 0.0, 0.0]
+    iters = 10
+    for it in range(iters + 2):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record()
+        for blk in blocks:
+            lo, hi, _ = blk.rows_of(T)
+            blk.phase_norm(x[lo:hi], r[lo:hi], T)
+        ev[1].record()
+        for blk in blocks:
+            blk.phase_gate_up(T)
+        ev[2].record()
+        for blk in blocks:
+            blk.phase_down(T)
+        ev[3].record()
+        for blk in blocks:
+            blk.phase_reduce(T)
+        ev[4].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            for k in range(4):
+                acc[k] += ev[k].elapsed_time(ev[k + 1])
+    per = [a / iters / world * 1e3 for a in acc]
+    print(f"tp-emul world={world} H={H} I={I}: per rank norm+signal {per[0]:.0f} us  gate/up+pull {per[1]:.0f} us  "
+          f"down+push+signal {per[2]:.0f} us  reduce {per[3]:.0f} us", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     if what == "decode":
@@ -172,6 +210,10 @@ if __name__ == "__main__":
         train(4096, 14336, 8192)
     elif what == "tp_shapes":
         tp_shapes()
+    elif what == "tp_emul":
+        tp_emul(8)
+        tp_emul(4)
+        tp_emul(8, 8192, 28672)
     elif what == "norm":
         norm(4096, 8192)
         norm(8192, 8192)

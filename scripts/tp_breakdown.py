@@ -35,10 +35,17 @@ def main():
     names = ["norm+signal", "gate/up+allgather", "down+reduce-scatter+signal", "reduce"]
     acc = [0.0] * 4
     iters, warm = 30, 5
-    for i in range(iters + warm):
+    for i in range(warm):
+        blk.forward(xs[i % 2], rs[i % 2], tokens)
+    # back-to-back steps (no barrier in between, the CPU runs ahead): the regime bench.py reports.  Events between the
+    # phases give the steady-state per-phase times on each rank's GPU timeline.
+    dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        dist.barrier()
-        torch.cuda.synchronize()
         ev[0].record()
         blk.phase_norm(xs[i % 2], rs[i % 2], tokens)
         ev[1].record()
@@ -48,20 +55,13 @@ def main():
         ev[3].record()
         blk.phase_reduce(tokens)
         ev[4].record()
-        torch.cuda.synchronize()
-        if i >= warm:
-            for k in range(4):
-                acc[k] += ev[k].elapsed_time(ev[k + 1])
-    # back-to-back steps (no barrier in between): the number bench.py reports
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        blk.forward(xs[i % 2], rs[i % 2], tokens)
+        evs.append(ev)
     e1.record()
     torch.cuda.synchronize()
     total = e0.elapsed_time(e1) / iters
+    for ev in evs:
+        for k in range(4):
+            acc[k] += ev[k].elapsed_time(ev[k + 1])
     t = torch.tensor(acc + [total], device=dev, dtype=torch.float64)
     gathered = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(gathered, t)
