@@ -14,8 +14,9 @@ hidden_dim 14336, bf16 prefill, 4 x 2048 tokens).  Prints ONE JSON line on rank 
             that launch inside the timed region, against MEASURED_PEAKS.json;
   cpu_baseline: the reference's own CPU path (PyTorch fp32 expressions, oracle port) on this box's host cores.
 --impl reference times that CPU path alone (rank 0 only) and prints the same line with "impl": "reference".
-N > 1: tensor-parallel FFN (column-sharded gate/up, row-sharded down), sequence-parallel Add-RMSNorm, same total batch
--> "scaling": "strong".  Default --tp-impl fused: the all-gather is pulled over NVLink inside the gate/up tcgen05 GEMM
+N > 1: tensor-parallel FFN (column-sharded gate/up, row-sharded down), sequence-parallel Add-RMSNorm.  Default
+--scaling weak: every GPU keeps config 2's 4 x 2048 tokens (global batch = N x 8192; per-GPU flops fixed, the exchanged
+bytes per GPU grow with N); --scaling strong keeps the global batch at 8192 tokens.  Default --tp-impl fused: the all-gather is pulled over NVLink inside the gate/up tcgen05 GEMM
 and the reduce-scatter is pushed from the down-GEMM epilogue (peer memory, no NCCL on the data path); --tp-impl nccl is
 the NCCL reduce-scatter / all-gather baseline with the same sharding.
 """
@@ -166,7 +167,7 @@ def run_reference(args):
                   "oracle port of reference Model/model.py:166-171,217 + Tools/swiglu/FusedSwiglu.py:18-20")
     line = {
         "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": label, "hidden": hidden, "hidden_dim": inter, "tokens_per_step": sample,
                    "note": "reference CPU path on host cores (the reference has no working accelerated FFN)"},
@@ -278,10 +279,13 @@ def run_ours(args):
     from llama32_b200.tp import FusedTensorParallelBlock, TensorParallelFFN, TpRankBuffers
 
     hidden, inter, batch, seq, label = WORKLOADS[args.workload]
-    tokens = batch * seq
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    weak = world > 1 and args.scaling == "weak"
+    if weak:
+        batch *= world                                 # 4 x 2048 tokens PER GPU
+    tokens = batch * seq
     if args.gpus != world:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
@@ -306,19 +310,23 @@ def run_ours(args):
     ffn = ffn.to(dev, dt)
     nbuf = 2                                           # rotate input buffers; footprint per step >> 126 MB L2
     gen = torch.Generator(device=dev).manual_seed(1)
-    xs = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)]
-    rs = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)]
-    dys = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)] if train else None
     tp = fused = None
-    if world > 1 and args.tp_impl == "nccl":
-        tp = TensorParallelFFN(ffn, chunks=args.tp_chunks)
-    elif world > 1:
+    xs = rs = dys = None
+    if world > 1 and args.tp_impl == "fused":
         bufs = TpRankBuffers.symmetric(tokens, hidden, dt, dev)
         fused = FusedTensorParallelBlock(norm.weight.detach(), EPS, ffn.swiglu.w_gate.detach(), ffn.swiglu.w_up.detach(),
                                          ffn.w_down.weight.detach(), bufs)
         lo, hi, _ = fused.rows_of(tokens)
-        xs_loc = [x.view(tokens, hidden)[lo:hi].contiguous() for x in xs]   # sequence-parallel: this rank's rows only
-        rs_loc = [r.view(tokens, hidden)[lo:hi].contiguous() for r in rs]
+        gen = torch.Generator(device=dev).manual_seed(1 + rank)
+        # sequence-parallel: every rank holds (and generates) only its own rows
+        xs_loc = [torch.randn(hi - lo, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)]
+        rs_loc = [torch.randn(hi - lo, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)]
+    else:
+        xs = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)]
+        rs = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)]
+        dys = [torch.randn(batch, seq, hidden, device=dev, generator=gen).to(dt) for _ in range(nbuf)] if train else None
+        if world > 1:
+            tp = TensorParallelFFN(ffn, chunks=args.tp_chunks)
     if world > 1:
         ffn = None                                     # the unsharded copy is not needed any more
         torch.cuda.empty_cache()
@@ -329,7 +337,8 @@ def run_ours(args):
     k_ev = []                                          # (start, end) events around the dominant kernel
 
     def step(i, instrument=False):
-        x, r = xs[i % nbuf], rs[i % nbuf]
+        if fused is None:
+            x, r = xs[i % nbuf], rs[i % nbuf]
         if train:
             x = x.detach().requires_grad_(True)
             normed = norm(x, residual=r)
@@ -483,7 +492,7 @@ def run_ours(args):
 
     extra = None
     if world == 1 and not train and not args.no_extra:
-        del xs, rs, d_x, d_r
+        xs = rs = d_x = d_r = None
         torch.cuda.empty_cache()
         extra = extra_numbers(dev, peaks)
 
@@ -497,10 +506,11 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong",
+        "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": label + (" fwd+bwd (all weights trainable)" if train else " forward"),
-                   "hidden": hidden, "hidden_dim": inter, "global_batch_tokens": tokens,
+                   "hidden": hidden, "hidden_dim": inter, "global_batch_tokens": tokens, "tokens_per_gpu": tokens // world,
                    "parallelism": (f"tp{world} ({args.tp_impl}), sequence-parallel norm" if world > 1 else "single-gpu"),
                    "l2_policy": "inputs larger than L2: ~0.85 GB touched per step, 2 rotating activation buffers",
                    "step_tflops": step_tflops, "step_frac_of_bf16_peak": step_tflops * (1 if world == 1 else 1.0 / world) / peaks["bf16_tflops"]},
@@ -523,6 +533,8 @@ def main():
     ap.add_argument("--mode", choices=["prefill", "train"], default="prefill")
     ap.add_argument("--tp-chunks", type=int, default=4)
     ap.add_argument("--tp-impl", choices=["fused", "nccl"], default="fused")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="N > 1: weak = 4x2048 tokens per GPU (global batch grows with N), strong = 4x2048 tokens in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (RMSNorm GB/s, decode, 90B, train)")
     args = ap.parse_args()

@@ -192,8 +192,10 @@ L32_API int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, 
  * Flags are uint32 step counters ("epoch", monotonic, starting at 1) living in each rank's own memory.
  */
 
-/* flag[index] := value on every rank, after everything this stream did before is visible system-wide. */
-L32_API int l32_tp_signal(void* const* peer_flags, int world, int index, uint32_t value, void* stream);
+/* flag[index] := value on every rank, after everything this stream did before is visible system-wide.
+ * zero8 : optional, 8 uint32 of this rank's memory cleared by the same kernel (the `done` counters of the next
+ *         l32_tp_swiglu_forward_allgather -- saves a memset launch). */
+L32_API int l32_tp_signal(void* const* peer_flags, int world, int index, uint32_t value, uint32_t* zero8, void* stream);
 
 /* Plain SM copy between (peer) buffers: the NVLink bandwidth reference for the fused kernels (pull when src is peer
  * memory, push when dst is).  bytes % 16 == 0; `ctas` CTAs of `warps` warps, `unroll` (4, 8 or 16) loads in flight per lane. */
@@ -205,7 +207,8 @@ L32_API int l32_tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas,
  *              warps of the tcgen05 GEMM CTAs) while the tensor cores already work on the rows that have arrived;
  *              tiles are visited starting at the own rows, then rank+1, rank+2, ... (the pull order).
  *   ready    : own flags, ready[s] >= epoch once rank s has written its rows (see l32_tp_signal).
- *   done     : own scratch counters, `world` uint32, zeroed by this call (cudaMemsetAsync on `stream`).
+ *   done     : own scratch counters, 8 uint32, which must be ZERO on entry (pass them as `zero8` to the l32_tp_signal
+ *              that announces this rank's rows, or clear them with a memset).
  *   w_gate, w_up : this rank's shard [inter_local, hidden]; act : [tokens, inter_local].
  */
 L32_API int l32_tp_swiglu_forward_allgather(void* x_full, const void* const* peer_x, const uint32_t* ready, uint32_t* done,

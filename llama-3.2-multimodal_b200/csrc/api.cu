@@ -477,12 +477,12 @@ int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t 
     return gemm_sm100(g, as_stream(stream));
 }
 
-int l32_tp_signal(void* const* peer_flags, int world, int index, uint32_t value, void* stream) {
+int l32_tp_signal(void* const* peer_flags, int world, int index, uint32_t value, uint32_t* zero8, void* stream) {
     if (peer_flags == nullptr) return L32_ERR_NULL;
     if (world < 1 || world > kMaxTpWorld || index < 0) return L32_ERR_BAD_SHAPE;
     for (int i = 0; i < world; ++i)
         if (peer_flags[i] == nullptr) return L32_ERR_NULL;
-    return static_cast<int>(tp_signal(peer_flags, world, index, value, as_stream(stream)));
+    return static_cast<int>(tp_signal(peer_flags, world, index, value, zero8, as_stream(stream)));
 }
 
 int l32_tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, void* stream) {
@@ -519,8 +519,6 @@ int l32_tp_swiglu_forward_allgather(void* x_full, const void* const* peer_x, con
     g.cta_group = 2;
     if (world > 1) {
         if (peer_x == nullptr || ready == nullptr || done == nullptr) return L32_ERR_NULL;
-        cudaError_t e = cudaMemsetAsync(done, 0, sizeof(uint32_t) * kMaxTpWorld, as_stream(stream));
-        if (e != cudaSuccess) return static_cast<int>(e);
         g.ag.world = world;
         g.ag.rank = rank;
         g.ag.rows_per_rank = static_cast<int>(rows_per_rank);

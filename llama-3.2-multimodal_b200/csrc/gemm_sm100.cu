@@ -240,6 +240,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     if constexpr (kCtaGroup == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) overlapped the tail of the
+    // previous kernel of the stream; from here on its results are needed.  The next kernel may be scheduled as soon as
+    // SM resources free up (it orders itself behind this grid with griddepcontrol.wait).
+    pdl_launch_dependents();
+    pdl_wait_prior_grid();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -557,13 +562,15 @@ int launch(const GemmKernelParams& kp, int num_tiles, int max_ctas, cudaStream_t
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kCtaGroup;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, kp);
     if (e == cudaSuccess) count_launch();
     return static_cast<int>(e);

@@ -16,8 +16,11 @@ struct PeerFlags {
     uint32_t* ptr[kMaxTpWorld];
 };
 
-__global__ void tp_signal_kernel(PeerFlags flags, int world, int index, uint32_t value) {
+__global__ void tp_signal_kernel(PeerFlags flags, int world, int index, uint32_t value, uint32_t* zero8) {
     const int d = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait_prior_grid();   // the kernel whose completion is being announced
+    if (zero8 != nullptr && d < kMaxTpWorld) zero8[d] = 0u;   // arrival counters of the next fused all-gather
     if (d < world) {
         __threadfence_system();   // everything this GPU wrote before (earlier kernels of the stream) is visible first
         st_release_sys_u32(flags.ptr[d] + index, value);
@@ -37,6 +40,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) tp_reduce_partials_kernel(const T* slots, const uint32_t* flags, uint32_t epoch,
                                                                  int world, int rank, const T* addend, T* __restrict__ y,
                                                                  int64_t rows, int64_t slot_rows, int hidden) {
+    pdl_wait_prior_grid();   // this rank's own slot was written by the down GEMM launched before
     if (threadIdx.x < world && static_cast<int>(threadIdx.x) != rank) wait_flag_ge<true>(&flags[threadIdx.x], epoch);
     __syncthreads();
     const int64_t nvec = rows * hidden / 8;
@@ -105,12 +109,26 @@ cudaError_t tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int
     return cudaGetLastError();
 }
 
-cudaError_t tp_signal(void* const* peer_flags, int world, int index, uint32_t value, cudaStream_t s) {
+static cudaLaunchConfig_t pdl_config(unsigned grid, unsigned block, cudaStream_t s, cudaLaunchAttribute* attr) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cfg;
+}
+
+cudaError_t tp_signal(void* const* peer_flags, int world, int index, uint32_t value, uint32_t* zero8, cudaStream_t s) {
     PeerFlags f;
     for (int i = 0; i < kMaxTpWorld; ++i) f.ptr[i] = i < world ? static_cast<uint32_t*>(peer_flags[i]) : nullptr;
-    tp_signal_kernel<<<1, 32, 0, s>>>(f, world, index, value);
-    count_launch();
-    return cudaGetLastError();
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = pdl_config(1, 32, s, attr);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tp_signal_kernel, f, world, index, value, zero8);
+    if (e == cudaSuccess) count_launch();
+    return e;
 }
 
 cudaError_t tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_t epoch, int world, int rank,
@@ -121,16 +139,18 @@ cudaError_t tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_
     int64_t blocks = (nvec + 255) / 256;
     const int64_t cap = static_cast<int64_t>(num_sms()) * 8;
     if (blocks > cap) blocks = cap;
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = pdl_config(static_cast<unsigned>(blocks), 256, s, attr);
+    cudaError_t e;
     if (dtype == L32_BF16)
-        tp_reduce_partials_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), 256, 0, s>>>(
-            static_cast<const __nv_bfloat16*>(slots), flags, epoch, world, rank, static_cast<const __nv_bfloat16*>(addend),
-            static_cast<__nv_bfloat16*>(y), rows, slot_rows, hidden);
+        e = cudaLaunchKernelEx(&cfg, tp_reduce_partials_kernel<__nv_bfloat16>, static_cast<const __nv_bfloat16*>(slots), flags,
+                               epoch, world, rank, static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(y),
+                               rows, slot_rows, hidden);
     else
-        tp_reduce_partials_kernel<__half><<<static_cast<unsigned>(blocks), 256, 0, s>>>(
-            static_cast<const __half*>(slots), flags, epoch, world, rank, static_cast<const __half*>(addend),
-            static_cast<__half*>(y), rows, slot_rows, hidden);
-    count_launch();
-    return cudaGetLastError();
+        e = cudaLaunchKernelEx(&cfg, tp_reduce_partials_kernel<__half>, static_cast<const __half*>(slots), flags, epoch, world,
+                               rank, static_cast<const __half*>(addend), static_cast<__half*>(y), rows, slot_rows, hidden);
+    if (e == cudaSuccess) count_launch();
+    return e;
 }
 
 }  // namespace l32

@@ -344,11 +344,12 @@ def _ptr_array(ptrs):
     return arr
 
 
-def tp_signal(peer_flag_ptrs, index, value, device):
-    """flag[index] := value on every rank (host list of `world` device pointers to each rank's uint32 flag array)."""
+def tp_signal(peer_flag_ptrs, index, value, device, zero8=None):
+    """flag[index] := value on every rank (host list of `world` device pointers to each rank's uint32 flag array);
+    optionally clears 8 uint32 counters (`zero8`) in the same kernel."""
     arr = _ptr_array(peer_flag_ptrs)
     with torch.cuda.device(device):
-        check(lib().l32_tp_signal(arr, len(peer_flag_ptrs), int(index), int(value),
+        check(lib().l32_tp_signal(arr, len(peer_flag_ptrs), int(index), int(value), _ptr(zero8),
                                   torch.cuda.current_stream(device).cuda_stream), "l32_tp_signal")
 
 

@@ -216,7 +216,7 @@ class FusedTensorParallelBlock:
         lo, hi, _ = self.rows_of(tokens)
         if hi > lo:
             ops.add_rmsnorm_forward(x_local, self.gamma, residual_local, self.eps, want_rms=False, out=b.normed[lo:hi])
-        ops.tp_signal(b.peer_flags, FLAG_READY + b.rank, self.epoch, b.normed.device)
+        ops.tp_signal(b.peer_flags, FLAG_READY + b.rank, self.epoch, b.normed.device, zero8=b.done)
 
     def phase_gate_up(self, tokens):
         b = self.bufs
