@@ -198,8 +198,11 @@ L32_API int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, 
 L32_API int l32_tp_signal(void* const* peer_flags, int world, int index, uint32_t value, uint32_t* zero8, void* stream);
 
 /* Plain SM copy between (peer) buffers: the NVLink bandwidth reference for the fused kernels (pull when src is peer
- * memory, push when dst is).  bytes % 16 == 0; `ctas` CTAs of `warps` warps, `unroll` (4, 8 or 16) loads in flight per lane. */
-L32_API int l32_tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, void* stream);
+ * memory, push when dst is).  bytes % 16 == 0; `ctas` CTAs of `warps` warps, `unroll` (4, 8 or 16) loads in flight per lane.
+ * seg_bytes = 0: linear copy; otherwise the buffer is walked like a GEMM epilogue walks its output (runs of seg_bytes
+ * contiguous bytes at a row pitch of 8192 bytes), to measure what short contiguous runs cost on NVLink. */
+L32_API int l32_tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, int seg_bytes,
+                             void* stream);
 
 /* Fused all-gather + gate/up projection + SiLU*mul.
  *   x_full   : this rank's [tokens, hidden] activation buffer; only rows [rank*rows_per_rank, ...) are valid on

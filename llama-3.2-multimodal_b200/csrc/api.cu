@@ -485,11 +485,12 @@ int l32_tp_signal(void* const* peer_flags, int world, int index, uint32_t value,
     return static_cast<int>(tp_signal(peer_flags, world, index, value, zero8, as_stream(stream)));
 }
 
-int l32_tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, void* stream) {
+int l32_tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, int seg_bytes, void* stream) {
     if (dst == nullptr || src == nullptr) return L32_ERR_NULL;
     if (!is_aligned16(dst) || !is_aligned16(src) || (bytes % 16) != 0) return L32_ERR_BAD_ALIGN;
     if (ctas < 1 || warps < 1 || warps > 32) return L32_ERR_BAD_SHAPE;
-    return static_cast<int>(tp_peer_copy(dst, src, bytes, ctas, warps, unroll, as_stream(stream)));
+    if (seg_bytes != 0 && (seg_bytes < 16 || seg_bytes > 8192 || (8192 % seg_bytes) != 0 || (bytes % 8192) != 0)) return L32_ERR_BAD_SHAPE;
+    return static_cast<int>(tp_peer_copy(dst, src, bytes, ctas, warps, unroll, seg_bytes, as_stream(stream)));
 }
 
 int l32_tp_swiglu_forward_allgather(void* x_full, const void* const* peer_x, const uint32_t* ready, uint32_t* done,

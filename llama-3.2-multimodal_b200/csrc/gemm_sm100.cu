@@ -70,6 +70,8 @@ struct GemmKernelParams {
     long long ldd;
     int n_act;              // EPI_SWIGLU: act columns per tile (UMMA N = 2 * n_act), multiple of 16, <= 128
     int m_rotate;           // m-tiles are visited starting at this tile index (wrapping around)
+    int m_il_world;         // > 0: interleaved visiting order of the fused reduce-scatter -- consecutive m-tiles belong to
+    int m_il_tpc;           //      different owner ranks (tiles per owner chunk = m_il_tpc), own rank last in each round
     TpAllGather ag;         // all-gather of A fused into the kernel (world == 0: off)
     TpReduceScatter rs;     // reduce-scatter fused into the EPI_STORE epilogue (world == 0: off)
 };
@@ -120,15 +122,27 @@ L32_DEVICE void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.
 struct TileCoord {
     int m_blk, n_blk;
 };
-L32_DEVICE TileCoord tile_coord(int t, int tiles_m, int tiles_n, int group, int m_rotate) {
-    const int per_group = group * tiles_n;
+struct TileOrder {
+    int tiles_m, tiles_n, group, m_rotate, il_world, il_tpc, il_rank;
+};
+L32_DEVICE TileCoord tile_coord(int t, const TileOrder& o) {
+    const int per_group = o.group * o.tiles_n;
     const int g = t / per_group;
-    const int first_m = g * group;
-    const int gsize = min(group, tiles_m - first_m);
+    const int first_m = g * o.group;
+    const int gsize = min(o.group, o.tiles_m - first_m);
     const int r = t - g * per_group;
     TileCoord c;
-    c.m_blk = first_m + r % gsize + m_rotate;
-    if (c.m_blk >= tiles_m) c.m_blk -= tiles_m;
+    const int logical = first_m + r % gsize;
+    if (o.il_world > 0) {
+        // round-robin over the owner ranks: NVLink stays busy for the whole kernel and every receiver is fed evenly
+        const int j = logical / o.il_world, k = logical - j * o.il_world;
+        int owner = o.il_rank + 1 + k;
+        if (owner >= o.il_world) owner -= o.il_world;
+        c.m_blk = owner * o.il_tpc + j;
+    } else {
+        c.m_blk = logical + o.m_rotate;
+        if (c.m_blk >= o.tiles_m) c.m_blk -= o.tiles_m;
+    }
     c.n_blk = r / gsize;
     return c;
 }
@@ -213,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     const int cluster_id = blockIdx.x / kCtaGroup;
     const int num_clusters = gridDim.x / kCtaGroup;
     const int num_tiles = p.tiles_m * p.tiles_n;
+    const TileOrder order = {p.tiles_m, p.tiles_n, p.raster_group, p.m_rotate, p.m_il_world, p.m_il_tpc, p.rs.rank};
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.map_a[0]);
@@ -251,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-                const TileCoord tc = tile_coord(t, p.tiles_m, p.tiles_n, p.raster_group, p.m_rotate);
+                const TileCoord tc = tile_coord(t, order);
                 const int m0 = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM;
                 const int n0 = tc.n_blk * kTileNOut;
                 if (p.ag.world > 1 && m0 < p.m) {
@@ -341,7 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         uint32_t acc = 0, acc_phase = 0;
         const size_t esz = sizeof(T);
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-            const TileCoord tc = tile_coord(t, p.tiles_m, p.tiles_n, p.raster_group, p.m_rotate);
+            const TileCoord tc = tile_coord(t, order);
             const int row = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM + q * 32 + lane;
             const int n0 = tc.n_blk * kTileNOut;
             const bool row_ok = row < p.m;
@@ -679,6 +694,14 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
     kp.bias[0] = g.bias[0]; kp.bias[1] = g.bias[1];
     kp.ldd = g.ldd;
     kp.m_rotate = (g.m_rotate_rows > 0) ? (g.m_rotate_rows / tile_m) % kp.tiles_m : 0;
+    if (g.rs.world > 1 && g.rs.rows_per_rank > 0 && (g.rs.rows_per_rank % tile_m) == 0 &&
+        kp.tiles_m == g.rs.world * (g.rs.rows_per_rank / tile_m)) {
+        kp.m_il_world = g.rs.world;
+        kp.m_il_tpc = g.rs.rows_per_rank / tile_m;
+        if (const char* env = getenv("L32_RS_INTERLEAVE")) {   // tuning knob for experiments only
+            if (atoi(env) == 0) kp.m_il_world = 0;
+        }
+    }
     kp.ag = g.ag;
     kp.rs = g.rs;
     if (g.ag.world > kMaxTpWorld || g.rs.world > kMaxTpWorld) return L32_ERR_BAD_SHAPE;

@@ -95,7 +95,8 @@ int ffn_decode_linear(const void* a, const void* w, const void* bias, const void
 
 // ---- tp.cu : tensor-parallel glue (cross-GPU flags, reduction of the partial slots)
 cudaError_t tp_signal(void* const* peer_flags, int world, int index, uint32_t value, uint32_t* zero8, cudaStream_t s);
-cudaError_t tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, cudaStream_t s);
+cudaError_t tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, int seg_bytes,
+                         cudaStream_t s);
 cudaError_t tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_t epoch, int world, int rank,
                                const void* addend, void* y, int64_t rows, int64_t slot_rows, int hidden, int dtype,
                                cudaStream_t s);

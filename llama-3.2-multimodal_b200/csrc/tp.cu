@@ -80,31 +80,42 @@ __global__ void __launch_bounds__(256) tp_reduce_partials_kernel(const T* slots,
 
 // Plain peer copy (pull when src is peer memory, push when dst is): the NVLink bandwidth reference the fused kernels are
 // compared with.  `warps` warps per CTA, 16-byte vectors, kUnroll loads in flight per lane.
+// seg_bytes < 8192 emulates a GEMM epilogue: the buffer is viewed as rows of 8192 bytes and consecutive work items cover
+// one `seg_bytes` segment of a row, then the same column block of the NEXT row (stride 8 KiB), ... -- i.e. contiguous
+// runs of only seg_bytes on the wire.  seg_bytes = 0: fully linear copy.
 template <int kUnroll>
 __global__ void __launch_bounds__(1024) tp_peer_copy_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
-                                                            long long nvec) {
+                                                            long long nvec, int seg_bytes) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long vps = seg_bytes > 0 ? seg_bytes / 16 : 1;
+    const long long nrows = nvec * 16 / 8192;
+    auto offset = [&](long long v) -> long long {
+        if (seg_bytes <= 0) return v * 16;
+        const long long seg = v / vps, in = v % vps;
+        return (seg % nrows) * 8192 + (seg / nrows) * seg_bytes + in * 16;
+    };
     for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < nvec; v += stride * kUnroll) {
         uint4 buf[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
-            if (v + u * stride < nvec) buf[u] = ld_relaxed_sys_v4(src + (v + u * stride) * 16);
+            if (v + u * stride < nvec) buf[u] = ld_relaxed_sys_v4(src + offset(v + u * stride));
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u)
-            if (v + u * stride < nvec) *reinterpret_cast<uint4*>(dst + (v + u * stride) * 16) = buf[u];
+            if (v + u * stride < nvec) *reinterpret_cast<uint4*>(dst + offset(v + u * stride)) = buf[u];
     }
 }
 
 }  // namespace
 
-cudaError_t tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, cudaStream_t s) {
+cudaError_t tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int warps, int unroll, int seg_bytes,
+                         cudaStream_t s) {
     const long long nvec = static_cast<long long>(bytes / 16);
     if (nvec == 0) return cudaSuccess;
     auto* d = static_cast<uint8_t*>(dst);
     auto* sp = static_cast<const uint8_t*>(src);
-    if (unroll >= 16) tp_peer_copy_kernel<16><<<ctas, warps * 32, 0, s>>>(d, sp, nvec);
-    else if (unroll >= 8) tp_peer_copy_kernel<8><<<ctas, warps * 32, 0, s>>>(d, sp, nvec);
-    else tp_peer_copy_kernel<4><<<ctas, warps * 32, 0, s>>>(d, sp, nvec);
+    if (unroll >= 16) tp_peer_copy_kernel<16><<<ctas, warps * 32, 0, s>>>(d, sp, nvec, seg_bytes);
+    else if (unroll >= 8) tp_peer_copy_kernel<8><<<ctas, warps * 32, 0, s>>>(d, sp, nvec, seg_bytes);
+    else tp_peer_copy_kernel<4><<<ctas, warps * 32, 0, s>>>(d, sp, nvec, seg_bytes);
     count_launch();
     return cudaGetLastError();
 }

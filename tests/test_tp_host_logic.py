@@ -1,0 +1,44 @@
+"""CPU checks of the tensor-parallel host logic (no GPU, no process group): row / shard partitions."""
+import pytest
+import torch
+
+from llama32_b200.tp import FusedTensorParallelBlock, TpRankBuffers, shard_ffn_weights, shard_range
+
+
+@pytest.mark.parametrize("inter,world", [(14336, 8), (28672, 8), (14336, 3), (688, 2), (1152, 3), (104, 4), (8, 2)])
+def test_shard_range_is_a_partition(inter, world):
+    spans = [shard_range(inter, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == inter
+    for (lo, hi), (lo2, _) in zip(spans, spans[1:]):
+        assert lo <= hi == lo2
+    assert all((hi - lo) % 8 == 0 for lo, hi in spans[:-1])          # TMA row pitch / 16-byte stores
+    if inter // 128 >= world:
+        assert all(lo % 128 == 0 for lo, _ in spans)                  # shards start on an act tile of the tcgen05 kernel
+
+
+def test_shard_ffn_weights_reassemble():
+    torch.manual_seed(0)
+    wg, wu, wd = torch.randn(384, 64), torch.randn(384, 64), torch.randn(64, 384)
+    x = torch.randn(5, 64)
+    full = torch.nn.functional.linear(torch.nn.functional.silu(x @ wg.t()) * (x @ wu.t()), wd)
+    acc = torch.zeros_like(full)
+    for r in range(3):
+        g, u, d = shard_ffn_weights(wg, wu, wd, 3, r)
+        assert d.is_contiguous()
+        acc += torch.nn.functional.linear(torch.nn.functional.silu(x @ g.t()) * (x @ u.t()), d)
+    assert torch.allclose(acc, full, atol=1e-4)
+
+
+@pytest.mark.parametrize("tokens,world", [(8192, 8), (777, 3), (5, 8), (1000, 4), (1, 2)])
+def test_rows_of_covers_every_row_once(tokens, world):
+    class _B:   # the only fields rows_of reads
+        pass
+    covered = []
+    for r in range(world):
+        blk = FusedTensorParallelBlock.__new__(FusedTensorParallelBlock)
+        blk.bufs = _B()
+        blk.bufs.rank, blk.bufs.world = r, world
+        lo, hi, per = blk.rows_of(tokens)
+        assert 0 <= lo <= hi <= tokens and hi - lo <= per == TpRankBuffers.slot_rows_for(tokens, world)
+        covered += list(range(lo, hi))
+    assert covered == list(range(tokens))
