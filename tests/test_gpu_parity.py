@@ -434,6 +434,20 @@ def test_decode_shapes_11b(batch):
     close(y[:1], yo, FWD, "decode y[0] vs CPU oracle")
 
 
+def test_decode_shape_90b():
+    """KV-cached decode at the 90B shape (hidden 8192, hidden_dim 28672; 1.4 GB of weights streamed per step)."""
+    hidden, inter, batch = 8192, 28672, 4
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    x = torch.randn(batch, 1, hidden, device=DEV, generator=gen).bfloat16()
+    wg = ((torch.rand(inter, hidden, device=DEV, generator=gen) * 2 - 1) / 90).bfloat16()
+    wu = ((torch.rand(inter, hidden, device=DEV, generator=gen) * 2 - 1) / 90).bfloat16()
+    wd = ((torch.rand(hidden, inter, device=DEV, generator=gen) * 2 - 1) / 170).bfloat16()
+    y, _, _ = ops.ffn_forward(x, wg, wu, wd)
+    xf = x.float().view(batch, hidden)
+    ref = torch.nn.functional.linear(torch.nn.functional.silu(xf @ wg.float().t()) * (xf @ wu.float().t()), wd.float())
+    close(y.view(batch, hidden), ref, FWD, "decode 90B y")
+
+
 @pytest.mark.parametrize("tokens,hidden,inter,dtype,bias", [
     (1, 256, 688, torch.bfloat16, False),      # config-1 shape: ragged last row block (688 = 10.75 * 64)
     (3, 264, 696, torch.bfloat16, True),       # K tail (264 = 4.125 * 64), biases
