@@ -488,6 +488,16 @@ def run_ours(args):
                     "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_step,
                     "frac_of_sustained_peak": (achieved / peaks["bf16_tflops_sustained"]) if peaks["bf16_tflops_sustained"] else None,
                     "traffic": None, "traffic_note": "see profiles/ for dram__bytes of this kernel from ncu --set full"}
+        if world == 1 and args.workload == "11b":
+            try:   # DRAM bytes of this kernel at this shape from the committed ncu --set full capture (per launch)
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    tr = json.load(f)["gemm_swiglu_11b_8192tok"]
+                roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                roofline["traffic_note"] = (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch, {tr['source']}; "
+                                            f"algorithmic bytes {tr['algorithmic_bytes']} (x, both weight matrices, act): the "
+                                            "re-reads are L2 misses of re-used operand tiles, DRAM runs at ~16 % of peak")
+            except (OSError, KeyError, ValueError):
+                pass
     step_tflops = flops_step / (ms_step * 1e-3) / 1e12
 
     extra = None

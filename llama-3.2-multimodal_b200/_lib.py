@@ -13,7 +13,8 @@ import re
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libl32ffn.so")
+# L32_LIB_PATH: A/B experiments against another build of the same ABI (never set in production)
+LIB_PATH = os.environ.get("L32_LIB_PATH") or os.path.join(_HERE, "libl32ffn.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "l32_ffn.h")
 
 _lock = threading.Lock()

@@ -6,12 +6,14 @@
 // swiglu_backward_kernel (reference Tools/swiglu/swiglu.cu:58-100, :228-272, :179-223) and the cuBLAS
 // F.linear calls of the live PyTorch path (reference Tools/swiglu/FusedSwiglu.py:18-20, Model/model.py:214-217).
 //
-// Structure (one CTA per SM, 320 threads; optional CTA pair = cta_group::2 with UMMA M = 256):
+// Structure (one CTA per SM, 448 threads; optional CTA pair = cta_group::2 with UMMA M = 256):
 //   warp 0   : TMA producer  (cp.async.bulk.tensor, 128-byte swizzle, ring of kStages smem slots)
 //   warp 1   : MMA issuer    (tcgen05.mma kind::f16, one elected thread of the leader CTA)
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue      (tcgen05.ld -> registers -> fused math -> 16-byte global stores)
-//   warps 2-3, 8-9: all-gather pullers of the tensor-parallel variant (idle otherwise): NVLink loads from peer memory
+//   warps 4-11: epilogue     (tcgen05.ld -> registers -> fused math -> global stores).  Two groups of four warps
+//                            (one warp per TMEM lane quarter each); the SwiGLU epilogues, which read / write several
+//                            [M, I] tensors per tile, split the columns of a tile between the groups, EPI_STORE uses one
+//   warps 2-3, 12-13: all-gather pullers of the tensor-parallel variant (idle otherwise): NVLink loads from peer memory
 // TMEM holds two 256-column fp32 accumulator stages, so the epilogue of tile t overlaps the main loop of
 // tile t+1.  Tiles are visited in a grouped raster so concurrently running CTAs share A and B panels in L2.
 //
@@ -38,7 +40,7 @@ constexpr int kBlockM = 128;   // accumulator rows per CTA (= TMEM lanes)
 constexpr int kBlockK = 64;    // one 128-byte swizzle atom of 16-bit elements
 constexpr int kUmmaK = 16;
 constexpr int kAccCols = 256;  // TMEM columns per accumulator stage (= UMMA N)
-constexpr int kThreads = 320;             // warps 0-1 TMA / MMA, 2-3 + 8-9 all-gather pullers (2 allocates TMEM), 4-7 epilogue
+constexpr int kThreads = 448;             // warps 0-1 TMA / MMA, 2-3 + 12-13 all-gather pullers (2 allocates TMEM), 4-11 epilogue
 constexpr int kPullWarps = 4;
 constexpr int kAtomBytes = kBlockK * 128;   // 64 rows x 128 B = 8 KiB: one swizzle-atom column of a tile
 constexpr int kEpiRowPitch = 272;           // 256 B of one output row + 16 B so the lanes' st.shared hit distinct banks
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     using Cfg = TileCfg<kCtaGroup>;
     constexpr int kStages = Cfg::kStages;
     const int kTileNOut = (kEpi == EPI_SWIGLU) ? p.n_act : 256;   // output columns per tile
+    constexpr int kEpiWarps = (kEpi == EPI_STORE) ? 4 : 8;        // epilogue warps per CTA that take part
     // bytes the pair's TMA loads deliver per ring stage (EPI_SWIGLU stages n_act gate + n_act up weight rows)
     const uint32_t stage_tx = (kEpi == EPI_SWIGLU) ? static_cast<uint32_t>(kCtaGroup * Cfg::kABytes + 2 * p.n_act * 128)
                                                    : static_cast<uint32_t>(Cfg::kStageBytes * kCtaGroup);
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);               // one tcgen05.commit
-            mbar_init(&tempty_bar[i], 4 * kCtaGroup);  // one arrival per epilogue warp of every CTA
+            mbar_init(&tempty_bar[i], kEpiWarps * kCtaGroup);  // one arrival per (active) epilogue warp of every CTA
         }
         fence_mbar_init();
     }
@@ -343,16 +346,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 if (acc == 0) acc_phase ^= 1u;
             }
         }
-    } else if (warp == 2 || warp == 3 || warp >= 8) {
+    } else if (warp == 2 || warp == 3 || warp >= 12) {
         // ------------------------------------------------------------------ all-gather pullers (tensor-parallel only)
         if (p.ag.world > 1) {
-            const int idx = static_cast<int>(warp >= 8 ? warp - 6 : warp - 2);   // 0..3
+            const int idx = static_cast<int>(warp >= 12 ? warp - 10 : warp - 2);   // 0..3
             ag_pull(p.ag, p.m, static_cast<size_t>(p.k[0]) * sizeof(T), static_cast<int>(blockIdx.x) * kPullWarps + idx,
                     static_cast<int>(gridDim.x) * kPullWarps, lane);
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 4 + kEpiWarps) {
         // ------------------------------------------------------------------ epilogue
-        const uint32_t q = warp - 4;                       // TMEM lane quarter owned by this warp
+        const uint32_t q = (warp - 4) & 3u;                // TMEM lane quarter owned by this warp (warp id % 4)
+        const uint32_t eg = (warp - 4) >> 2;               // epilogue group: which share of the tile's columns
+        (void)eg;
         uint32_t acc = 0, acc_phase = 0;
         const size_t esz = sizeof(T);
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
@@ -467,13 +472,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 for (; c0 + 32 <= p.n_act; c0 += 32) {
                     const int col = n0 + c0;
                     if (col >= p.n) break;
+                    if (((c0 >> 5) & 1) != static_cast<int>(eg)) continue;   // the other warp group's chunk
                     uint32_t g[32], u[32];
                     tmem_ld_32x32b_x32(taddr + c0, g);
                     tmem_ld_32x32b_x32(taddr + p.n_act + c0, u);
                     tmem_ld_wait();
                     finish(g, u, col, std::integral_constant<int, 32>{});
                 }
-                if (c0 < p.n_act && n0 + c0 < p.n) {   // n_act = 32 k + 16: one 16-column tail
+                if (c0 < p.n_act && n0 + c0 < p.n && ((c0 >> 5) & 1) == static_cast<int>(eg)) {   // n_act = 32 k + 16: 16-column tail
                     uint32_t g[16], u[16];
                     tmem_ld_32x32b_x16(taddr + c0, g);
                     tmem_ld_32x32b_x16(taddr + p.n_act + c0, u);
@@ -482,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 }
             } else {   // EPI_SWIGLU_BWD
 #pragma unroll 1
-                for (int c = 0; c < kAccCols / 32; ++c) {
+                for (int c = static_cast<int>(eg); c < kAccCols / 32; c += 2) {
                     const int col = n0 + c * 32;
                     if (col >= p.n) break;
                     uint32_t v[32];
