@@ -228,6 +228,19 @@ L32_API int l32_tp_linear_forward_reduce_scatter(const void* a, const void* w, v
                                                  int64_t rows_per_rank, int64_t tokens, int in_local, int out_features,
                                                  int dtype, void* stream);
 
+/* The two calls above as ONE persistent kernel: gate/up tiles (all-gather pulled in) and down tiles (reduce-scatter pushed
+ * out) share the tile loop -- the down tiles of one group of rows are interleaved with the gate/up tiles of the next
+ * group, so the NVLink pushes overlap the (twice as long) gate/up math instead of only the down projection, and the
+ * intermediate act is consumed while it is still in L2.
+ *   act_ws   : [tokens, inter_local] scratch;  act_done : ceil(tokens / 256) uint32 scratch (cleared by this call);
+ *   other arguments as in l32_tp_swiglu_forward_allgather / l32_tp_linear_forward_reduce_scatter.
+ */
+L32_API int l32_tp_ffn_forward_fused(void* x_full, const void* const* peer_x, const uint32_t* ready, uint32_t* done,
+                                     uint32_t epoch, int rank, int world, int64_t rows_per_rank, const void* w_gate,
+                                     const void* w_up, const void* w_down, void* act_ws, uint32_t* act_done,
+                                     void* const* peer_slots, int64_t tokens, int hidden, int inter_local, int dtype,
+                                     void* stream);
+
 /* y[rows, hidden] = sum_s slots[s][rows, hidden] (+ addend), fp32 accumulation in rank order, after waiting until
  * flags[s] >= epoch for every s != rank.  slots : own [world, slot_rows, hidden] buffer the peers pushed into. */
 L32_API int l32_tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_t epoch, int world, int rank,

@@ -573,6 +573,67 @@ int l32_tp_linear_forward_reduce_scatter(const void* a, const void* w, void* con
     return gemm_sm100(g, as_stream(stream));
 }
 
+int l32_tp_ffn_forward_fused(void* x_full, const void* const* peer_x, const uint32_t* ready, uint32_t* done, uint32_t epoch,
+                             int rank, int world, int64_t rows_per_rank, const void* w_gate, const void* w_up,
+                             const void* w_down, void* act_ws, uint32_t* act_done, void* const* peer_slots, int64_t tokens,
+                             int hidden, int inter_local, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, inter_local)) return L32_ERR_BAD_SHAPE;
+    if (world < 1 || world > kMaxTpWorld || rank < 0 || rank >= world || rows_per_rank <= 0 ||
+        rows_per_rank * world < tokens || rows_per_rank > 0x7fffffff)
+        return L32_ERR_BAD_SHAPE;
+    if (tokens == 0) return L32_OK;
+    if (x_full == nullptr || w_gate == nullptr || w_up == nullptr || w_down == nullptr || act_ws == nullptr ||
+        act_done == nullptr || peer_slots == nullptr)
+        return L32_ERR_NULL;
+    cudaStream_t s = as_stream(stream);
+    const int tile_m = 256;
+    const int tiles_m = static_cast<int>((tokens + tile_m - 1) / tile_m);
+    cudaError_t e = cudaMemsetAsync(act_done, 0, sizeof(uint32_t) * static_cast<size_t>(tiles_m), s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    GemmProblem g = blank(static_cast<int>(tokens), inter_local, dtype);
+    g.k[0] = hidden;
+    g.a[0] = op(x_full, hidden, 0);
+    g.b[0] = op(w_gate, hidden, 0);
+    g.b[1] = op(w_up, hidden, 0);
+    g.epilogue = EPI_FFN_TP;
+    g.d[0] = act_ws;
+    g.ldd = inter_local;
+    g.cta_group = 2;
+    g.dn.w = w_down;
+    g.dn.ld = inter_local;
+    g.dn.n = hidden;
+    g.dn.act_done = act_done;
+    g.rs.world = world;
+    g.rs.rank = rank;
+    g.rs.rows_per_rank = static_cast<int>(rows_per_rank);
+    for (int o = 0; o < world; ++o) {
+        if (peer_slots[o] == nullptr || !is_aligned16(peer_slots[o])) return L32_ERR_NULL;
+        g.rs.peer_dst[o] = peer_slots[o];
+    }
+    int grp = static_cast<int>(rows_per_rank / tile_m);
+    if (grp < 1) grp = 1;
+    if (grp > 8) grp = 8;
+    g.raster_group = grp;   // one group of m-tiles = (a divisor of) one rank's chunk: pulls, math and pushes move in step
+    g.m_rotate_rows = static_cast<int>(rank * rows_per_rank);
+    if (world > 1) {
+        if (peer_x == nullptr || ready == nullptr || done == nullptr) return L32_ERR_NULL;
+        g.ag.world = world;
+        g.ag.rank = rank;
+        g.ag.rows_per_rank = static_cast<int>(rows_per_rank);
+        for (int r = 0; r < world; ++r) {
+            if (peer_x[r] == nullptr) return L32_ERR_NULL;
+            g.ag.peer_src[r] = peer_x[r];
+        }
+        g.ag.local_dst = x_full;
+        g.ag.ready = ready;
+        g.ag.done = done;
+        g.ag.epoch = epoch;
+        g.ag.done_base = 0;
+    }
+    return gemm_sm100(g, s);
+}
+
 int l32_tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_t epoch, int world, int rank, const void* addend,
                            void* y, int64_t rows, int64_t slot_rows, int hidden, int dtype, void* stream) {
     if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;

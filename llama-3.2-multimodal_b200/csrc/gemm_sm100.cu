@@ -76,6 +76,13 @@ struct GemmKernelParams {
     int m_il_tpc;           //      different owner ranks (tiles per owner chunk = m_il_tpc), own rank last in each round
     TpAllGather ag;         // all-gather of A fused into the kernel (world == 0: off)
     TpReduceScatter rs;     // reduce-scatter fused into the EPI_STORE epilogue (world == 0: off)
+    // EPI_FFN_TP: the down projection that shares the tile loop (A = act = d[0], K = n, B = w_down shard)
+    CUtensorMap map_a_dn, map_b_dn;
+    int k_dn, n_dn, tiles_n_dn;
+    int ffn_prefix;         // gate/up-only tiles at the head of every mixed round
+    int ffn_nowait;         // timing experiments only (L32_FFN_NOWAIT=1): skip the act_done wait -> WRONG results
+    uint32_t idesc_dn;
+    uint32_t* act_done;
 };
 
 // One operand tile of `rows` x 64 (K) elements into shared memory.
@@ -123,6 +130,7 @@ L32_DEVICE void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.
 
 struct TileCoord {
     int m_blk, n_blk;
+    int prob;   // EPI_FFN_TP: 0 = gate/up tile, 1 = down tile
 };
 struct TileOrder {
     int tiles_m, tiles_n, group, m_rotate, il_world, il_tpc, il_rank;
@@ -146,6 +154,49 @@ L32_DEVICE TileCoord tile_coord(int t, const TileOrder& o) {
         if (c.m_blk >= o.tiles_m) c.m_blk -= o.tiles_m;
     }
     c.n_blk = r / gsize;
+    c.prob = 0;
+    return c;
+}
+
+// EPI_FFN_TP tile sequence.  Rows are processed in groups of `group` m-tiles; round r holds the gate/up tiles of group r
+// and the down tiles of group r - 1 (whose act is complete or about to be), interleaved evenly after a gate/up-only
+// prefix so that (1) the NVLink pushes of the down epilogues are spread over the whole kernel instead of only its last
+// third and (2) nobody waits long for the act of the previous group.  Every tile depends only on tiles with a smaller
+// index, and every cluster walks its tiles in increasing order, so the waits cannot deadlock.
+struct FfnOrder {
+    int tiles_m, n_gu, n_dn, group, m_rotate, prefix;
+};
+L32_DEVICE TileCoord ffn_tile_coord(int t, const FfnOrder& o) {
+    const int A = o.group * o.n_gu, B = o.group * o.n_dn;
+    const int rounds = o.tiles_m / o.group;
+    int r, idx, prob;
+    if (t < A) {
+        r = 0; idx = t; prob = 0;
+    } else {
+        const int tt = t - A;
+        r = 1 + tt / (A + B);
+        const int i = tt - (r - 1) * (A + B);
+        if (r == rounds) {
+            idx = i; prob = 1;
+        } else if (i < o.prefix) {
+            idx = i; prob = 0;
+        } else {
+            const int i2 = i - o.prefix, A2 = A - o.prefix, T2 = A2 + B;
+            const int c0 = static_cast<int>(static_cast<long long>(i2) * A2 / T2);
+            const int c1 = static_cast<int>(static_cast<long long>(i2 + 1) * A2 / T2);
+            if (c1 > c0) { idx = o.prefix + c0; prob = 0; }
+            else { idx = i2 - c0; prob = 1; }
+        }
+    }
+    // within a group the tiles are m-major (all n-tiles of one row block, then the next row block): a row block's act is
+    // complete long before its down tiles come up (>= 1.5 waves of distance, also in the down-only last round)
+    const int g = prob ? r - 1 : r;
+    const int nt = prob ? o.n_dn : o.n_gu;
+    TileCoord c;
+    c.prob = prob;
+    c.m_blk = g * o.group + idx / nt + o.m_rotate;
+    if (c.m_blk >= o.tiles_m) c.m_blk -= o.tiles_m;
+    c.n_blk = idx % nt;
     return c;
 }
 
@@ -204,11 +255,13 @@ template <int kCtaGroup, int kEpi, typename T>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant__ GemmKernelParams p) {
     using Cfg = TileCfg<kCtaGroup>;
     constexpr int kStages = Cfg::kStages;
-    const int kTileNOut = (kEpi == EPI_SWIGLU) ? p.n_act : 256;   // output columns per tile
+    constexpr bool kTp = (kEpi == EPI_FFN_TP);
+    const int kTileNOut = (kEpi == EPI_SWIGLU || kTp) ? p.n_act : 256;   // output columns per (gate/up) tile
     constexpr int kEpiWarps = (kEpi == EPI_STORE) ? 4 : 8;        // epilogue warps per CTA that take part
     // bytes the pair's TMA loads deliver per ring stage (EPI_SWIGLU stages n_act gate + n_act up weight rows)
-    const uint32_t stage_tx = (kEpi == EPI_SWIGLU) ? static_cast<uint32_t>(kCtaGroup * Cfg::kABytes + 2 * p.n_act * 128)
-                                                   : static_cast<uint32_t>(Cfg::kStageBytes * kCtaGroup);
+    const uint32_t stage_tx_full = static_cast<uint32_t>(Cfg::kStageBytes * kCtaGroup);
+    const uint32_t stage_tx = (kEpi == EPI_SWIGLU || kTp) ? static_cast<uint32_t>(kCtaGroup * Cfg::kABytes + 2 * p.n_act * 128)
+                                                          : stage_tx_full;
 
     // 128-byte-swizzled tiles need 1024-byte alignment; the kernel has no static shared memory, so the dynamic window
     // starts aligned (checked: a misaligned base traps instead of corrupting tiles).
@@ -229,14 +282,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     const uint32_t rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
     const int cluster_id = blockIdx.x / kCtaGroup;
     const int num_clusters = gridDim.x / kCtaGroup;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_tiles = p.tiles_m * (p.tiles_n + (kTp ? p.tiles_n_dn : 0));
     const TileOrder order = {p.tiles_m, p.tiles_n, p.raster_group, p.m_rotate, p.m_il_world, p.m_il_tpc, p.rs.rank};
+    const FfnOrder forder = {p.tiles_m, p.tiles_n, p.tiles_n_dn, p.raster_group, p.m_rotate, p.ffn_prefix};
+    auto get_tile = [&](int t) -> TileCoord {
+        if constexpr (kTp) return ffn_tile_coord(t, forder);
+        else return tile_coord(t, order);
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.map_a[0]);
         tma_prefetch_desc(&p.map_b[0]);
         if (p.num_phases == 2) tma_prefetch_desc(&p.map_a[1]);
-        if (p.num_phases == 2 || kEpi == EPI_SWIGLU) tma_prefetch_desc(&p.map_b[1]);
+        if (p.num_phases == 2 || kEpi == EPI_SWIGLU || kTp) tma_prefetch_desc(&p.map_b[1]);
+        if constexpr (kTp) {
+            tma_prefetch_desc(&p.map_a_dn);
+            tma_prefetch_desc(&p.map_b_dn);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
@@ -269,10 +331,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-                const TileCoord tc = tile_coord(t, order);
+                const TileCoord tc = get_tile(t);
+                const bool dn = kTp && tc.prob == 1;                       // down tile of the fused feed-forward
+                const bool swiglu_tile = (kEpi == EPI_SWIGLU) || (kTp && !dn);
                 const int m0 = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM;
-                const int n0 = tc.n_blk * kTileNOut;
-                if (p.ag.world > 1 && m0 < p.m) {
+                const int n0 = tc.n_blk * (dn ? kAccCols : kTileNOut);
+                if (dn) {
+                    // its A operand is the act of this m-tile: every epilogue warp of every gate/up tile of the row
+                    // block must have stored (generic proxy, other SMs) before the TMA (async proxy) may read it
+                    if (!(p.ffn_nowait & 1))
+                        wait_flag_ge<false>(&p.act_done[tc.m_blk], static_cast<uint32_t>(p.tiles_n * kEpiWarps * kCtaGroup));
+                    if (!(p.ffn_nowait & 2)) fence_proxy_async_all();
+                }
+                if (!dn && p.ag.world > 1 && m0 < p.m) {
                     // the A rows of this tile may belong to other ranks: wait until every puller warp has landed them
                     const int c_lo = m0 / p.ag.rows_per_rank;
                     const int c_hi = (min(m0 + kBlockM, p.m) - 1) / p.ag.rows_per_rank;
@@ -285,14 +356,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     if (waited) fence_proxy_async_all();   // generic-proxy stores of other SMs -> TMA (async proxy) loads
                 }
                 for (int ph = 0; ph < p.num_phases; ++ph) {
-                    const int num_kb = (p.k[ph] + kBlockK - 1) / kBlockK;
+                    const int num_kb = ((dn ? p.k_dn : p.k[ph]) + kBlockK - 1) / kBlockK;
+                    const CUtensorMap* map_a = dn ? &p.map_a_dn : &p.map_a[ph];
+                    const CUtensorMap* map_b = dn ? &p.map_b_dn : &p.map_b[ph];
                     for (int kb = 0; kb < num_kb; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
                         uint8_t* sa = smem_a + stage * Cfg::kABytes;
                         uint8_t* sb = smem_b + stage * Cfg::kBBytes;
-                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-                        load_tile<kCtaGroup>(&p.map_a[ph], sa, &full_bar[stage], p.a_mn_major, m0, kBlockM, kb * kBlockK);
-                        if constexpr (kEpi == EPI_SWIGLU) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], swiglu_tile ? stage_tx : stage_tx_full);
+                        load_tile<kCtaGroup>(map_a, sa, &full_bar[stage], p.a_mn_major, m0, kBlockM, kb * kBlockK);
+                        if (swiglu_tile) {
                             if constexpr (kCtaGroup == 2) {
                                 // leader stages the gate rows, its peer the up rows of the same 128 act columns
                                 load_tile<2>(&p.map_b[rank], sb, &full_bar[stage], 0, n0, 128, kb * kBlockK);
@@ -301,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                                 load_tile<1>(&p.map_b[1], sb + p.n_act * 128, &full_bar[stage], 0, n0, 128, kb * kBlockK);
                             }
                         } else {
-                            load_tile<kCtaGroup>(&p.map_b[ph], sb, &full_bar[stage], p.b_mn_major,
+                            load_tile<kCtaGroup>(map_b, sb, &full_bar[stage], p.b_mn_major,
                                                  n0 + static_cast<int>(rank) * Cfg::kBRows, Cfg::kBRows, kb * kBlockK);
                         }
                         if (rank != 0) mbar_arrive_remote(&full_bar[stage], 0);
@@ -319,12 +392,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const uint32_t b_lbo = p.b_mn_major ? kAtomBytes : 0;
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                bool dn = false;
+                if constexpr (kTp) dn = get_tile(t).prob == 1;
+                const uint32_t idesc = dn ? p.idesc_dn : p.idesc;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kAccCols;
                 uint32_t accumulate = 0;
                 for (int ph = 0; ph < p.num_phases; ++ph) {
-                    const int num_kb = (p.k[ph] + kBlockK - 1) / kBlockK;
+                    const int num_kb = ((dn ? p.k_dn : p.k[ph]) + kBlockK - 1) / kBlockK;
                     for (int kb = 0; kb < num_kb; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
@@ -334,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                             const uint64_t adesc = make_smem_desc_sw128(a_addr + k * a_kstep, a_lbo, 1024);
                             const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * b_kstep, b_lbo, 1024);
-                            umma_f16<kCtaGroup>(d_tmem, adesc, bdesc, p.idesc, accumulate);
+                            umma_f16<kCtaGroup>(d_tmem, adesc, bdesc, idesc, accumulate);
                             accumulate = 1;
                         }
                         umma_commit<kCtaGroup>(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
@@ -357,48 +433,53 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         // ------------------------------------------------------------------ epilogue
         const uint32_t q = (warp - 4) & 3u;                // TMEM lane quarter owned by this warp (warp id % 4)
         const uint32_t eg = (warp - 4) >> 2;               // epilogue group: which share of the tile's columns
-        (void)eg;
         uint32_t acc = 0, acc_phase = 0;
         const size_t esz = sizeof(T);
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-            const TileCoord tc = tile_coord(t, order);
+            const TileCoord tc = get_tile(t);
+            const bool dn = kTp && tc.prob == 1;
+            const bool store_tile = (kEpi == EPI_STORE) || dn;
+            const bool swiglu_tile = (kEpi == EPI_SWIGLU) || (kTp && !dn);
+            const int tile_n = dn ? p.n_dn : p.n;                              // valid output columns of this problem
+            const size_t tile_ldd = static_cast<size_t>(dn ? p.n_dn : p.ldd);  // and its row pitch
             const int row = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM + q * 32 + lane;
-            const int n0 = tc.n_blk * kTileNOut;
+            const int n0 = tc.n_blk * (dn ? kAccCols : kTileNOut);
             const bool row_ok = row < p.m;
-            const size_t row_off = static_cast<size_t>(row_ok ? row : 0) * static_cast<size_t>(p.ldd);
+            const size_t row_off = static_cast<size_t>(row_ok ? row : 0) * tile_ldd;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * kAccCols;
 
-            if constexpr (kEpi == EPI_STORE) {
+            if (store_tile) {
+              if (eg == 0) {   // EPI_STORE runs on one group of four epilogue warps
                 // Every lane parks 128 columns (256 B) of its own row in shared memory and ships them with ONE bulk
                 // async store (cp.async.bulk shared -> global): whole 256-byte row segments on the wire, which is what
                 // NVLink needs when the reduce-scatter is fused in (the row then goes straight to the rank that owns
                 // it -- a peer store), no second pass through the LSU, and the TMEM stage is released without waiting
                 // for the stores.  Row pitch 272 B keeps the 16-byte st.shared of the 32 lanes conflict-free.
                 uint8_t* my_row = epi_stage + q * kEpiStageBytes + lane * kEpiRowPitch;
-                const T* bias = static_cast<const T*>(p.bias[0]);
+                const T* bias = kTp ? nullptr : static_cast<const T*>(p.bias[0]);
                 uint8_t* d_row = nullptr;
                 if (row_ok) {
                     if (p.rs.world > 0) {
                         int owner = row / p.rs.rows_per_rank;
                         if (owner >= p.rs.world) owner = p.rs.world - 1;
                         d_row = static_cast<uint8_t*>(p.rs.peer_dst[owner]) +
-                                static_cast<size_t>(row - owner * p.rs.rows_per_rank) * static_cast<size_t>(p.ldd) * esz;
+                                static_cast<size_t>(row - owner * p.rs.rows_per_rank) * tile_ldd * esz;
                     } else {
                         d_row = static_cast<uint8_t*>(p.d[0]) + row_off * esz;
                     }
                 }
-                const uint8_t* add_row = (p.e[0] != nullptr) ? static_cast<const uint8_t*>(p.e[0]) + row_off * esz : nullptr;
+                const uint8_t* add_row = (!kTp && p.e[0] != nullptr) ? static_cast<const uint8_t*>(p.e[0]) + row_off * esz : nullptr;
 #pragma unroll 1
                 for (int c = 0; c < kAccCols / 128; ++c) {
                     const int col = n0 + c * 128;
-                    if (col >= p.n) break;
+                    if (col >= tile_n) break;
                     bulk_store_wait_read();   // the previous store of this lane has finished reading its row buffer
 #pragma unroll
                     for (int part = 0; part < 4; ++part) {
                         const int pcol = col + part * 32;
-                        if (pcol >= p.n) break;
+                        if (pcol >= tile_n) break;
                         uint32_t v[32];
                         tmem_ld_32x32b_x32(taddr + c * 128 + part * 32, v);
                         tmem_ld_wait();
@@ -407,14 +488,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                         for (int j = 0; j < 16; ++j) {
                             float lo = __uint_as_float(v[2 * j]), hi = __uint_as_float(v[2 * j + 1]);
                             if (bias != nullptr) {
-                                if (pcol + 2 * j < p.n) lo += static_cast<float>(bias[pcol + 2 * j]);
-                                if (pcol + 2 * j + 1 < p.n) hi += static_cast<float>(bias[pcol + 2 * j + 1]);
+                                if (pcol + 2 * j < tile_n) lo += static_cast<float>(bias[pcol + 2 * j]);
+                                if (pcol + 2 * j + 1 < tile_n) hi += static_cast<float>(bias[pcol + 2 * j + 1]);
                             }
                             o[j] = Pack2<T>::pack(lo, hi);
                         }
                         if (add_row != nullptr && row_ok) {   // fused "+ addend" (block tail: attn_out + ff_out, model.py:273)
                             uint32_t ad[16];
-                            load_row32(add_row + static_cast<size_t>(pcol) * esz, ad, p.n - pcol);
+                            load_row32(add_row + static_cast<size_t>(pcol) * esz, ad, tile_n - pcol);
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
                                 const float2 a = Pack2<T>::unpack(o[j]), b = Pack2<T>::unpack(ad[j]);
@@ -427,12 +508,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     }
                     fence_proxy_async_smem();   // generic-proxy st.shared -> async-proxy bulk store
                     if (row_ok) {
-                        const int ncols = min(p.n - col, 128);
+                        const int ncols = min(tile_n - col, 128);
                         bulk_store_row(d_row + static_cast<size_t>(col) * esz, my_row, static_cast<uint32_t>(ncols) * static_cast<uint32_t>(esz));
                     }
                     bulk_store_commit();
                 }
-            } else if constexpr (kEpi == EPI_SWIGLU) {
+              }
+            } else if (swiglu_tile) {
                 // accumulator columns [0, n_act) = gate, [n_act, 2 n_act) = up of the same act columns
                 const T* bg = static_cast<const T*>(p.bias[0]);
                 const T* bu = static_cast<const T*>(p.bias[1]);
@@ -486,7 +568,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     tmem_ld_wait();
                     finish(g, u, n0 + c0, std::integral_constant<int, 16>{});
                 }
-            } else {   // EPI_SWIGLU_BWD
+                if constexpr (kTp) {
+                    // this warp's share of the act tile is stored: publish it to the producers of the down tiles
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) red_release_gpu_add_u32(&p.act_done[tc.m_blk], 1u);
+                }
+            } else if constexpr (kEpi == EPI_SWIGLU_BWD) {
 #pragma unroll 1
                 for (int c = static_cast<int>(eg); c < kAccCols / 32; c += 2) {
                     const int col = n0 + c * 32;
@@ -530,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             acc ^= 1u;
             if (acc == 0) acc_phase ^= 1u;
         }
-        if constexpr (kEpi == EPI_STORE) bulk_store_wait_read();   // shared memory must outlive the last bulk stores
+        if (kEpi == EPI_STORE || kTp) bulk_store_wait_read();   // shared memory must outlive the last bulk stores
     }
 
     __syncwarp();
@@ -603,6 +691,9 @@ int launch_epi(const GemmKernelParams& kp, int epi, int num_tiles, int max_ctas,
         case EPI_STORE: return launch<kCtaGroup, EPI_STORE, T>(kp, num_tiles, max_ctas, s);
         case EPI_SWIGLU: return launch<kCtaGroup, EPI_SWIGLU, T>(kp, num_tiles, max_ctas, s);
         case EPI_SWIGLU_BWD: return launch<kCtaGroup, EPI_SWIGLU_BWD, T>(kp, num_tiles, max_ctas, s);
+        case EPI_FFN_TP:
+            if constexpr (kCtaGroup == 2) return launch<2, EPI_FFN_TP, T>(kp, num_tiles, max_ctas, s);
+            else return L32_ERR_BAD_SHAPE;
         default: return L32_ERR_BAD_SHAPE;
     }
 }
@@ -638,11 +729,13 @@ int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
 }
 
 int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
+    const bool ffn_tp = g.epilogue == EPI_FFN_TP;
+    const bool swiglu_like = g.epilogue == EPI_SWIGLU || ffn_tp;
     if (g.dtype != L32_BF16 && g.dtype != L32_FP16) return L32_ERR_BAD_DTYPE;
     if (g.m < 0 || g.n <= 0 || g.num_phases < 1 || g.num_phases > 2) return L32_ERR_BAD_SHAPE;
     if (g.m == 0) return L32_OK;
     if ((g.n % 8) != 0 || (g.ldd % 8) != 0) return L32_ERR_BAD_ALIGN;
-    if (g.epilogue == EPI_SWIGLU && (g.num_phases != 1 || g.b[0].mn_major || g.b[1].mn_major)) return L32_ERR_BAD_SHAPE;
+    if (swiglu_like && (g.num_phases != 1 || g.b[0].mn_major || g.b[1].mn_major)) return L32_ERR_BAD_SHAPE;
     for (int i = 0; i < 3; ++i)
         if (g.d[i] != nullptr && !is_aligned16(g.d[i])) return L32_ERR_BAD_ALIGN;
     if (g.d[0] == nullptr && g.rs.world == 0) return L32_ERR_NULL;
@@ -655,6 +748,12 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
     int cta_group = g.cta_group;
     if (cta_group == 0) cta_group = (g.m > kBlockM) ? 2 : 1;
     if (cta_group != 1 && cta_group != 2) return L32_ERR_BAD_SHAPE;
+    if (ffn_tp) {
+        if (cta_group != 2 || g.dn.w == nullptr || g.dn.n <= 0 || (g.dn.n % 8) != 0 || g.dn.act_done == nullptr ||
+            g.rs.world < 1 || g.d[0] == nullptr || g.d[1] != nullptr || g.a[0].mn_major || g.bias[0] != nullptr ||
+            g.bias[1] != nullptr)
+            return L32_ERR_BAD_SHAPE;
+    }
 
     GemmKernelParams kp;
     memset(&kp, 0, sizeof(kp));
@@ -669,7 +768,7 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
     // tensor-parallel shard of 1792 act columns is 7 waves of 112 columns instead of 7 waves of 128 (the last one
     // nearly empty).  Ties go to the wider tile.
     int n_act = 128;
-    if (g.epilogue == EPI_SWIGLU) {
+    if (swiglu_like) {
         int ctas = num_sms();
         if (g.max_ctas > 0 && g.max_ctas < ctas) ctas = g.max_ctas;
         const long long clusters = ctas / cta_group > 0 ? ctas / cta_group : 1;
@@ -685,7 +784,7 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
         }
     }
     kp.n_act = n_act;
-    const int tile_n_out = (g.epilogue == EPI_SWIGLU) ? n_act : 256;
+    const int tile_n_out = swiglu_like ? n_act : 256;
     kp.tiles_n = (g.n + tile_n_out - 1) / tile_n_out;
     kp.raster_group = g.raster_group > 0 ? g.raster_group : 16 / cta_group;
     if (const char* env = getenv("L32_RASTER_GROUP")) {   // tuning knob for experiments only
@@ -693,7 +792,7 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
         if (v > 0) kp.raster_group = v;
     }
     kp.idesc = make_idesc_f16(g.dtype == L32_BF16, static_cast<uint32_t>(tile_m),
-                              g.epilogue == EPI_SWIGLU ? static_cast<uint32_t>(2 * n_act) : static_cast<uint32_t>(kAccCols),
+                              swiglu_like ? static_cast<uint32_t>(2 * n_act) : static_cast<uint32_t>(kAccCols),
                               g.a[0].mn_major != 0, g.b[0].mn_major != 0);
     for (int i = 0; i < 3; ++i) kp.d[i] = g.d[i];
     kp.e[0] = g.e[0]; kp.e[1] = g.e[1];
@@ -717,10 +816,10 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
             g.ag.local_dst != g.a[0].ptr || g.ag.ready == nullptr || g.ag.done == nullptr)
             return L32_ERR_BAD_SHAPE;
     }
-    if (g.rs.world > 0 && (g.epilogue != EPI_STORE || g.rs.rows_per_rank <= 0 || g.e[0] != nullptr)) return L32_ERR_BAD_SHAPE;
+    if (g.rs.world > 0 && ((g.epilogue != EPI_STORE && !ffn_tp) || g.rs.rows_per_rank <= 0 || g.e[0] != nullptr)) return L32_ERR_BAD_SHAPE;
     if (g.epilogue == EPI_STORE && g.e[0] != nullptr && !is_aligned16(g.e[0])) return L32_ERR_BAD_ALIGN;
 
-    const int b_box_rows = (g.epilogue == EPI_SWIGLU) ? 128 : kAccCols / cta_group;
+    const int b_box_rows = swiglu_like ? 128 : kAccCols / cta_group;
     for (int ph = 0; ph < g.num_phases; ++ph) {
         if (g.k[ph] <= 0) return L32_ERR_BAD_SHAPE;   // any K: TMA zero-fills the ragged last k-block
         if (g.a[ph].mn_major != g.a[0].mn_major || g.b[ph].mn_major != g.b[0].mn_major) return L32_ERR_BAD_SHAPE;
@@ -729,20 +828,47 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
         if (!g.a[ph].mn_major) rc = make_tensor_map_2d(&kp.map_a[ph], g.a[ph].ptr, g.m, g.k[ph], g.a[ph].ld, kBlockM, kBlockK, g.dtype);
         else rc = make_tensor_map_2d(&kp.map_a[ph], g.a[ph].ptr, g.k[ph], g.m, g.a[ph].ld, kBlockK, 64, g.dtype);
         if (rc != L32_OK) return rc;
-        if (g.epilogue != EPI_SWIGLU) {
+        if (!swiglu_like) {
             if (!g.b[ph].mn_major) rc = make_tensor_map_2d(&kp.map_b[ph], g.b[ph].ptr, g.n, g.k[ph], g.b[ph].ld, b_box_rows, kBlockK, g.dtype);
             else rc = make_tensor_map_2d(&kp.map_b[ph], g.b[ph].ptr, g.k[ph], g.n, g.b[ph].ld, kBlockK, 64, g.dtype);
             if (rc != L32_OK) return rc;
         }
     }
-    if (g.epilogue == EPI_SWIGLU) {
+    if (swiglu_like) {
         for (int i = 0; i < 2; ++i) {
             int rc = make_tensor_map_2d(&kp.map_b[i], g.b[i].ptr, g.n, g.k[0], g.b[i].ld, n_act, kBlockK, g.dtype);
             if (rc != L32_OK) return rc;
         }
     }
+    if (ffn_tp) {
+        // second problem: y_partial = act (= d[0], [m, n] with pitch ldd) * w_down_shard^T, 256-column tiles, RS epilogue
+        kp.k_dn = g.n;
+        kp.n_dn = g.dn.n;
+        kp.tiles_n_dn = (g.dn.n + kAccCols - 1) / kAccCols;
+        kp.idesc_dn = make_idesc_f16(g.dtype == L32_BF16, static_cast<uint32_t>(tile_m), kAccCols, false, false);
+        kp.act_done = g.dn.act_done;
+        int rc = make_tensor_map_2d(&kp.map_a_dn, g.d[0], g.m, g.n, g.ldd, kBlockM, kBlockK, g.dtype);
+        if (rc != L32_OK) return rc;
+        rc = make_tensor_map_2d(&kp.map_b_dn, g.dn.w, g.dn.n, g.n, g.dn.ld, kAccCols / cta_group, kBlockK, g.dtype);
+        if (rc != L32_OK) return rc;
+        // the tile sequence works on whole groups of m-tiles: largest group size <= the requested one that divides tiles_m
+        int grp = kp.raster_group < 1 ? 1 : kp.raster_group;
+        if (grp > kp.tiles_m) grp = kp.tiles_m;
+        while (kp.tiles_m % grp != 0) --grp;
+        kp.raster_group = grp;
+        int ctas = num_sms();
+        if (g.max_ctas > 0 && g.max_ctas < ctas) ctas = g.max_ctas;
+        const int a_tiles = grp * kp.tiles_n;
+        kp.ffn_prefix = a_tiles < ctas / 2 ? a_tiles : ctas / 2;   // one wave of gate/up-only tiles at the head of a round
+        if (const char* env = getenv("L32_FFN_PREFIX")) {   // tuning knob for experiments only
+            const int v = atoi(env);
+            if (v >= 0 && v <= a_tiles) kp.ffn_prefix = v;
+        }
+        if (const char* env = getenv("L32_FFN_NOWAIT")) kp.ffn_nowait = atoi(env);
+        kp.m_il_world = 0;
+    }
 
-    const int num_tiles = kp.tiles_m * kp.tiles_n;
+    const int num_tiles = kp.tiles_m * (kp.tiles_n + kp.tiles_n_dn);
     if (g.dtype == L32_BF16) {
         if (cta_group == 2) return launch_epi<2, __nv_bfloat16>(kp, g.epilogue, num_tiles, g.max_ctas, s);
         return launch_epi<1, __nv_bfloat16>(kp, g.epilogue, num_tiles, g.max_ctas, s);

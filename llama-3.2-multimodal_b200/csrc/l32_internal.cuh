@@ -27,6 +27,9 @@ enum : int {
     EPI_STORE = 0,       // D -> d[0]                                     (tile 128*cta_group x 256)
     EPI_SWIGLU = 1,      // b[0]=gate weights, b[1]=up weights; act = silu(g)*u -> d[0]; optional g -> d[1], u -> d[2]
     EPI_SWIGLU_BWD = 2,  // D = d_act; e[0]=gate cache, e[1]=up cache; d_gate -> d[0], d_up -> d[1], optional act -> d[2]
+    EPI_FFN_TP = 3,      // tensor-parallel feed-forward in ONE kernel: the EPI_SWIGLU problem (act -> d[0]) and the down
+                         // projection of that act (GemmProblem::dn, reduce-scatter epilogue) share the persistent tile loop,
+                         // the down tiles of one group of rows interleaved with the gate/up tiles of the next group
 };
 
 struct GemmOperand {
@@ -60,6 +63,14 @@ struct TpReduceScatter {
     void* peer_dst[kMaxTpWorld];    // peer_dst[o]: rank o's slot for THIS rank's partial, [rows_per_rank, ldd]
 };
 
+// Second problem of EPI_FFN_TP: y_partial[m, n] = act[m, k = GemmProblem::n] * w[n, k]^T, rows scattered by GemmProblem::rs.
+struct TpFfnDown {
+    const void* w;          // this rank's w_down shard [n, k], K-major (null: not an EPI_FFN_TP problem)
+    int64_t ld;             // its row pitch, elements
+    int n;                  // output columns (hidden size)
+    uint32_t* act_done;     // [ceil(m / 256)] arrival counters, ZERO on entry: epilogue warps that finished act tiles
+};
+
 struct GemmProblem {
     int m, n;               // D is [m, n]; for EPI_SWIGLU n = intermediate size (act columns)
     int num_phases;         // 1, or 2 for D = A0*B0^T + A1*B1^T (EPI_SWIGLU: must be 1)
@@ -77,7 +88,8 @@ struct GemmProblem {
     int max_ctas;           // 0 = all SMs (testing / tuning knob)
     int m_rotate_rows;      // visit the m-tiles starting at this row (rounded down to a tile), wrapping around
     TpAllGather ag;         // ag.world == 0: off
-    TpReduceScatter rs;     // rs.world == 0: off (EPI_STORE only)
+    TpReduceScatter rs;     // rs.world == 0: off (EPI_STORE and the down half of EPI_FFN_TP)
+    TpFfnDown dn;           // EPI_FFN_TP only
 };
 int gemm_sm100(const GemmProblem& p, cudaStream_t s);   // returns L32_* / cudaError_t
 

@@ -381,6 +381,26 @@ def tp_linear_forward_reduce_scatter(a, weight, peer_slot_ptrs, rank, rows_per_r
               "l32_tp_linear_forward_reduce_scatter")
 
 
+def tp_ffn_forward_fused(x_full, peer_x_ptrs, ready, done, epoch, rank, rows_per_rank, w_gate, w_up, w_down, peer_slot_ptrs,
+                         act=None, act_done=None):
+    """Gate/up (+ pulled all-gather) and down (+ pushed reduce-scatter) of this rank's shard in ONE persistent kernel."""
+    _check_cuda(x_full, ready, done, w_gate, w_up, w_down)
+    tokens, hidden = x_full.shape
+    inter = w_gate.shape[0]
+    if act is None:
+        act = torch.empty(tokens, inter, dtype=x_full.dtype, device=x_full.device)
+    if act_done is None:
+        act_done = torch.empty((tokens + 255) // 256, dtype=torch.int32, device=x_full.device)
+    world = len(peer_x_ptrs)
+    px, ps = _ptr_array(peer_x_ptrs), _ptr_array(peer_slot_ptrs)
+    with torch.cuda.device(x_full.device):
+        check(lib().l32_tp_ffn_forward_fused(_ptr(x_full), px, _ptr(ready), _ptr(done), int(epoch), int(rank), world,
+                                             int(rows_per_rank), _ptr(w_gate), _ptr(w_up), _ptr(w_down), _ptr(act),
+                                             _ptr(act_done), ps, tokens, hidden, inter, _dtype_code(x_full), _stream(x_full)),
+              "l32_tp_ffn_forward_fused")
+    return act
+
+
 def tp_reduce_partials(slots, flags, epoch, rank, rows, addend=None, out=None):
     """y = sum over ranks of the partial slots [world, slot_rows, hidden] (+ addend), after every peer signalled."""
     _check_cuda(slots, flags, addend)

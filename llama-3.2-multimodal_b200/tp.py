@@ -193,9 +193,11 @@ class TpRankBuffers:
 class FusedTensorParallelBlock:
     """norm2(x, residual) -> feed-forward of one rank, collectives fused into the GEMM kernels (see above)."""
 
-    def __init__(self, gamma, eps, w_gate, w_up, w_down, bufs: TpRankBuffers):
-        """gamma [H]; w_gate / w_up / w_down are the FULL matrices ([I,H], [I,H], [H,I]); the shard is taken here."""
+    def __init__(self, gamma, eps, w_gate, w_up, w_down, bufs: TpRankBuffers, one_kernel: bool = True):
+        """gamma [H]; w_gate / w_up / w_down are the FULL matrices ([I,H], [I,H], [H,I]); the shard is taken here.
+        one_kernel: run gate/up and down as ONE persistent kernel (l32_tp_ffn_forward_fused) instead of two."""
         self.bufs = bufs
+        self.one_kernel = one_kernel
         self.eps = eps
         self.gamma = gamma
         wg, wu, wd = shard_ffn_weights(w_gate, w_up, w_down, bufs.world, bufs.rank)
@@ -230,6 +232,14 @@ class FusedTensorParallelBlock:
         ops.tp_linear_forward_reduce_scatter(self._act, self.w_down, b.peer_slots, b.rank, per)
         ops.tp_signal(b.peer_flags, FLAG_RS_DONE + b.rank, self.epoch, b.normed.device)
 
+    def phase_ffn(self, tokens):
+        """phase_gate_up + phase_down as one persistent kernel, then the rs_done signal."""
+        b = self.bufs
+        _, _, per = self.rows_of(tokens)
+        ops.tp_ffn_forward_fused(b.normed[:tokens], b.peer_normed, b.flags[FLAG_READY:FLAG_READY + 8], b.done, self.epoch,
+                                 b.rank, per, self.w_gate, self.w_up, self.w_down, b.peer_slots)
+        ops.tp_signal(b.peer_flags, FLAG_RS_DONE + b.rank, self.epoch, b.normed.device)
+
     def phase_reduce(self, tokens, addend=None):
         b = self.bufs
         lo, hi, _ = self.rows_of(tokens)
@@ -240,6 +250,9 @@ class FusedTensorParallelBlock:
         if tokens > self.bufs.max_tokens:
             raise ValueError(f"tokens {tokens} exceeds the buffers' capacity {self.bufs.max_tokens}")
         self.phase_norm(x_local, residual_local, tokens)
-        self.phase_gate_up(tokens)
-        self.phase_down(tokens)
+        if self.one_kernel:
+            self.phase_ffn(tokens)
+        else:
+            self.phase_gate_up(tokens)
+            self.phase_down(tokens)
         return self.phase_reduce(tokens, addend)

@@ -160,7 +160,7 @@ def tp_shapes():
                   f"down {t2 * 1e3:.0f} us ({2.0 * T * H * Il / t2 / 1e9:.0f} TF/s)", flush=True)
 
 
-def tp_emul(world=8, H=4096, I=14336, T=8192):
+def tp_emul(world=8, H=4096, I=14336, T=8192, one_kernel=False):
     """Fused TP phases with all ranks emulated on one GPU (peer pointers = local buffers): cost of the mechanism itself
     (rotation, raster, flag waits, pulls / pushes through local memory) without NVLink."""
     from llama32_b200.tp import FusedTensorParallelBlock, TpRankBuffers
@@ -168,7 +168,7 @@ def tp_emul(world=8, H=4096, I=14336, T=8192):
     wg, wu, wd = weights(H, I)
     gamma = torch.ones(H, device="cuda", dtype=dt)
     bufs = TpRankBuffers.local_world(world, T, H, dt, "cuda")
-    blocks = [FusedTensorParallelBlock(gamma, 1e-5, wg, wu, wd, b) for b in bufs]
+    blocks = [FusedTensorParallelBlock(gamma, 1e-5, wg, wu, wd, b, one_kernel=one_kernel) for b in bufs]
     x = torch.randn(T, H, device="cuda").to(dt)
     r = torch.randn(T, H, device="cuda").to(dt)
     acc = [0.0, 0.0, 0.0, 0.0]
@@ -180,11 +180,16 @@ def tp_emul(world=8, H=4096, I=14336, T=8192):
             lo, hi, _ = blk.rows_of(T)
             blk.phase_norm(x[lo:hi], r[lo:hi], T)
         ev[1].record()
-        for blk in blocks:
-            blk.phase_gate_up(T)
-        ev[2].record()
-        for blk in blocks:
-            blk.phase_down(T)
+        if one_kernel:
+            for blk in blocks:
+                blk.phase_ffn(T)
+            ev[2].record()
+        else:
+            for blk in blocks:
+                blk.phase_gate_up(T)
+            ev[2].record()
+            for blk in blocks:
+                blk.phase_down(T)
         ev[3].record()
         for blk in blocks:
             blk.phase_reduce(T)
@@ -194,7 +199,7 @@ def tp_emul(world=8, H=4096, I=14336, T=8192):
             for k in range(4):
                 acc[k] += ev[k].elapsed_time(ev[k + 1])
     per = [a / iters / world * 1e3 for a in acc]
-    print(f"tp-emul world={world} H={H} I={I}: per rank norm+signal {per[0]:.0f} us  gate/up+pull {per[1]:.0f} us  "
+    print(f"tp-emul world={world} H={H} I={I} T={T} one_kernel={one_kernel}: per rank norm+signal {per[0]:.0f} us  gate/up+pull {per[1]:.0f} us  "
           f"down+push+signal {per[2]:.0f} us  reduce {per[3]:.0f} us", flush=True)
 
 
@@ -211,9 +216,15 @@ if __name__ == "__main__":
     elif what == "tp_shapes":
         tp_shapes()
     elif what == "tp_emul":
-        tp_emul(8)
-        tp_emul(4)
-        tp_emul(8, 8192, 28672)
+        tp_emul(8, one_kernel=False)
+        tp_emul(8, T=32768, one_kernel=False)
+        for env in ({}, {"L32_RASTER_GROUP": "32"}, {"L32_RASTER_GROUP": "16"}, {}, {"L32_RASTER_GROUP": "32"}, {"L32_RASTER_GROUP": "16"}):
+            for k in ("L32_FFN_NOWAIT", "L32_FFN_PREFIX", "L32_SWIGLU_TILE_N", "L32_RASTER_GROUP"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            print(env)
+            tp_emul(8, one_kernel=True)
+            tp_emul(8, T=32768, one_kernel=True)
     elif what == "norm":
         norm(4096, 8192)
         norm(8192, 8192)

@@ -27,7 +27,8 @@ def main():
     wu = ((torch.rand(inter, hidden, device=dev, generator=gen) * 2 - 1) / hidden ** 0.5).to(dt)
     wd = ((torch.rand(hidden, inter, device=dev, generator=gen) * 2 - 1) / inter ** 0.5).to(dt)
     bufs = TpRankBuffers.symmetric(tokens, hidden, dt, dev)
-    blk = FusedTensorParallelBlock(gamma, 1e-5, wg, wu, wd, bufs)
+    one = os.environ.get("TP_ONE_KERNEL", "1") != "0"
+    blk = FusedTensorParallelBlock(gamma, 1e-5, wg, wu, wd, bufs, one_kernel=one)
     del wg, wu, wd
     lo, hi, _ = blk.rows_of(tokens)
     xs = [torch.randn(hi - lo, hidden, device=dev, generator=gen).to(dt) for _ in range(2)]
@@ -49,9 +50,13 @@ def main():
         ev[0].record()
         blk.phase_norm(xs[i % 2], rs[i % 2], tokens)
         ev[1].record()
-        blk.phase_gate_up(tokens)
-        ev[2].record()
-        blk.phase_down(tokens)
+        if one:
+            blk.phase_ffn(tokens)
+            ev[2].record()
+        else:
+            blk.phase_gate_up(tokens)
+            ev[2].record()
+            blk.phase_down(tokens)
         ev[3].record()
         blk.phase_reduce(tokens)
         ev[4].record()
@@ -71,7 +76,7 @@ def main():
         for r, g in enumerate(gathered):
             g = g.tolist()
             ph = [v / iters for v in g[:4]]
-            print(f"{wl} p={world} tokens={tokens} rank {r}: " + "  ".join(f"{n} {v * 1e3:.0f} us" for n, v in zip(names, ph)) +
+            print(f"{wl} p={world} tokens={tokens} {'ONE-KERNEL ffn (phase 2 = gate/up+down+signal, phase 3 = 0)' if one else 'two kernels'} rank {r}: " + "  ".join(f"{n} {v * 1e3:.0f} us" for n, v in zip(names, ph)) +
                   f" | gate/up {fl_gu / ph[1] / 1e9:.0f} TF/s down {fl_dn / ph[2] / 1e9:.0f} TF/s | sum {sum(ph):.3f} ms | back-to-back {g[4]:.3f} ms "
                   f"= {tokens / g[4] / 1e3:.2f} M tok/s", flush=True)
     dist.destroy_process_group()

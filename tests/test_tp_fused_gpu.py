@@ -28,9 +28,11 @@ def _close(got, ref, what):
     assert r <= 1e-2 and m <= 2.0 ** -6, f"{what}: rel-L2 {r:.3e}, max-abs/max|ref| {m:.3e}"
 
 
+@pytest.mark.parametrize("one_kernel", [False, True])
 @pytest.mark.parametrize("world,tokens,hidden,inter", [
-    (1, 300, 256, 512), (2, 512, 512, 1024), (4, 1000, 256, 1536), (8, 2048, 1024, 2048), (3, 777, 384, 1152)])
-def test_fused_tp_single_gpu_emulation(world, tokens, hidden, inter):
+    (1, 300, 256, 512), (2, 512, 512, 1024), (4, 1000, 256, 1536), (8, 2048, 1024, 2048), (3, 777, 384, 1152),
+    (2, 4096, 512, 1792), (8, 8192, 256, 1024)])
+def test_fused_tp_single_gpu_emulation(world, tokens, hidden, inter, one_kernel):
     s = O.synthetic_ffn(tokens, hidden, inter, seed=world * 100 + 7)
     bf = lambda t: t.to(DEV, torch.bfloat16)
     x, res, gamma, wg, wu, wd = (bf(s[k]) for k in ("x", "residual", "gamma", "w_gate", "w_up", "w_down"))
@@ -41,10 +43,14 @@ def test_fused_tp_single_gpu_emulation(world, tokens, hidden, inter):
         for blk in blocks:
             lo, hi, _ = blk.rows_of(tokens)
             blk.phase_norm(x[lo:hi], res[lo:hi], tokens)
-        for blk in blocks:
-            blk.phase_gate_up(tokens)
-        for blk in blocks:
-            blk.phase_down(tokens)
+        if one_kernel:   # gate/up + down as ONE persistent kernel per rank
+            for blk in blocks:
+                blk.phase_ffn(tokens)
+        else:
+            for blk in blocks:
+                blk.phase_gate_up(tokens)
+            for blk in blocks:
+                blk.phase_down(tokens)
         ys = [blk.phase_reduce(tokens) for blk in blocks]
         torch.cuda.synchronize()
         y = torch.cat(ys)
