@@ -315,7 +315,7 @@ def run_ours(args):
     if world > 1 and args.tp_impl == "fused":
         bufs = TpRankBuffers.symmetric(tokens, hidden, dt, dev)
         fused = FusedTensorParallelBlock(norm.weight.detach(), EPS, ffn.swiglu.w_gate.detach(), ffn.swiglu.w_up.detach(),
-                                         ffn.w_down.weight.detach(), bufs)
+                                         ffn.w_down.weight.detach(), bufs, one_kernel=args.tp_one_kernel)
         lo, hi, _ = fused.rows_of(tokens)
         gen = torch.Generator(device=dev).manual_seed(1 + rank)
         # sequence-parallel: every rank holds (and generates) only its own rows
@@ -351,6 +351,10 @@ def run_ours(args):
                     fused.phase_norm(xs_loc[i % nbuf], rs_loc[i % nbuf], tokens)
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
+                    if fused.one_kernel:
+                        fused.phase_ffn(tokens)
+                        fused.phase_reduce(tokens)
+                        return None
                     fused.phase_gate_up(tokens)
                     e1.record()
                     k_ev.append((e0, e1))
@@ -543,6 +547,8 @@ def main():
     ap.add_argument("--mode", choices=["prefill", "train"], default="prefill")
     ap.add_argument("--tp-chunks", type=int, default=4)
     ap.add_argument("--tp-impl", choices=["fused", "nccl"], default="fused")
+    ap.add_argument("--tp-one-kernel", action="store_true",
+                    help="N > 1, fused: gate/up and down as ONE persistent kernel (l32_tp_ffn_forward_fused)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="N > 1: weak = 4x2048 tokens per GPU (global batch grows with N), strong = 4x2048 tokens in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")

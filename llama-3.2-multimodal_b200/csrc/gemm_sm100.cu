@@ -568,12 +568,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     tmem_ld_wait();
                     finish(g, u, n0 + c0, std::integral_constant<int, 16>{});
                 }
-                if constexpr (kTp) {
-                    // this warp's share of the act tile is stored: publish it to the producers of the down tiles
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) red_release_gpu_add_u32(&p.act_done[tc.m_blk], 1u);
-                }
             } else if constexpr (kEpi == EPI_SWIGLU_BWD) {
 #pragma unroll 1
                 for (int c = static_cast<int>(eg); c < kAccCols / 32; c += 2) {
@@ -614,6 +608,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             if (lane == 0) {
                 if (rank == 0) mbar_arrive(&tempty_bar[acc]);
                 else mbar_arrive_remote(&tempty_bar[acc], 0);
+            }
+            if constexpr (kTp) {
+                // This warp's share of the act tile is stored: publish it to the producers of the down tiles.  Done AFTER
+                // the TMEM stage went back to the MMA issuer -- the fence waits for the stores to be acknowledged, which
+                // takes microseconds under load and must not sit between a short down tile and the next main loop.
+                if (swiglu_tile) {
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) red_release_gpu_add_u32(&p.act_done[tc.m_blk], 1u);
+                }
             }
             acc ^= 1u;
             if (acc == 0) acc_phase ^= 1u;

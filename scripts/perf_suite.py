@@ -203,6 +203,37 @@ def tp_emul(world=8, H=4096, I=14336, T=8192, one_kernel=False):
           f"down+push+signal {per[2]:.0f} us  reduce {per[3]:.0f} us", flush=True)
 
 
+def ffn1k():
+    """One-kernel feed-forward (EPI_FFN_TP, world = 1: no NVLink) against the two separate GEMM kernels."""
+    dt = torch.bfloat16
+    for T, H, I in ((8192, 4096, 1792), (32768, 4096, 1792)):
+        wg, wu, wd = weights(H, I)
+        x = torch.randn(T, H, device="cuda").to(dt)
+        slot = torch.empty(T, H, device="cuda", dtype=dt)
+        ready = torch.zeros(8, dtype=torch.int32, device="cuda")
+        done = torch.zeros(8, dtype=torch.int32, device="cuda")
+        act = torch.empty(T, I, device="cuda", dtype=dt)
+        act_done = torch.empty((T + 255) // 256, dtype=torch.int32, device="cuda")
+
+        def two():
+            a, _, _ = ops.swiglu_forward(x, wg, wu)
+            ops.linear_forward(a, wd)
+
+        def one():
+            ops.tp_ffn_forward_fused(x, [x.data_ptr()], ready, done, 1, 0, T, wg, wu, wd, [slot.data_ptr()], act=act, act_done=act_done)
+        fl = 6.0 * T * H * I
+        for env in ({}, {"L32_RASTER_GROUP": "4"}, {"L32_RASTER_GROUP": "32"}):
+            for k in ("L32_FFN_NOWAIT", "L32_FFN_PREFIX", "L32_RASTER_GROUP"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            t1 = timeit(one, iters=20)
+            print(f"ffn1k T={T} H={H} I={I} {env}: one kernel {t1 * 1e3:.0f} us ({fl / t1 / 1e9:.0f} TF/s)", flush=True)
+        for k in ("L32_FFN_NOWAIT", "L32_FFN_PREFIX", "L32_RASTER_GROUP"):
+            os.environ.pop(k, None)
+        t2 = timeit(two, iters=20)
+        print(f"ffn1k T={T} H={H} I={I}: two kernels {t2 * 1e3:.0f} us ({fl / t2 / 1e9:.0f} TF/s)", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     if what == "decode":
@@ -215,6 +246,8 @@ if __name__ == "__main__":
         train(4096, 14336, 8192)
     elif what == "tp_shapes":
         tp_shapes()
+    elif what == "ffn1k":
+        ffn1k()
     elif what == "tp_emul":
         tp_emul(8, one_kernel=False)
         tp_emul(8, T=32768, one_kernel=False)

@@ -27,7 +27,7 @@ def main():
     wu = ((torch.rand(inter, hidden, device=dev, generator=gen) * 2 - 1) / hidden ** 0.5).to(dt)
     wd = ((torch.rand(hidden, inter, device=dev, generator=gen) * 2 - 1) / inter ** 0.5).to(dt)
     bufs = TpRankBuffers.symmetric(tokens, hidden, dt, dev)
-    one = os.environ.get("TP_ONE_KERNEL", "1") != "0"
+    one = os.environ.get("TP_ONE_KERNEL", "0") != "0"
     blk = FusedTensorParallelBlock(gamma, 1e-5, wg, wu, wd, bufs, one_kernel=one)
     del wg, wu, wd
     lo, hi, _ = blk.rows_of(tokens)
