@@ -790,7 +790,10 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
     kp.n_act = n_act;
     const int tile_n_out = swiglu_like ? n_act : 256;
     kp.tiles_n = (g.n + tile_n_out - 1) / tile_n_out;
-    kp.raster_group = g.raster_group > 0 ? g.raster_group : 16 / cta_group;
+    // m-tiles per raster group: 2048 rows for the plain / backward epilogues, 4096 rows for the fused gate/up GEMM (its B
+    // operand -- two weight matrices -- is the big one: larger groups re-read it from HBM half as often; measured
+    // +1.8 % at the 11B shape, scripts/raster_ab.py)
+    kp.raster_group = g.raster_group > 0 ? g.raster_group : (swiglu_like ? 32 : 16) / cta_group;
     if (const char* env = getenv("L32_RASTER_GROUP")) {   // tuning knob for experiments only
         const int v = atoi(env);
         if (v > 0) kp.raster_group = v;
