@@ -352,7 +352,8 @@ int env_int(const char* name, int dflt) {
 template <int kEpi, typename T>
 int launch_decode(const DecodeParams& p, int grid, size_t smem_bytes, cudaStream_t s) {
     auto* kernel = ffn_decode_kernel<kEpi, T>;
-    static size_t configured = 0;   // per instantiation: largest dynamic smem opted into so far
+    static size_t configured_dev[kMaxDevices] = {};   // per instantiation and device: dynamic smem opted into so far
+    size_t& configured = configured_dev[current_device_slot()];
     if (smem_bytes > configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return static_cast<int>(e);

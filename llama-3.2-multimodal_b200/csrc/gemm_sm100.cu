@@ -658,7 +658,8 @@ template <int kCtaGroup, int kEpi, typename T>
 int launch(const GemmKernelParams& kp, int num_tiles, int max_ctas, cudaStream_t s) {
     using Cfg = TileCfg<kCtaGroup>;
     auto* kernel = gemm_kernel<kCtaGroup, kEpi, T>;
-    static bool configured = false;   // per instantiation
+    static bool configured_dev[kMaxDevices] = {};   // per instantiation and device
+    bool& configured = configured_dev[current_device_slot()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return static_cast<int>(e);
@@ -705,10 +706,11 @@ int launch_epi(const GemmKernelParams& kp, int epi, int num_tiles, int max_ctas,
 }  // namespace
 
 int num_sms() {
-    static int n = 0;
+    static int cached[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int& n = cached[(dev >= 0 && dev < kMaxDevices) ? dev : 0];
     if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
         int v = 0;
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
         n = v;

@@ -13,7 +13,14 @@ void count_launch(int n = 1);
 unsigned long long launch_count();
 
 inline bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-int num_sms();
+int num_sms();   // of the current device
+// Kernel attributes (opt-in shared memory size) are per device: one "already configured" flag per device ordinal.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    return dev;
+}
 
 // ---- rmsnorm.cu
 cudaError_t add_rmsnorm_fwd(const void* x, const void* residual, const void* weight, void* y, void* h_out, float* rms,

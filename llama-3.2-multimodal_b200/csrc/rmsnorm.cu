@@ -487,7 +487,8 @@ static cudaError_t launch_bwd_fast(const T* dy, const T* h, const T* weight, con
     if (stages < 2 || stages < G - 1) return cudaErrorInvalidConfiguration;   // the d_weight fold reuses the ring
     const size_t smem = stages * stage_bytes + kBwdBarrierBytes + kBwdRedBytes;
     auto* k = rmsnorm_bwd_kernel<T, RT, VPT>;
-    static bool configured = false;
+    static bool configured_dev[kMaxDevices] = {};   // per instantiation and device
+    bool& configured = configured_dev[current_device_slot()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
