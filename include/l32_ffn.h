@@ -210,8 +210,7 @@ L32_API int l32_tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas,
  *              warps of the tcgen05 GEMM CTAs) while the tensor cores already work on the rows that have arrived;
  *              tiles are visited starting at the own rows, then rank+1, rank+2, ... (the pull order).
  *   ready    : own flags, ready[s] >= epoch once rank s has written its rows (see l32_tp_signal).
- *   done     : own scratch counters, 8 uint32, which must be ZERO on entry (pass them as `zero8` to the l32_tp_signal
- *              that announces this rank's rows, or clear them with a memset).
+ *   done     : own scratch counters, 8 uint32, cleared by this call (cudaMemsetAsync on `stream`).
  *   w_gate, w_up : this rank's shard [inter_local, hidden]; act : [tokens, inter_local].
  */
 L32_API int l32_tp_swiglu_forward_allgather(void* x_full, const void* const* peer_x, const uint32_t* ready, uint32_t* done,

@@ -520,6 +520,9 @@ int l32_tp_swiglu_forward_allgather(void* x_full, const void* const* peer_x, con
     g.cta_group = 2;
     if (world > 1) {
         if (peer_x == nullptr || ready == nullptr || done == nullptr) return L32_ERR_NULL;
+        // arrival counters of the pull: cleared here so that a call never sees the counts of an earlier one
+        cudaError_t e = cudaMemsetAsync(done, 0, sizeof(uint32_t) * kMaxTpWorld, as_stream(stream));
+        if (e != cudaSuccess) return static_cast<int>(e);
         g.ag.world = world;
         g.ag.rank = rank;
         g.ag.rows_per_rank = static_cast<int>(rows_per_rank);
@@ -618,6 +621,8 @@ int l32_tp_ffn_forward_fused(void* x_full, const void* const* peer_x, const uint
     g.m_rotate_rows = static_cast<int>(rank * rows_per_rank);
     if (world > 1) {
         if (peer_x == nullptr || ready == nullptr || done == nullptr) return L32_ERR_NULL;
+        e = cudaMemsetAsync(done, 0, sizeof(uint32_t) * kMaxTpWorld, s);
+        if (e != cudaSuccess) return static_cast<int>(e);
         g.ag.world = world;
         g.ag.rank = rank;
         g.ag.rows_per_rank = static_cast<int>(rows_per_rank);

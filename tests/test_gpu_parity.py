@@ -513,6 +513,26 @@ def test_decode_is_deterministic_and_graph_capturable():
     assert torch.equal(y0, yg)
 
 
+def test_second_device_in_the_same_process():
+    """Kernel attributes and SM counts are tracked per device: the hot path must work on cuda:1 after cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    for d in ("cuda:0", "cuda:1", "cuda:0"):
+        gen = torch.Generator(device=d).manual_seed(3)
+        x = torch.randn(300, 512, device=d, generator=gen).bfloat16()
+        wg = ((torch.rand(1024, 512, device=d, generator=gen) * 2 - 1) / 22).bfloat16()
+        wu = ((torch.rand(1024, 512, device=d, generator=gen) * 2 - 1) / 22).bfloat16()
+        wd = ((torch.rand(512, 1024, device=d, generator=gen) * 2 - 1) / 32).bfloat16()
+        gamma = torch.ones(512, device=d).bfloat16()
+        for rows in (300, 7):   # tiled kernels and small-M kernels
+            xx = x[:rows]
+            y = ops.ffn_forward(ops.add_rmsnorm_forward(xx, gamma, None, 1e-5)[0], wg, wu, wd)[0]
+            n = O.add_rmsnorm(xx.float().cpu(), gamma.float().cpu(), 1e-5)
+            close(y, O.feedforward(n, wg.float().cpu(), wu.float().cpu(), wd.float().cpu()), FWD, f"ffn on {d}")
+        dy = torch.randn(300, 512, device=d, generator=gen).bfloat16()
+        ops.rmsnorm_backward(dy, x, gamma, torch.ones(300, device=d))
+
+
 def test_reference_cuda_rmsnorm_ab():
     """A/B against the one reference CUDA kernel that builds (oracle/_ref, fp16 only)."""
     import glob
