@@ -80,7 +80,6 @@ struct GemmKernelParams {
     CUtensorMap map_a_dn, map_b_dn;
     int k_dn, n_dn, tiles_n_dn;
     int ffn_prefix;         // gate/up-only tiles at the head of every mixed round
-    int ffn_nowait;         // timing experiments only (L32_FFN_NOWAIT=1): skip the act_done wait -> WRONG results
     uint32_t idesc_dn;
     uint32_t* act_done;
 };
@@ -339,9 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 if (dn) {
                     // its A operand is the act of this m-tile: every epilogue warp of every gate/up tile of the row
                     // block must have stored (generic proxy, other SMs) before the TMA (async proxy) may read it
-                    if (!(p.ffn_nowait & 1))
-                        wait_flag_ge<false>(&p.act_done[tc.m_blk], static_cast<uint32_t>(p.tiles_n * kEpiWarps * kCtaGroup));
-                    if (!(p.ffn_nowait & 2)) fence_proxy_async_all();
+                    wait_flag_ge<false>(&p.act_done[tc.m_blk], static_cast<uint32_t>(p.tiles_n * kEpiWarps * kCtaGroup));
+                    fence_proxy_async_all();
                 }
                 if (!dn && p.ag.world > 1 && m0 < p.m) {
                     // the A rows of this tile may belong to other ranks: wait until every puller warp has landed them
@@ -873,7 +871,6 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
             const int v = atoi(env);
             if (v >= 0 && v <= a_tiles) kp.ffn_prefix = v;
         }
-        if (const char* env = getenv("L32_FFN_NOWAIT")) kp.ffn_nowait = atoi(env);
         kp.m_il_world = 0;
     }
 

@@ -223,12 +223,12 @@ def ffn1k():
             ops.tp_ffn_forward_fused(x, [x.data_ptr()], ready, done, 1, 0, T, wg, wu, wd, [slot.data_ptr()], act=act, act_done=act_done)
         fl = 6.0 * T * H * I
         for env in ({}, {"L32_RASTER_GROUP": "4"}, {"L32_RASTER_GROUP": "32"}):
-            for k in ("L32_FFN_NOWAIT", "L32_FFN_PREFIX", "L32_RASTER_GROUP"):
+            for k in ("L32_FFN_PREFIX", "L32_RASTER_GROUP"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             t1 = timeit(one, iters=20)
             print(f"ffn1k T={T} H={H} I={I} {env}: one kernel {t1 * 1e3:.0f} us ({fl / t1 / 1e9:.0f} TF/s)", flush=True)
-        for k in ("L32_FFN_NOWAIT", "L32_FFN_PREFIX", "L32_RASTER_GROUP"):
+        for k in ("L32_FFN_PREFIX", "L32_RASTER_GROUP"):
             os.environ.pop(k, None)
         t2 = timeit(two, iters=20)
         print(f"ffn1k T={T} H={H} I={I}: two kernels {t2 * 1e3:.0f} us ({fl / t2 / 1e9:.0f} TF/s)", flush=True)
@@ -251,8 +251,8 @@ if __name__ == "__main__":
     elif what == "tp_emul":
         tp_emul(8, one_kernel=False)
         tp_emul(8, T=32768, one_kernel=False)
-        for env in ({}, {"L32_RASTER_GROUP": "32"}, {"L32_RASTER_GROUP": "16"}, {}, {"L32_RASTER_GROUP": "32"}, {"L32_RASTER_GROUP": "16"}):
-            for k in ("L32_FFN_NOWAIT", "L32_FFN_PREFIX", "L32_SWIGLU_TILE_N", "L32_RASTER_GROUP"):
+        for env in ({}, {"L32_RASTER_GROUP": "32"}, {"L32_RASTER_GROUP": "16"}):
+            for k in ("L32_FFN_PREFIX", "L32_SWIGLU_TILE_N", "L32_RASTER_GROUP"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             print(env)
