@@ -252,7 +252,17 @@ def extra_numbers(dev, peaks):
     fl = 18.0 * T * H * I
     out["train_11b_fwd_bwd_8192tok"] = {"ms": t * 1e3, "tokens_per_s": T / t, "TFLOPs": fl / t / 1e12,
                                         "frac_of_bf16_burst_peak": fl / t / 1e12 / peaks["bf16_tflops"]}
-    del norm, ffn, x, r, dy
+    # ---- config 4 proper: LoRA (rank 16, alpha 32) on a frozen w_down, gate / up trainable; adapter fused into the GEMMs
+    lo = L.Linear_LORA(I, H, rank=16, alpha=32.0, dropout=0.0).to(dev, dt)
+    with torch.no_grad():
+        lo.linear.weight.copy_(ffn.w_down.weight)
+        lo.lora_b.weight.normal_(0, 0.02)
+    ffn.w_down = lo
+    t = _time_cuda(train_step, 10, warm=3)
+    fl = 16.0 * T * H * I                                # 6 fwd + d_act 2 + dX 4 + dWg/dWu 4 (no dW_down); O(rank) terms ignored
+    out["train_11b_lora_r16_fwd_bwd_8192tok"] = {"ms": t * 1e3, "tokens_per_s": T / t, "TFLOPs": fl / t / 1e12,
+                                                 "frac_of_bf16_burst_peak": fl / t / 1e12 / peaks["bf16_tflops"]}
+    del norm, ffn, lo, x, r, dy
     torch.cuda.empty_cache()
     # ---- 90B shape prefill on one GPU (config 5 at p = 1)
     H, I, T = 8192, 28672, 8192

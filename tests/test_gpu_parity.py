@@ -416,6 +416,44 @@ def test_full_size_prefill_subsets_and_properties(hidden, inter):
     assert torch.isfinite(dgam.float()).all()
 
 
+def test_full_size_lora_step_11b():
+    """BASELINE config 4: LoRA (rank 16, alpha 32) on a frozen w_down at the 11B shape, seq 2048, forward + backward with
+    the adapter fused into the GEMMs.  Row subset against the oracle (autograd), adapter gradients against the closed
+    form evaluated in fp32 on the device over all 2048 tokens."""
+    tokens, hidden, inter, rank, alpha = 2048, 4096, 14336, 16, 32.0
+    scale = alpha / rank
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    rn = lambda *sh: torch.randn(*sh, device=DEV, generator=gen)
+    ru = lambda *sh: torch.rand(*sh, device=DEV, generator=gen) * 2 - 1
+    x, dy = rn(tokens, hidden).bfloat16(), rn(tokens, hidden).bfloat16()
+    wg, wu = (ru(inter, hidden) / hidden ** 0.5).bfloat16(), (ru(inter, hidden) / hidden ** 0.5).bfloat16()
+    wd = (ru(hidden, inter) / inter ** 0.5).bfloat16()
+    la = (rn(rank, inter) / inter ** 0.5).bfloat16()
+    lb = (0.02 * rn(hidden, rank)).bfloat16()
+    lbs = (lb.float() * scale).bfloat16()
+    y, t, gate, up = ops.ffn_lora_forward(x, wg, wu, wd, la, lbs, want_cache=True)
+    dx, dwg, dwu, dla, dlbs = ops.ffn_lora_backward(dy, x, wg, wu, wd, la, lbs, t, gate, up)
+    c = lambda v: v.float().cpu()
+    rows = torch.randperm(tokens, generator=torch.Generator().manual_seed(2))[:48].sort().values
+    xs = c(x[rows]).requires_grad_(True)
+    yr = O.linear_lora(O.swiglu(xs, c(wg), c(wu)), c(wd), c(la), c(lbs) / scale, alpha, rank)
+    yr.backward(c(dy[rows]))
+    close(y[rows], yr, FWD, "lora y rows")
+    close(dx[rows], xs.grad, BWD, "lora dx rows")
+    f = lambda v: v.float()
+    g_, u_ = f(x) @ f(wg).t(), f(x) @ f(wu).t()
+    act = torch.nn.functional.silu(g_) * u_
+    uu = f(dy) @ f(lbs)                                            # [T, rank] = dy (s B)
+    close(t, act @ f(la).t(), (1.5e-2, 2.0 ** -5), "t = act A^T")
+    close(dla, uu.t() @ act, (1.5e-2, 2.0 ** -5), "dlora_a")
+    close(dlbs, f(dy).t() @ (act @ f(la).t()), (1.5e-2, 2.0 ** -5), "dlora_b (scaled matrix)")
+    d_act = f(dy) @ f(wd) + uu @ f(la)
+    sg = torch.sigmoid(g_)
+    cols = torch.arange(0, inter, inter // 16)[:16].to(DEV)
+    dg = d_act * u_ * (sg * (1 + g_ * (1 - sg)))
+    close(dwg[cols], dg[:, cols].t() @ f(x), BWD, "dw_gate rows (through the fused adapter)")
+
+
 @pytest.mark.parametrize("batch", [1, 2, 8, 33, 64])
 def test_decode_shapes_11b(batch):
     """BASELINE config 3: KV-cached decode, x [B, 1, 4096]; whole-matrix check against the oracle."""
