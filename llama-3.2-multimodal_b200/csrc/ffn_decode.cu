@@ -7,7 +7,7 @@
 // Model/model.py:217).
 //
 // Design ("swap-AB" on tcgen05): the WEIGHT rows are the UMMA M operand (128 rows per CTA), the tokens are the
-// UMMA N operand (padded to 16/32/64/128), the accumulator D[weight row, token] lives in TMEM.
+// UMMA N operand (padded to a multiple of 16), the accumulator D[weight row, token] lives in TMEM.
 //   * one CTA = one block of 128 weight rows x one K split; a cluster of `splits` CTAs shares a row block and
 //     reduces its fp32 partials through distributed shared memory (no atomics, no workspace, deterministic);
 //   * the host sizes the grid so that ALL CTAs are co-resident (2-4 per SM): equal work per CTA and a fair
@@ -44,7 +44,7 @@ struct DecodeParams {
     const void* bias[2];    // optional per-output-row bias ([0] gate / linear, [1] up)
     const void* addend;     // linear only, optional [tokens, rows_out]: out = a w^T + bias + addend
     void* cache[2];         // SwiGLU only, optional: pre-activation gate / up projections [tokens, rows_out]
-    int tokens, n_pad;      // n_pad = UMMA N in {16, 32, 64, 128}
+    int tokens, n_pad;      // n_pad = UMMA N = tokens rounded up to a multiple of 16 (<= 128)
     int rows_out;           // inter (SwiGLU) or out_features (linear)
     int k;                  // reduction length
     int splits;             // K splits = cluster size
@@ -390,7 +390,7 @@ int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0
     DecodeParams p;
     memset(&p, 0, sizeof(p));
     p.tokens = tokens;
-    p.n_pad = tokens <= 16 ? 16 : tokens <= 32 ? 32 : tokens <= 64 ? 64 : 128;
+    p.n_pad = ((tokens + 15) / 16) * 16;   // UMMA N: any multiple of 16 (M = 128); a smaller token tile leaves more ring stages
     p.rows_out = rows_out;
     p.k = k;
     p.ldo = rows_out;
@@ -401,7 +401,8 @@ int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0
     p.cache[0] = cache0;
     p.cache[1] = cache1;
     p.idesc = make_idesc_f16(dtype == L32_BF16, kRowsA, static_cast<uint32_t>(p.n_pad), false, false);
-    p.tmem_cols = p.n_pad < 32 ? 32u : static_cast<uint32_t>(p.n_pad);
+    p.tmem_cols = 32u;                     // TMEM allocations are powers of two >= 32 columns
+    while (p.tmem_cols < static_cast<uint32_t>(p.n_pad)) p.tmem_cols *= 2u;
 
     const int row_blocks = (rows_out + rows_per_block - 1) / rows_per_block;
     const int nkb = (k + kBlockK - 1) / kBlockK;

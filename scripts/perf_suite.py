@@ -236,7 +236,9 @@ def ffn1k():
 
 if __name__ == "__main__":
     what = sys.argv[1]
-    if what == "decode":
+    if what == "decode_mid":
+        decode(4096, 14336, batches=(24, 40, 48, 64, 80, 96))
+    elif what == "decode":
         decode(4096, 14336)
         decode(8192, 28672, nsets=2)
     elif what == "decode_sweep":
