@@ -45,7 +45,7 @@ extern "C" {
 #define L32_ERR_DRIVER (-5)
 #define L32_ERR_WORKSPACE (-6)
 
-/* ABI version of this header (bumped on any signature change). */
+/* ABI version of this header (bumped on any signature change).  2: tensor-parallel, LoRA and block-tail entry points. */
 L32_API int l32_abi_version(void);
 /* Number of CUDA kernels this library has launched in the calling process so far (monotonic). */
 L32_API unsigned long long l32_kernel_launch_count(void);

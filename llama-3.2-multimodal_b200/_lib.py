@@ -85,8 +85,15 @@ def lib() -> ctypes.CDLL:
                 fn = getattr(handle, name)
                 fn.restype = res
                 fn.argtypes = args
+            got = handle.l32_abi_version()
+            if got != ABI_VERSION:
+                raise L32Error(f"{LIB_PATH} has ABI version {got}, this package needs {ABI_VERSION}: rebuild the library "
+                               "(python -c 'import __graft_entry__ as g; g.build()')")
             _lib = handle
     return _lib
+
+
+ABI_VERSION = 2   # must match l32_abi_version() of the loaded library (include/l32_ffn.h)
 
 
 def check(code: int, what: str) -> None:

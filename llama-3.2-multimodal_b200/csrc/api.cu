@@ -82,7 +82,7 @@ bool shapes_ok(int64_t tokens, int hidden, int inter) {
 
 extern "C" {
 
-int l32_abi_version(void) { return 1; }
+int l32_abi_version(void) { return 2; }
 
 unsigned long long l32_kernel_launch_count(void) { return launch_count(); }
 
