@@ -113,11 +113,6 @@ L32_DEVICE uint4 ld_global_nc_v4(const void* p) {
 L32_DEVICE void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-L32_DEVICE uint4 ld_shared_v4(const void* p) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)) : "memory");
-    return r;
-}
 
 // Bulk async store of one contiguous row segment (shared -> global), tracked by the issuing thread's bulk group.
 L32_DEVICE void bulk_store_row(void* gdst, const void* smem_src, uint32_t bytes) {
