@@ -246,6 +246,12 @@ L32_API int l32_tp_reduce_partials(const void* slots, const uint32_t* flags, uin
                                    const void* addend, void* y, int64_t rows, int64_t slot_rows, int hidden, int dtype,
                                    void* stream);
 
+/* Host-side view of the persistent kernels' tile sequences (no GPU needed; used by the CPU tests).
+ *   kind 0: plain / reduce-scatter order, cfg = {tiles_m, tiles_n, group, m_rotate, il_world, il_tiles_per_chunk, il_rank}
+ *   kind 1: one-kernel feed-forward order, cfg = {tiles_m, n_tiles_gate_up, n_tiles_down, group, m_rotate, prefix}
+ *   out3 = {problem (0 gate/up or plain, 1 down), m_tile, n_tile} of the t-th tile. */
+L32_API int l32_debug_tile_order(int kind, int t, const int* cfg, int* out3);
+
 /* Elementwise helpers (unfused reference points for tests / benchmarks of the fusion saving). */
 L32_API int l32_swiglu_act(const void* gate, const void* up, void* act, int64_t n, int dtype, void* stream);
 

@@ -652,6 +652,14 @@ int l32_tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_t ep
                                                as_stream(stream)));
 }
 
+int l32_debug_tile_order(int kind, int t, const int* cfg, int* out3) {
+    if (cfg == nullptr || out3 == nullptr) return L32_ERR_NULL;
+    if (kind == 0) debug_tile_order(t, cfg[0], cfg[1], cfg[2], cfg[3], cfg[4], cfg[5], cfg[6], out3);
+    else if (kind == 1) debug_ffn_tile_order(t, cfg[0], cfg[1], cfg[2], cfg[3], cfg[4], cfg[5], out3);
+    else return L32_ERR_BAD_SHAPE;
+    return L32_OK;
+}
+
 int l32_swiglu_act(const void* gate, const void* up, void* act, int64_t n, int dtype, void* stream) {
     if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
     if (n < 0 || (n % 8) != 0) return L32_ERR_BAD_SHAPE;

@@ -129,11 +129,11 @@ struct TileCoord {
 struct TileOrder {
     int tiles_m, tiles_n, group, m_rotate, il_world, il_tpc, il_rank;
 };
-L32_DEVICE TileCoord tile_coord(int t, const TileOrder& o) {
+__host__ L32_DEVICE TileCoord tile_coord(int t, const TileOrder& o) {
     const int per_group = o.group * o.tiles_n;
     const int g = t / per_group;
     const int first_m = g * o.group;
-    const int gsize = min(o.group, o.tiles_m - first_m);
+    const int gsize = o.group < o.tiles_m - first_m ? o.group : o.tiles_m - first_m;
     const int r = t - g * per_group;
     TileCoord c;
     const int logical = first_m + r % gsize;
@@ -160,7 +160,7 @@ L32_DEVICE TileCoord tile_coord(int t, const TileOrder& o) {
 struct FfnOrder {
     int tiles_m, n_gu, n_dn, group, m_rotate, prefix;
 };
-L32_DEVICE TileCoord ffn_tile_coord(int t, const FfnOrder& o) {
+__host__ L32_DEVICE TileCoord ffn_tile_coord(int t, const FfnOrder& o) {
     const int A = o.group * o.n_gu, B = o.group * o.n_dn;
     const int rounds = o.tiles_m / o.group;
     int r, idx, prob;
@@ -725,6 +725,19 @@ int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
     CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? L32_OK : L32_ERR_DRIVER;
+}
+
+// Host-side view of the persistent kernels' tile sequences (tests/test_tile_order.py checks on the CPU that every tile is
+// visited exactly once and that every down tile of EPI_FFN_TP comes well after the act tiles it consumes).
+void debug_tile_order(int t, int tiles_m, int tiles_n, int group, int m_rotate, int il_world, int il_tpc, int il_rank, int* out3) {
+    const TileOrder o = {tiles_m, tiles_n, group, m_rotate, il_world, il_tpc, il_rank};
+    const TileCoord c = tile_coord(t, o);
+    out3[0] = c.prob; out3[1] = c.m_blk; out3[2] = c.n_blk;
+}
+void debug_ffn_tile_order(int t, int tiles_m, int n_gu, int n_dn, int group, int m_rotate, int prefix, int* out3) {
+    const FfnOrder o = {tiles_m, n_gu, n_dn, group, m_rotate, prefix};
+    const TileCoord c = ffn_tile_coord(t, o);
+    out3[0] = c.prob; out3[1] = c.m_blk; out3[2] = c.n_blk;
 }
 
 int gemm_sm100(const GemmProblem& g, cudaStream_t s) {

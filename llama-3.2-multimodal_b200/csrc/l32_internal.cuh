@@ -99,6 +99,8 @@ struct GemmProblem {
     TpFfnDown dn;           // EPI_FFN_TP only
 };
 int gemm_sm100(const GemmProblem& p, cudaStream_t s);   // returns L32_* / cudaError_t
+void debug_tile_order(int t, int tiles_m, int tiles_n, int group, int m_rotate, int il_world, int il_tpc, int il_rank, int* out3);
+void debug_ffn_tile_order(int t, int tiles_m, int n_gu, int n_dn, int group, int m_rotate, int prefix, int* out3);
 
 // ---- elementwise.cu (n = element count, multiple of 8)
 cudaError_t swiglu_bwd_elementwise(const void* d_act, const void* gate, const void* up, void* d_gate, void* d_up,
