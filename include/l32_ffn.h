@@ -17,6 +17,12 @@
  *   - Inputs are borrowed; outputs are written in place into caller-owned buffers.
  *   - Weight layout is the Python/HF one: w_gate, w_up are [inter, hidden]; w_down is [hidden, inter]
  *     (reference Tools/swiglu/FusedSwiglu.py:63-64, Model/model.py:214).
+ *   - WEIGHTS MUST BE FINAL BEFORE THE PREVIOUS KERNEL OF THE STREAM STARTS.  Every kernel here is launched with
+ *     programmatic dependent launch and prefetches its weight operands (norm weight, w_gate / w_up / w_down, LoRA
+ *     matrices) BEFORE it waits for the preceding kernel of the stream; only activations / gradients are read after that
+ *     wait.  A weight that is itself produced on the same stream (a dtype cast, an optimiser step, an l32_gemm output
+ *     used as a weight) must therefore be separated from its consumer by at least one other kernel or event -- the
+ *     Python layer (ops.py) caches cast / contiguous weight copies so that it never launches such a producer itself.
  */
 #ifndef L32_FFN_H_
 #define L32_FFN_H_
@@ -44,8 +50,10 @@ extern "C" {
 #define L32_ERR_NULL (-4)
 #define L32_ERR_DRIVER (-5)
 #define L32_ERR_WORKSPACE (-6)
+#define L32_ERR_NOT_RESIDENT (-7)
 
-/* ABI version of this header (bumped on any signature change).  2: tensor-parallel, LoRA and block-tail entry points. */
+/* ABI version of this header (bumped on any signature change).  2: tensor-parallel, LoRA and block-tail entry points.
+ * 3: tensor-parallel backward; the all-gather entry points accept an A buffer distinct from the published one. */
 L32_API int l32_abi_version(void);
 /* Number of CUDA kernels this library has launched in the calling process so far (monotonic). */
 L32_API unsigned long long l32_kernel_launch_count(void);
@@ -205,8 +213,9 @@ L32_API int l32_tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas,
                              void* stream);
 
 /* Fused all-gather + gate/up projection + SiLU*mul.
- *   x_full   : this rank's [tokens, hidden] activation buffer; only rows [rank*rows_per_rank, ...) are valid on
- *              entry.  The kernel PULLS the other ranks' rows out of peer_x[s] (NVLink loads issued by the spare
+ *   x_full   : this rank's [tokens, hidden] activation buffer.  If x_full == peer_x[rank] (gather in place) only rows
+ *              [rank*rows_per_rank, ...) are valid on entry; otherwise the own rows are copied from peer_x[rank] too and
+ *              x_full may be a tensor the caller keeps (the saved input of the weight gradients).  The kernel PULLS the other ranks' rows out of peer_x[s] (NVLink loads issued by the spare
  *              warps of the tcgen05 GEMM CTAs) while the tensor cores already work on the rows that have arrived;
  *              tiles are visited starting at the own rows, then rank+1, rank+2, ... (the pull order).
  *   ready    : own flags, ready[s] >= epoch once rank s has written its rows (see l32_tp_signal).
@@ -227,7 +236,31 @@ L32_API int l32_tp_linear_forward_reduce_scatter(const void* a, const void* w, v
                                                  int64_t rows_per_rank, int64_t tokens, int in_local, int out_features,
                                                  int dtype, void* stream);
 
-/* The two calls above as ONE persistent kernel: gate/up tiles (all-gather pulled in) and down tiles (reduce-scatter pushed
+/* Tensor-parallel BACKWARD of the feed-forward (mirror image of the two forward calls: all-gather of dY pulled inside
+ * the d_act GEMM, reduce-scatter of the partial dX pushed from the two-phase dX GEMM; the weight gradients are local
+ * l32_gemm calls on the shard).  No reference counterpart (SwiGLUFunction.backward, Tools/swiglu/FusedSwiglu.py:32-40,
+ * never ran and the reference has no distributed code); the gradient oracle is autograd over FusedSwiglu.py:18-20 +
+ * Model/model.py:217.
+ *   dy_full  : this rank's [tokens, hidden] buffer for the gathered output gradient (rows of rank s pulled from
+ *              peer_dy[s]; when peer_dy[rank] != dy_full the own rows are copied in as well, so dy_full can be a tensor
+ *              the caller keeps for the w_down weight gradient).
+ *   w_down   : this rank's shard [hidden, inter_local] (consumed MN-major, no transpose);
+ *   gate_cache, up_cache : [tokens, inter_local] from the forward;  d_gate, d_up : [tokens, inter_local] outputs;
+ *   act_out  : optional [tokens, inter_local], the recomputed act = silu(gate) * up (operand of dW_down).
+ */
+L32_API int l32_tp_ffn_backward_dact_allgather(void* dy_full, const void* const* peer_dy, const uint32_t* ready,
+                                               uint32_t* done, uint32_t epoch, int rank, int world, int64_t rows_per_rank,
+                                               const void* w_down, const void* gate_cache, const void* up_cache,
+                                               void* d_gate, void* d_up, void* act_out, int64_t tokens, int hidden,
+                                               int inter_local, int dtype, void* stream);
+/*   partial dx = d_gate w_gate_shard + d_up w_up_shard (ONE GEMM, two accumulation phases), every row stored into the
+ *   slot of the rank that owns it (peer_slots as in l32_tp_linear_forward_reduce_scatter); the owner then sums the
+ *   slots with l32_tp_reduce_partials. */
+L32_API int l32_tp_ffn_backward_dx_reduce_scatter(const void* d_gate, const void* d_up, const void* w_gate, const void* w_up,
+                                                  void* const* peer_slots, int rank, int world, int64_t rows_per_rank,
+                                                  int64_t tokens, int hidden, int inter_local, int dtype, void* stream);
+
+/* The two forward calls above as ONE persistent kernel: gate/up tiles (all-gather pulled in) and down tiles (reduce-scatter pushed
  * out) share the tile loop -- the down tiles of one group of rows are interleaved with the gate/up tiles of the next
  * group, so the NVLink pushes overlap the (twice as long) gate/up math instead of only the down projection, and the
  * intermediate act is consumed while it is still in L2.

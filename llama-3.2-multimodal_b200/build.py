@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{out}")
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", *objs, "-o", LIB,
-            "-cudart", "static"]
+            "-cudart", "shared"]   # torch has already mapped libcudart.so.12; a static cudart would embed its whole symbol table
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

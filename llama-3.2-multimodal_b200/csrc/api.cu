@@ -12,6 +12,16 @@ namespace l32 {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+uint64_t spin_timeout_ns() {
+    static const uint64_t ns = [] {
+        const char* v = getenv("L32_TP_TIMEOUT_S");
+        double sec = (v != nullptr && *v != '\0') ? atof(v) : 120.0;
+        if (!(sec >= 1.0)) sec = 1.0;
+        if (sec > 86400.0) sec = 86400.0;
+        return static_cast<uint64_t>(sec * 1e9);
+    }();
+    return ns;
+}
 }  // namespace l32
 
 namespace {
@@ -82,7 +92,7 @@ bool shapes_ok(int64_t tokens, int hidden, int inter) {
 
 extern "C" {
 
-int l32_abi_version(void) { return 2; }
+int l32_abi_version(void) { return 3; }
 
 unsigned long long l32_kernel_launch_count(void) { return launch_count(); }
 
@@ -95,6 +105,7 @@ const char* l32_error_string(int code) {
         case L32_ERR_NULL: return "required pointer is null";
         case L32_ERR_DRIVER: return "CUDA driver entry point unavailable (cuTensorMapEncodeTiled)";
         case L32_ERR_WORKSPACE: return "workspace too small or misaligned";
+        case L32_ERR_NOT_RESIDENT: return "tensor-parallel kernel: the persistent grid cannot be co-resident on this context's SMs";
         default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown error";
     }
 }
@@ -493,6 +504,64 @@ int l32_tp_peer_copy(void* dst, const void* src, size_t bytes, int ctas, int war
     return static_cast<int>(tp_peer_copy(dst, src, bytes, ctas, warps, unroll, seg_bytes, as_stream(stream)));
 }
 
+namespace {
+bool tp_args_ok(int rank, int world, int64_t rows_per_rank, int64_t tokens) {
+    return world >= 1 && world <= kMaxTpWorld && rank >= 0 && rank < world && rows_per_rank > 0 &&
+           rows_per_rank * world >= tokens && rows_per_rank <= 0x7fffffff;
+}
+
+// All-gather of the A operand fused into the GEMM `g` (g.a[0] = a_full must already be set).  Clears the arrival
+// counters on the stream.  When a_full is not the buffer the peers pull from (peer_a[rank]) the own rows are copied in
+// by the pullers as well, so a_full may be a fresh tensor the caller keeps (e.g. saved for the backward).
+int setup_allgather(GemmProblem& g, void* a_full, const void* const* peer_a, const uint32_t* ready, uint32_t* done,
+                    uint32_t epoch, int rank, int world, int64_t rows_per_rank, cudaStream_t s) {
+    if (world <= 1) {
+        if (peer_a != nullptr && peer_a[0] != nullptr && peer_a[0] != a_full) return L32_ERR_BAD_SHAPE;   // nothing would copy the rows
+        return L32_OK;
+    }
+    if (peer_a == nullptr || ready == nullptr || done == nullptr) return L32_ERR_NULL;
+    // arrival counters of the pull: cleared here so that a call never sees the counts of an earlier one
+    cudaError_t e = cudaMemsetAsync(done, 0, sizeof(uint32_t) * kMaxTpWorld, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    g.ag.world = world;
+    g.ag.rank = rank;
+    g.ag.rows_per_rank = static_cast<int>(rows_per_rank);
+    for (int r = 0; r < world; ++r) {
+        if (peer_a[r] == nullptr || !is_aligned16(peer_a[r])) return L32_ERR_NULL;
+        g.ag.peer_src[r] = peer_a[r];
+    }
+    g.ag.local_dst = a_full;
+    g.ag.ready = ready;
+    g.ag.done = done;
+    g.ag.epoch = epoch;
+    g.ag.done_base = 0;
+    g.ag.copy_own = (peer_a[rank] != a_full) ? 1 : 0;
+    g.m_rotate_rows = static_cast<int>(rank * rows_per_rank);
+    // one raster group = the m-tiles of one rank's chunk, so tiles only ever wait for the chunk being consumed
+    const int tile_m = 256;
+    int grp = static_cast<int>(rows_per_rank / tile_m);
+    if (grp < 1) grp = 1;
+    if (grp > 8) grp = 8;
+    g.raster_group = grp;
+    return L32_OK;
+}
+
+int setup_reduce_scatter(GemmProblem& g, void* const* peer_slots, int rank, int world, int64_t rows_per_rank, int64_t tokens) {
+    if (peer_slots == nullptr) return L32_ERR_NULL;
+    g.rs.world = world;
+    g.rs.rank = rank;
+    g.rs.rows_per_rank = static_cast<int>(rows_per_rank);
+    for (int o = 0; o < world; ++o) {
+        if (peer_slots[o] == nullptr || !is_aligned16(peer_slots[o])) return L32_ERR_NULL;
+        g.rs.peer_dst[o] = peer_slots[o];
+    }
+    // start with the rows owned by the next rank so that at any moment the ranks push to different owners
+    g.m_rotate_rows = static_cast<int>(((rank + 1) % world) * rows_per_rank);
+    if (g.m_rotate_rows >= tokens) g.m_rotate_rows = 0;
+    return L32_OK;
+}
+}  // namespace
+
 int l32_tp_swiglu_forward_allgather(void* x_full, const void* const* peer_x, const uint32_t* ready, uint32_t* done,
                                     uint32_t epoch, int rank, int world, int64_t rows_per_rank, const void* w_gate,
                                     const void* w_up, const void* b_gate, const void* b_up, void* act, void* gate_cache,
@@ -518,31 +587,8 @@ int l32_tp_swiglu_forward_allgather(void* x_full, const void* const* peer_x, con
     g.bias[1] = b_up;
     g.ldd = inter_local;
     g.cta_group = 2;
-    if (world > 1) {
-        if (peer_x == nullptr || ready == nullptr || done == nullptr) return L32_ERR_NULL;
-        // arrival counters of the pull: cleared here so that a call never sees the counts of an earlier one
-        cudaError_t e = cudaMemsetAsync(done, 0, sizeof(uint32_t) * kMaxTpWorld, as_stream(stream));
-        if (e != cudaSuccess) return static_cast<int>(e);
-        g.ag.world = world;
-        g.ag.rank = rank;
-        g.ag.rows_per_rank = static_cast<int>(rows_per_rank);
-        for (int s = 0; s < world; ++s) {
-            if (peer_x[s] == nullptr) return L32_ERR_NULL;
-            g.ag.peer_src[s] = peer_x[s];
-        }
-        g.ag.local_dst = x_full;
-        g.ag.ready = ready;
-        g.ag.done = done;
-        g.ag.epoch = epoch;
-        g.ag.done_base = 0;
-        g.m_rotate_rows = static_cast<int>(rank * rows_per_rank);
-        // one raster group = the m-tiles of one rank's chunk, so tiles only ever wait for the chunk being consumed
-        const int tile_m = 256;
-        int grp = static_cast<int>(rows_per_rank / tile_m);
-        if (grp < 1) grp = 1;
-        if (grp > 8) grp = 8;
-        g.raster_group = grp;
-    }
+    const int rc = setup_allgather(g, x_full, peer_x, ready, done, epoch, rank, world, rows_per_rank, as_stream(stream));
+    if (rc != L32_OK) return rc;
     return gemm_sm100(g, as_stream(stream));
 }
 
@@ -563,16 +609,60 @@ int l32_tp_linear_forward_reduce_scatter(const void* a, const void* w, void* con
     g.epilogue = EPI_STORE;
     g.ldd = out_features;
     g.cta_group = 2;
-    g.rs.world = world;
-    g.rs.rank = rank;
-    g.rs.rows_per_rank = static_cast<int>(rows_per_rank);
-    for (int o = 0; o < world; ++o) {
-        if (peer_slots[o] == nullptr || !is_aligned16(peer_slots[o])) return L32_ERR_NULL;
-        g.rs.peer_dst[o] = peer_slots[o];
-    }
-    // start with the rows owned by the next rank so that at any moment the ranks push to different owners
-    g.m_rotate_rows = static_cast<int>(((rank + 1) % world) * rows_per_rank);
-    if (g.m_rotate_rows >= tokens) g.m_rotate_rows = 0;
+    const int rc = setup_reduce_scatter(g, peer_slots, rank, world, rows_per_rank, tokens);
+    if (rc != L32_OK) return rc;
+    return gemm_sm100(g, as_stream(stream));
+}
+
+/* ---- tensor-parallel backward: d_act GEMM with the all-gather of dY pulled in, dX GEMM with the reduce-scatter pushed out */
+int l32_tp_ffn_backward_dact_allgather(void* dy_full, const void* const* peer_dy, const uint32_t* ready, uint32_t* done,
+                                       uint32_t epoch, int rank, int world, int64_t rows_per_rank, const void* w_down,
+                                       const void* gate_cache, const void* up_cache, void* d_gate, void* d_up, void* act_out,
+                                       int64_t tokens, int hidden, int inter_local, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, inter_local) || !tp_args_ok(rank, world, rows_per_rank, tokens)) return L32_ERR_BAD_SHAPE;
+    if (tokens == 0) return L32_OK;
+    if (dy_full == nullptr || w_down == nullptr || gate_cache == nullptr || up_cache == nullptr || d_gate == nullptr ||
+        d_up == nullptr)
+        return L32_ERR_NULL;
+    // d_act = dy w_down_shard (w_down_shard [hidden, inter_local] consumed MN-major); SiLU' recomputed in the epilogue
+    GemmProblem g = blank(static_cast<int>(tokens), inter_local, dtype);
+    g.k[0] = hidden;
+    g.a[0] = op(dy_full, hidden, 0);
+    g.b[0] = op(w_down, inter_local, 1);
+    g.epilogue = EPI_SWIGLU_BWD;
+    g.d[0] = d_gate;
+    g.d[1] = d_up;
+    g.d[2] = act_out;
+    g.e[0] = gate_cache;
+    g.e[1] = up_cache;
+    g.ldd = inter_local;
+    g.cta_group = 2;
+    const int rc = setup_allgather(g, dy_full, peer_dy, ready, done, epoch, rank, world, rows_per_rank, as_stream(stream));
+    if (rc != L32_OK) return rc;
+    return gemm_sm100(g, as_stream(stream));
+}
+
+int l32_tp_ffn_backward_dx_reduce_scatter(const void* d_gate, const void* d_up, const void* w_gate, const void* w_up,
+                                          void* const* peer_slots, int rank, int world, int64_t rows_per_rank, int64_t tokens,
+                                          int hidden, int inter_local, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, inter_local) || !tp_args_ok(rank, world, rows_per_rank, tokens)) return L32_ERR_BAD_SHAPE;
+    if (tokens == 0) return L32_OK;
+    if (d_gate == nullptr || d_up == nullptr || w_gate == nullptr || w_up == nullptr) return L32_ERR_NULL;
+    // partial dx = d_gate w_gate_shard + d_up w_up_shard: one two-phase GEMM, rows pushed to their owners' slots
+    GemmProblem g = blank(static_cast<int>(tokens), hidden, dtype);
+    g.num_phases = 2;
+    g.k[0] = g.k[1] = inter_local;
+    g.a[0] = op(d_gate, inter_local, 0);
+    g.a[1] = op(d_up, inter_local, 0);
+    g.b[0] = op(w_gate, hidden, 1);
+    g.b[1] = op(w_up, hidden, 1);
+    g.epilogue = EPI_STORE;
+    g.ldd = hidden;
+    g.cta_group = 2;
+    const int rc = setup_reduce_scatter(g, peer_slots, rank, world, rows_per_rank, tokens);
+    if (rc != L32_OK) return rc;
     return gemm_sm100(g, as_stream(stream));
 }
 
@@ -607,35 +697,18 @@ int l32_tp_ffn_forward_fused(void* x_full, const void* const* peer_x, const uint
     g.dn.ld = inter_local;
     g.dn.n = hidden;
     g.dn.act_done = act_done;
-    g.rs.world = world;
-    g.rs.rank = rank;
-    g.rs.rows_per_rank = static_cast<int>(rows_per_rank);
-    for (int o = 0; o < world; ++o) {
-        if (peer_slots[o] == nullptr || !is_aligned16(peer_slots[o])) return L32_ERR_NULL;
-        g.rs.peer_dst[o] = peer_slots[o];
-    }
+    int rc = setup_reduce_scatter(g, peer_slots, rank, world, rows_per_rank, tokens);
+    if (rc != L32_OK) return rc;
     int grp = static_cast<int>(rows_per_rank / tile_m);
     if (grp < 1) grp = 1;
     if (grp > 8) grp = 8;
+    if (world > 1) {
+        if (peer_x == nullptr || peer_x[rank] != x_full) return L32_ERR_BAD_SHAPE;   // this variant gathers in place
+        rc = setup_allgather(g, x_full, peer_x, ready, done, epoch, rank, world, rows_per_rank, s);
+        if (rc != L32_OK) return rc;
+    }
     g.raster_group = grp;   // one group of m-tiles = (a divisor of) one rank's chunk: pulls, math and pushes move in step
     g.m_rotate_rows = static_cast<int>(rank * rows_per_rank);
-    if (world > 1) {
-        if (peer_x == nullptr || ready == nullptr || done == nullptr) return L32_ERR_NULL;
-        e = cudaMemsetAsync(done, 0, sizeof(uint32_t) * kMaxTpWorld, s);
-        if (e != cudaSuccess) return static_cast<int>(e);
-        g.ag.world = world;
-        g.ag.rank = rank;
-        g.ag.rows_per_rank = static_cast<int>(rows_per_rank);
-        for (int r = 0; r < world; ++r) {
-            if (peer_x[r] == nullptr) return L32_ERR_NULL;
-            g.ag.peer_src[r] = peer_x[r];
-        }
-        g.ag.local_dst = x_full;
-        g.ag.ready = ready;
-        g.ag.done = done;
-        g.ag.epoch = epoch;
-        g.ag.done_base = 0;
-    }
     return gemm_sm100(g, s);
 }
 

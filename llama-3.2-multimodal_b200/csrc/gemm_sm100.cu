@@ -82,6 +82,7 @@ struct GemmKernelParams {
     int ffn_prefix;         // gate/up-only tiles at the head of every mixed round
     uint32_t idesc_dn;
     uint32_t* act_done;
+    unsigned long long spin_timeout_ns;   // bound of every cross-SM / cross-GPU flag wait
 };
 
 // One operand tile of `rows` x 64 (K) elements into shared memory.
@@ -196,15 +197,17 @@ __host__ L32_DEVICE TileCoord ffn_tile_coord(int t, const FfnOrder& o) {
 
 // All-gather fused into the kernel: this warp's share of pulling chunk after chunk of A rows out of peer memory
 // (NVLink loads that bypass the non-coherent L1) into the local A buffer, in the order the tiles consume them.
-L32_DEVICE void ag_pull(const TpAllGather& ag, int m, size_t row_bytes, int puller, int num_pullers, uint32_t lane) {
+L32_DEVICE void ag_pull(const TpAllGather& ag, int m, size_t row_bytes, int puller, int num_pullers, uint32_t lane,
+                        uint64_t timeout_ns) {
     constexpr int kUnroll = 8;   // measured (scripts/nvlink_probe.py): 4 warps/SM x 8 loads in flight saturate NVLink pulls; 16 is slower
-    for (int j = 1; j < ag.world; ++j) {
+    // copy_own: the A buffer is NOT the buffer the peers pull from, so the own rows are copied too (a local copy, first)
+    for (int j = ag.copy_own ? 0 : 1; j < ag.world; ++j) {
         const int s = (ag.rank + j) % ag.world;
         const long long r0 = static_cast<long long>(s) * ag.rows_per_rank;
         long long rows = static_cast<long long>(m) - r0;
         if (rows > ag.rows_per_rank) rows = ag.rows_per_rank;
         if (rows > 0) {
-            if (lane == 0) wait_flag_ge<true>(&ag.ready[s], ag.epoch);   // rank s has written its own rows
+            if (lane == 0 && j != 0) wait_flag_ge<true>(&ag.ready[s], ag.epoch, timeout_ns);   // rank s has written its own rows
             __syncwarp();
             const long long nvec = rows * static_cast<long long>(row_bytes / 16);
             const long long v0 = nvec * puller / num_pullers, v1 = nvec * (puller + 1) / num_pullers;
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 if (dn) {
                     // its A operand is the act of this m-tile: every epilogue warp of every gate/up tile of the row
                     // block must have stored (generic proxy, other SMs) before the TMA (async proxy) may read it
-                    wait_flag_ge<false>(&p.act_done[tc.m_blk], static_cast<uint32_t>(p.tiles_n * kEpiWarps * kCtaGroup));
+                    wait_flag_ge<false>(&p.act_done[tc.m_blk], static_cast<uint32_t>(p.tiles_n * kEpiWarps * kCtaGroup), p.spin_timeout_ns);
                     fence_proxy_async_all();
                 }
                 if (!dn && p.ag.world > 1 && m0 < p.m) {
@@ -342,8 +345,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     const int c_hi = (min(m0 + kBlockM, p.m) - 1) / p.ag.rows_per_rank;
                     bool waited = false;
                     for (int c = c_lo; c <= c_hi; ++c) {
-                        if (c == p.ag.rank) continue;
-                        wait_flag_ge<false>(&p.ag.done[c], p.ag.done_base + gridDim.x * static_cast<uint32_t>(kPullWarps));
+                        if (c == p.ag.rank && !p.ag.copy_own) continue;
+                        wait_flag_ge<false>(&p.ag.done[c], p.ag.done_base + gridDim.x * static_cast<uint32_t>(kPullWarps), p.spin_timeout_ns);
                         waited = true;
                     }
                     if (waited) fence_proxy_async_all();   // generic-proxy stores of other SMs -> TMA (async proxy) loads
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         if (p.ag.world > 1) {
             const int idx = static_cast<int>(warp >= 12 ? warp - 10 : warp - 2);   // 0..3
             ag_pull(p.ag, p.m, static_cast<size_t>(p.k[0]) * sizeof(T), static_cast<int>(blockIdx.x) * kPullWarps + idx,
-                    static_cast<int>(gridDim.x) * kPullWarps, lane);
+                    static_cast<int>(gridDim.x) * kPullWarps, lane, p.spin_timeout_ns);
         }
     } else if (warp >= 4 && warp < 4 + kEpiWarps) {
         // ------------------------------------------------------------------ epilogue
@@ -678,6 +681,24 @@ int launch(const GemmKernelParams& kp, int num_tiles, int max_ctas, cudaStream_t
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
+    if (kp.ag.world > 1 || kEpi == EPI_FFN_TP) {
+        // These variants spin on counters that only fill when EVERY CTA of the persistent grid is running (all-gather
+        // arrival counts, act_done): the whole grid must be co-resident.  Ask the driver how many clusters fit on the SMs
+        // this context may use (MPS limits, green contexts) and shrink the grid to that; no room at all is an error.
+        static int max_clusters_dev[kMaxDevices] = {};
+        int& max_clusters = max_clusters_dev[current_device_slot()];
+        if (max_clusters == 0) {
+            int n = 0;
+            cudaError_t q = cudaOccupancyMaxActiveClusters(&n, kernel, &cfg);
+            if (q != cudaSuccess) return static_cast<int>(q);
+            max_clusters = n > 0 ? n : -1;
+        }
+        if (max_clusters < 0) return L32_ERR_NOT_RESIDENT;
+        if (clusters > max_clusters) {
+            clusters = max_clusters;
+            cfg.gridDim = dim3(static_cast<unsigned>(clusters * kCtaGroup));
+        }
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, kp);
     if (e == cudaSuccess) count_launch();
     return static_cast<int>(e);
@@ -823,6 +844,7 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
         }
     }
     kp.ag = g.ag;
+    kp.spin_timeout_ns = spin_timeout_ns();
     kp.rs = g.rs;
     if (g.ag.world > kMaxTpWorld || g.rs.world > kMaxTpWorld) return L32_ERR_BAD_SHAPE;
     if (g.ag.world > 1) {

@@ -14,6 +14,8 @@ unsigned long long launch_count();
 
 inline bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 int num_sms();   // of the current device
+// Bound of every spin on a flag raised by another SM / GPU, after which the kernel traps (L32_TP_TIMEOUT_S, default 120 s).
+uint64_t spin_timeout_ns();
 // Kernel attributes (opt-in shared memory size) are per device: one "already configured" flag per device ordinal.
 constexpr int kMaxDevices = 64;
 inline int current_device_slot() {
@@ -63,6 +65,7 @@ struct TpAllGather {
     uint32_t* done;                 // local counters, done[s] += 1 per puller warp that finished chunk s
     uint32_t epoch;                 // step number (monotonic, >= 1)
     uint32_t done_base;             // value of every done[s] before this launch
+    int copy_own;                   // 1: local_dst is not the buffer the peers pull from -- the own rows are copied in too
 };
 struct TpReduceScatter {
     int world, rank;

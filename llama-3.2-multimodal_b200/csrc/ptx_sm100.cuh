@@ -81,9 +81,11 @@ L32_DEVICE uint4 ld_relaxed_sys_v4(const void* p) {
     return r;
 }
 L32_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-// Bounded spin on a flag another SM / GPU will raise: a protocol bug traps after ~10 s instead of hanging the GPU.
+// Bounded spin on a flag another SM / GPU will raise: a protocol bug traps after `timeout_ns` instead of hanging the GPU
+// for ever.  The bound comes from the host (l32::spin_timeout_ns(): 120 s unless L32_TP_TIMEOUT_S says otherwise) -- long
+// enough that a peer rank stalled by lazy initialisation, checkpointing or a data hiccup does not cost the context.
 template <bool kSys>
-L32_DEVICE void wait_flag_ge(const uint32_t* flag, uint32_t target) {
+L32_DEVICE void wait_flag_ge(const uint32_t* flag, uint32_t target, uint64_t timeout_ns) {
     uint64_t t0 = 0;
     uint32_t spins = 0;
     while (true) {
@@ -92,7 +94,7 @@ L32_DEVICE void wait_flag_ge(const uint32_t* flag, uint32_t target) {
         if ((++spins & 0xffu) == 0) {
             const uint64_t now = globaltimer_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 10000000000ull) __trap();
+            else if (now - t0 > timeout_ns) __trap();
             __nanosleep(64);
         }
     }

@@ -39,9 +39,9 @@ L32_DEVICE uint4 ldg_stream_v4(const void* p) {
 template <typename T>
 __global__ void __launch_bounds__(256) tp_reduce_partials_kernel(const T* slots, const uint32_t* flags, uint32_t epoch,
                                                                  int world, int rank, const T* addend, T* __restrict__ y,
-                                                                 int64_t rows, int64_t slot_rows, int hidden) {
+                                                                 int64_t rows, int64_t slot_rows, int hidden, unsigned long long timeout_ns) {
     pdl_wait_prior_grid();   // this rank's own slot was written by the down GEMM launched before
-    if (threadIdx.x < world && static_cast<int>(threadIdx.x) != rank) wait_flag_ge<true>(&flags[threadIdx.x], epoch);
+    if (threadIdx.x < world && static_cast<int>(threadIdx.x) != rank) wait_flag_ge<true>(&flags[threadIdx.x], epoch, timeout_ns);
     __syncthreads();
     const int64_t nvec = rows * hidden / 8;
     const int64_t slot_vec = slot_rows * hidden / 8;
@@ -156,10 +156,11 @@ cudaError_t tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_
     if (dtype == L32_BF16)
         e = cudaLaunchKernelEx(&cfg, tp_reduce_partials_kernel<__nv_bfloat16>, static_cast<const __nv_bfloat16*>(slots), flags,
                                epoch, world, rank, static_cast<const __nv_bfloat16*>(addend), static_cast<__nv_bfloat16*>(y),
-                               rows, slot_rows, hidden);
+                               rows, slot_rows, hidden, static_cast<unsigned long long>(spin_timeout_ns()));
     else
         e = cudaLaunchKernelEx(&cfg, tp_reduce_partials_kernel<__half>, static_cast<const __half*>(slots), flags, epoch, world,
-                               rank, static_cast<const __half*>(addend), static_cast<__half*>(y), rows, slot_rows, hidden);
+                               rank, static_cast<const __half*>(addend), static_cast<__half*>(y), rows, slot_rows, hidden,
+                               static_cast<unsigned long long>(spin_timeout_ns()));
     if (e == cudaSuccess) count_launch();
     return e;
 }

@@ -5,6 +5,8 @@ torch's current stream of the tensor's device.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from ._lib import L32Error, check, lib
@@ -41,6 +43,29 @@ def _check_cuda(*ts):
     return dev
 
 
+# Cast / contiguous copies of WEIGHTS are cached per source tensor (and its version counter): a norm weight kept in fp32
+# next to bf16 activations, or a non-contiguous view, would otherwise cost a cast kernel on every call -- a visible tax on
+# a 60 us decode step -- and, worse, that cast would be a producer launched directly in front of a kernel that prefetches
+# its weights before it waits for the previous kernel (include/l32_ffn.h, "weights must be final").  On a miss the new
+# copy is made and the stream is synchronised once (skipped while a CUDA graph is being captured: capture follows a
+# warm-up run, which has filled the cache).
+_weight_cache: dict[int, tuple] = {}
+
+
+def _weight(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    if w.dtype == dtype and w.is_contiguous():
+        return w
+    key = id(w)
+    ent = _weight_cache.get(key)
+    if ent is not None and ent[0]() is w and ent[1] == w._version and ent[2].dtype == dtype and ent[3] == w.data_ptr():
+        return ent[2]
+    cast = w.detach().contiguous().to(dtype)
+    if w.is_cuda and not torch.cuda.is_current_stream_capturing():
+        torch.cuda.current_stream(w.device).synchronize()
+    _weight_cache[key] = (weakref.ref(w, lambda _r, k=key: _weight_cache.pop(k, None)), w._version, cast, w.data_ptr())
+    return cast
+
+
 def supported(x: torch.Tensor) -> bool:
     """The reference's gate for its CUDA path (Model/model.py:165): CUDA tensor of a 16-bit float type."""
     return x.is_cuda and x.dtype in _DT
@@ -60,9 +85,7 @@ def add_rmsnorm_forward(x, weight, residual=None, eps=1e-5, *, want_h=False, wan
     rc = None if residual is None else residual.contiguous()
     if rc is not None and rc.shape != xc.shape:
         raise L32Error(f"residual shape {tuple(rc.shape)} != input shape {tuple(xc.shape)}")
-    w = weight.contiguous()
-    if w.dtype != xc.dtype:
-        w = w.to(xc.dtype)
+    w = _weight(weight, xc.dtype)
     if w.numel() != hidden:
         raise L32Error(f"weight has {w.numel()} elements, expected {hidden}")
     if out is not None:
@@ -90,9 +113,7 @@ def rmsnorm_backward(grad_out, h, weight, rms, *, want_dweight=True):
     if gc.dtype != hc.dtype:
         gc = gc.to(hc.dtype)
     rows = hc.numel() // hidden if hidden else 0
-    w = weight.contiguous()
-    if w.dtype != hc.dtype:
-        w = w.to(hc.dtype)
+    w = _weight(weight, hc.dtype)
     dx = torch.empty_like(hc)
     dw = torch.empty(hidden, dtype=hc.dtype, device=hc.device) if want_dweight else None
     L = lib()
@@ -127,14 +148,14 @@ def swiglu_forward(x, w_gate, w_up, b_gate=None, b_up=None, *, want_cache=False)
     """act = silu(x w_gate^T + b_gate) * (x w_up^T + b_up).  Returns (act, gate_cache|None, up_cache|None)."""
     _check_cuda(x, w_gate, w_up, b_gate, b_up)
     x2, tokens = _flat_tokens(x)
-    wg, wu = w_gate.contiguous(), w_up.contiguous()
+    wg, wu = _weight(w_gate, w_gate.dtype), _weight(w_up, w_up.dtype)
     hidden, inter = _check_ffn_weights(x2, wg, wu)
     out_shape = (*x.shape[:-1], inter)
     act = torch.empty(tokens, inter, dtype=x2.dtype, device=x2.device)
     gate = torch.empty_like(act) if want_cache else None
     up = torch.empty_like(act) if want_cache else None
-    bg = None if b_gate is None else b_gate.contiguous().to(x2.dtype)
-    bu = None if b_up is None else b_up.contiguous().to(x2.dtype)
+    bg = None if b_gate is None else _weight(b_gate, x2.dtype)
+    bu = None if b_up is None else _weight(b_up, x2.dtype)
     with torch.cuda.device(x2.device):
         check(lib().l32_swiglu_forward(_ptr(x2), _ptr(wg), _ptr(wu), _ptr(bg), _ptr(bu), _ptr(act), _ptr(gate), _ptr(up),
                                        tokens, hidden, inter, _dtype_code(x2), _stream(x2)), "l32_swiglu_forward")
@@ -147,7 +168,7 @@ def swiglu_backward(grad_act, x, w_gate, w_up, gate_cache, up_cache, *, want_dx=
     """(dx|None, dw_gate|None, dw_up|None, d_gate, d_up); d_gate/d_up are views into the workspace."""
     _check_cuda(grad_act, x, w_gate, w_up, gate_cache, up_cache)
     x2, tokens = _flat_tokens(x)
-    wg, wu = w_gate.contiguous(), w_up.contiguous()
+    wg, wu = _weight(w_gate, w_gate.dtype), _weight(w_up, w_up.dtype)
     hidden, inter = _check_ffn_weights(x2, wg, wu)
     ga = grad_act.contiguous().view(-1, inter)
     if ga.dtype != x2.dtype:
@@ -173,12 +194,12 @@ def linear_forward(a, weight, bias=None):
     """y = a weight^T + bias with weight [out_features, in_features] (nn.Linear layout)."""
     _check_cuda(a, weight, bias)
     a2, tokens = _flat_tokens(a)
-    w = weight.contiguous()
+    w = _weight(weight, weight.dtype)
     out_f, in_f = w.shape
     if a2.shape[1] != in_f or w.dtype != a2.dtype:
         raise L32Error(f"linear: a[..., {a2.shape[1]}] {a2.dtype} vs weight{tuple(w.shape)} {w.dtype}")
     y = torch.empty(tokens, out_f, dtype=a2.dtype, device=a2.device)
-    b = None if bias is None else bias.contiguous().to(a2.dtype)
+    b = None if bias is None else _weight(bias, a2.dtype)
     with torch.cuda.device(a2.device):
         check(lib().l32_linear_forward(_ptr(a2), _ptr(w), _ptr(b), _ptr(y), tokens, in_f, out_f, _dtype_code(a2),
                                        _stream(a2)), "l32_linear_forward")
@@ -189,13 +210,13 @@ def ffn_forward(x, w_gate, w_up, w_down, b_gate=None, b_up=None, b_down=None, *,
     """y = (silu(x w_gate^T) * (x w_up^T)) w_down^T.  Returns (y, gate_cache|None, up_cache|None)."""
     _check_cuda(x, w_gate, w_up, w_down, b_gate, b_up, b_down)
     x2, tokens = _flat_tokens(x)
-    wg, wu, wd = w_gate.contiguous(), w_up.contiguous(), w_down.contiguous()
+    wg, wu, wd = _weight(w_gate, w_gate.dtype), _weight(w_up, w_up.dtype), _weight(w_down, w_down.dtype)
     hidden, inter = _check_ffn_weights(x2, wg, wu, wd)
     y = torch.empty(tokens, hidden, dtype=x2.dtype, device=x2.device)
     act = torch.empty(tokens, inter, dtype=x2.dtype, device=x2.device)
     gate = torch.empty_like(act) if want_cache else None
     up = torch.empty_like(act) if want_cache else None
-    cast = lambda b: None if b is None else b.contiguous().to(x2.dtype)
+    cast = lambda b: None if b is None else _weight(b, x2.dtype)
     bg, bu, bd = cast(b_gate), cast(b_up), cast(b_down)
     with torch.cuda.device(x2.device):
         check(lib().l32_ffn_forward(_ptr(x2), _ptr(wg), _ptr(wu), _ptr(wd), _ptr(bg), _ptr(bu), _ptr(bd), _ptr(y),
@@ -209,14 +230,12 @@ def block_tail_forward(attn_out, residual, norm_weight, eps, w_gate, w_up, w_dow
     (reference Model/model.py:270-273), the final add fused into the down-GEMM epilogue.  Inference only."""
     _check_cuda(attn_out, residual, norm_weight, w_gate, w_up, w_down)
     a2, tokens = _flat_tokens(attn_out)
-    wg, wu, wd = w_gate.contiguous(), w_up.contiguous(), w_down.contiguous()
+    wg, wu, wd = _weight(w_gate, w_gate.dtype), _weight(w_up, w_up.dtype), _weight(w_down, w_down.dtype)
     hidden, inter = _check_ffn_weights(a2, wg, wu, wd)
     r2 = None if residual is None else residual.contiguous().view(-1, hidden)
     if r2 is not None and r2.shape != a2.shape:
         raise L32Error(f"residual shape {tuple(residual.shape)} != attn_out shape {tuple(attn_out.shape)}")
-    w = norm_weight.contiguous()
-    if w.dtype != a2.dtype:
-        w = w.to(a2.dtype)
+    w = _weight(norm_weight, a2.dtype)
     out = torch.empty_like(a2)
     normed = torch.empty_like(a2)
     act = torch.empty(tokens, inter, dtype=a2.dtype, device=a2.device)
@@ -232,7 +251,7 @@ def ffn_backward(grad_y, x, w_gate, w_up, w_down, gate_cache, up_cache, *, want_
     """(dx|None, dw_gate|None, dw_up|None, dw_down|None, d_gate, d_up) for the whole feed-forward."""
     _check_cuda(grad_y, x, w_gate, w_up, w_down, gate_cache, up_cache)
     x2, tokens = _flat_tokens(x)
-    wg, wu, wd = w_gate.contiguous(), w_up.contiguous(), w_down.contiguous()
+    wg, wu, wd = _weight(w_gate, w_gate.dtype), _weight(w_up, w_up.dtype), _weight(w_down, w_down.dtype)
     hidden, inter = _check_ffn_weights(x2, wg, wu, wd)
     gy = grad_y.contiguous().view(-1, hidden)
     if gy.dtype != x2.dtype:
@@ -260,7 +279,7 @@ def ffn_lora_forward(x, w_gate, w_up, w_down, lora_a, lora_bs, *, want_cache=Fal
     alpha / rank).  Returns (y, t [tokens, rank], gate_cache|None, up_cache|None)."""
     _check_cuda(x, w_gate, w_up, w_down, lora_a, lora_bs)
     x2, tokens = _flat_tokens(x)
-    wg, wu, wd = w_gate.contiguous(), w_up.contiguous(), w_down.contiguous()
+    wg, wu, wd = _weight(w_gate, w_gate.dtype), _weight(w_up, w_up.dtype), _weight(w_down, w_down.dtype)
     hidden, inter = _check_ffn_weights(x2, wg, wu, wd)
     la, lb = lora_a.contiguous(), lora_bs.contiguous()
     rank = la.shape[0]
@@ -283,7 +302,7 @@ def ffn_lora_backward(grad_y, x, w_gate, w_up, w_down, lora_a, lora_bs, t, gate_
     """(dx|None, dw_gate|None, dw_up|None, dlora_a|None, dlora_bs|None) for ffn_lora_forward (frozen w_down)."""
     _check_cuda(grad_y, x, w_gate, w_up, w_down, lora_a, lora_bs, t, gate_cache, up_cache)
     x2, tokens = _flat_tokens(x)
-    wg, wu, wd = w_gate.contiguous(), w_up.contiguous(), w_down.contiguous()
+    wg, wu, wd = _weight(w_gate, w_gate.dtype), _weight(w_up, w_up.dtype), _weight(w_down, w_down.dtype)
     hidden, inter = _check_ffn_weights(x2, wg, wu, wd)
     la, lb = lora_a.contiguous(), lora_bs.contiguous()
     rank = la.shape[0]
@@ -353,20 +372,59 @@ def tp_signal(peer_flag_ptrs, index, value, device, zero8=None):
                                   torch.cuda.current_stream(device).cuda_stream), "l32_tp_signal")
 
 
-def tp_swiglu_forward_allgather(x_full, peer_x_ptrs, ready, done, epoch, rank, rows_per_rank, w_gate, w_up, out=None):
-    """Fused all-gather (pulled over NVLink inside the GEMM) + gate/up projection + SiLU*mul on this rank's shard."""
+def tp_swiglu_forward_allgather(x_full, peer_x_ptrs, ready, done, epoch, rank, rows_per_rank, w_gate, w_up, out=None,
+                                want_cache=False):
+    """Fused all-gather (pulled over NVLink inside the GEMM) + gate/up projection + SiLU*mul on this rank's shard.
+    x_full may be the published buffer itself (gather in place) or a fresh [tokens, hidden] tensor (own rows copied too).
+    Returns act, or (act, gate_cache, up_cache) with want_cache."""
     _check_cuda(x_full, ready, done, w_gate, w_up)
     tokens, hidden = x_full.shape
     inter = w_gate.shape[0]
     act = out if out is not None else torch.empty(tokens, inter, dtype=x_full.dtype, device=x_full.device)
+    gate = torch.empty_like(act) if want_cache else None
+    up = torch.empty_like(act) if want_cache else None
     world = len(peer_x_ptrs)
     arr = _ptr_array(peer_x_ptrs)
     with torch.cuda.device(x_full.device):
         check(lib().l32_tp_swiglu_forward_allgather(_ptr(x_full), arr, _ptr(ready), _ptr(done), int(epoch), int(rank), world,
-                                                    int(rows_per_rank), _ptr(w_gate), _ptr(w_up), None, None, _ptr(act), None,
-                                                    None, tokens, hidden, inter, _dtype_code(x_full), _stream(x_full)),
+                                                    int(rows_per_rank), _ptr(w_gate), _ptr(w_up), None, None, _ptr(act),
+                                                    _ptr(gate), _ptr(up), tokens, hidden, inter, _dtype_code(x_full),
+                                                    _stream(x_full)),
               "l32_tp_swiglu_forward_allgather")
-    return act
+    return (act, gate, up) if want_cache else act
+
+
+def tp_ffn_backward_dact_allgather(dy_full, peer_dy_ptrs, ready, done, epoch, rank, rows_per_rank, w_down, gate_cache,
+                                   up_cache, want_act=True):
+    """Fused all-gather of dY (pulled inside the GEMM) + d_act = dY w_down_shard + SiLU' epilogue.
+    Returns (d_gate, d_up, act|None), all [tokens, inter_local]."""
+    _check_cuda(dy_full, ready, done, w_down, gate_cache, up_cache)
+    tokens, hidden = dy_full.shape
+    inter = w_down.shape[1]
+    d_gate = torch.empty(tokens, inter, dtype=dy_full.dtype, device=dy_full.device)
+    d_up = torch.empty_like(d_gate)
+    act = torch.empty_like(d_gate) if want_act else None
+    arr = _ptr_array(peer_dy_ptrs)
+    with torch.cuda.device(dy_full.device):
+        check(lib().l32_tp_ffn_backward_dact_allgather(_ptr(dy_full), arr, _ptr(ready), _ptr(done), int(epoch), int(rank),
+                                                       len(peer_dy_ptrs), int(rows_per_rank), _ptr(w_down), _ptr(gate_cache),
+                                                       _ptr(up_cache), _ptr(d_gate), _ptr(d_up), _ptr(act), tokens, hidden,
+                                                       inter, _dtype_code(dy_full), _stream(dy_full)),
+              "l32_tp_ffn_backward_dact_allgather")
+    return d_gate, d_up, act
+
+
+def tp_ffn_backward_dx_reduce_scatter(d_gate, d_up, w_gate, w_up, peer_slot_ptrs, rank, rows_per_rank):
+    """Partial dX = d_gate w_gate_shard + d_up w_up_shard (two-phase GEMM) + reduce-scatter pushed from the epilogue."""
+    _check_cuda(d_gate, d_up, w_gate, w_up)
+    tokens, inter = d_gate.shape
+    hidden = w_gate.shape[1]
+    arr = _ptr_array(peer_slot_ptrs)
+    with torch.cuda.device(d_gate.device):
+        check(lib().l32_tp_ffn_backward_dx_reduce_scatter(_ptr(d_gate), _ptr(d_up), _ptr(w_gate), _ptr(w_up), arr, int(rank),
+                                                          len(peer_slot_ptrs), int(rows_per_rank), tokens, hidden, inter,
+                                                          _dtype_code(d_gate), _stream(d_gate)),
+              "l32_tp_ffn_backward_dx_reduce_scatter")
 
 
 def tp_linear_forward_reduce_scatter(a, weight, peer_slot_ptrs, rank, rows_per_rank):

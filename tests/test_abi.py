@@ -43,9 +43,9 @@ def test_header_cites_reference_interfaces():
 
 
 def test_version_and_error_strings(lib):
-    assert lib.l32_abi_version() == 2
+    assert lib.l32_abi_version() == 3
     assert lib.l32_error_string(0) == b"success"
-    for code in (-1, -2, -3, -4, -5, -6):
+    for code in (-1, -2, -3, -4, -5, -6, -7):
         assert len(lib.l32_error_string(code)) > 8
 
 

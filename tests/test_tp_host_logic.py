@@ -5,7 +5,7 @@ import torch
 from llama32_b200.tp import FusedTensorParallelBlock, TpRankBuffers, shard_ffn_weights, shard_range
 
 
-@pytest.mark.parametrize("inter,world", [(14336, 8), (28672, 8), (14336, 3), (688, 2), (1152, 3), (104, 4), (8, 2)])
+@pytest.mark.parametrize("inter,world", [(14336, 8), (28672, 8), (14336, 3), (688, 2), (1152, 3), (104, 4), (16, 2)])
 def test_shard_range_is_a_partition(inter, world):
     spans = [shard_range(inter, world, r) for r in range(world)]
     assert spans[0][0] == 0 and spans[-1][1] == inter
@@ -14,6 +14,24 @@ def test_shard_range_is_a_partition(inter, world):
     assert all((hi - lo) % 8 == 0 for lo, hi in spans[:-1])          # TMA row pitch / 16-byte stores
     if inter // 128 >= world:
         assert all(lo % 128 == 0 for lo, _ in spans)                  # shards start on an act tile of the tcgen05 kernel
+
+
+def test_shard_range_rejects_empty_shards():
+    """a rank that would own no columns is an error at shard time, not a shape failure inside the kernels."""
+    with pytest.raises(ValueError):
+        [shard_range(8, 2, r) for r in range(2)]
+    with pytest.raises(ValueError):
+        [shard_range(40, 8, r) for r in range(8)]
+
+
+def test_epoch_counter_lives_in_the_buffers():
+    class _T:   # stand-in for a device tensor: TpRankBuffers only reads shape / element_size / device here
+        def __init__(self, shape): self.shape = shape; self.device = "cpu"
+        def element_size(self): return 2
+    import llama32_b200.tp as tp
+    b = tp.TpRankBuffers(0, 2, 64, 32, _T((64, 32)), _T((2, 32, 32)), _T((64,)), [0, 0], [0, 4096], [0, 0])
+    assert [b.next_epoch() for _ in range(3)] == [1, 2, 3]
+    assert b.peer_slots == [0, 4096]          # rank 0 writes slot 0 of every owner
 
 
 def test_shard_ffn_weights_reassemble():
