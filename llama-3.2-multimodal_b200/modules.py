@@ -94,16 +94,22 @@ class SwiGLUFunction(torch.autograd.Function):
     never defined); bias gradients are returned when biases exist.
     """
 
+    @staticmethod
+    def _cuda_path(x, w_gate, w_up):
+        # sm_100a kernels only when activations AND weights share a 16-bit CUDA dtype; anything else (fp32 master weights
+        # under bf16 activations, CPU, fp32) evaluates the reference's F.linear expressions (FusedSwiglu.py:17-20)
+        return ops.supported(x) and w_gate.dtype == x.dtype and w_up.dtype == x.dtype and w_gate.is_cuda and w_up.is_cuda
+
     @classmethod
     def apply(cls, x, w_gate, w_up, b_gate=None, b_up=None):
-        if ops.supported(x) and not _wants_grad(x, w_gate, w_up, b_gate, b_up):
+        if cls._cuda_path(x, w_gate, w_up) and not _wants_grad(x, w_gate, w_up, b_gate, b_up):
             return ops.swiglu_forward(x, w_gate, w_up, b_gate, b_up, want_cache=False)[0]
         return super().apply(x, w_gate, w_up, b_gate, b_up)
 
     @staticmethod
     def forward(ctx, x, w_gate, w_up, b_gate=None, b_up=None):
         need_grad = any(ctx.needs_input_grad)
-        ctx.cuda_path = ops.supported(x)
+        ctx.cuda_path = SwiGLUFunction._cuda_path(x, w_gate, w_up)
         if not ctx.cuda_path:
             gate = F.linear(x, w_gate, b_gate)
             up = F.linear(x, w_up, b_up)
