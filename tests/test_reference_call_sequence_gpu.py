@@ -55,7 +55,6 @@ class _RefStyleRMSNorm(torch.autograd.Function):
         residual = residual.contiguous()
         output, rms = rmsnorm.forward(x, weight, residual, eps)
         ctx.save_for_backward(x, weight, rms)
-        ctx.residual_after = residual
         return output
 
     @staticmethod
@@ -65,7 +64,9 @@ class _RefStyleRMSNorm(torch.autograd.Function):
         d_x, d_weight = rmsnorm.backward(grad_output.contiguous(), x, weight, rms)
         if d_weight.dtype != weight.dtype:
             d_weight = d_weight.to(weight.dtype)
-        return d_x, d_weight, None, d_x
+        # the reference returns `d_x` for the residual slot unconditionally (Model/model.py:155); autograd rejects a gradient
+        # for a None input, so with residual=None (the only case replayed through backward) the slot must be None
+        return d_x, d_weight, None, (d_x if ctx.needs_input_grad[3] else None)
 
 
 class _RefStyleSwiGLU(torch.autograd.Function):
