@@ -88,6 +88,11 @@ L32_API size_t l32_rmsnorm_backward_workspace_bytes(int64_t rows, int hidden);
 L32_API int l32_rmsnorm_backward(const void* dy, const void* h, const void* weight, const float* rms, void* dx,
                          void* dweight, void* workspace, size_t workspace_bytes, int64_t rows, int hidden,
                          int dtype, void* stream);
+/* Same, with dx = (norm backward) + addend: `addend` [rows, hidden] is a gradient that reaches the same tensor around the
+ * norm -- the "+ attn_out" of the block tail (Model/model.py:273) -- added in the store pass instead of a separate kernel. */
+L32_API int l32_rmsnorm_backward_add(const void* dy, const void* h, const void* weight, const float* rms, const void* addend,
+                                     void* dx, void* dweight, void* workspace, size_t workspace_bytes, int64_t rows,
+                                     int hidden, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SwiGLU forward: act = silu(x w_gate^T + b_gate) * (x w_up^T + b_up)

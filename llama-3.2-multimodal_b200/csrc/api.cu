@@ -126,6 +126,13 @@ size_t l32_rmsnorm_backward_workspace_bytes(int64_t rows, int hidden) {
 
 int l32_rmsnorm_backward(const void* dy, const void* h, const void* weight, const float* rms, void* dx, void* dweight,
                          void* workspace, size_t workspace_bytes, int64_t rows, int hidden, int dtype, void* stream) {
+    return l32_rmsnorm_backward_add(dy, h, weight, rms, nullptr, dx, dweight, workspace, workspace_bytes, rows, hidden, dtype,
+                                    stream);
+}
+
+int l32_rmsnorm_backward_add(const void* dy, const void* h, const void* weight, const float* rms, const void* addend, void* dx,
+                             void* dweight, void* workspace, size_t workspace_bytes, int64_t rows, int hidden, int dtype,
+                             void* stream) {
     if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
     if (rows < 0 || hidden <= 0) return L32_ERR_BAD_SHAPE;
     if (dy == nullptr || h == nullptr || weight == nullptr || rms == nullptr || dx == nullptr) {
@@ -134,7 +141,7 @@ int l32_rmsnorm_backward(const void* dy, const void* h, const void* weight, cons
     if (rows > 0 && (workspace == nullptr || workspace_bytes < rmsnorm_bwd_workspace_bytes(rows, hidden) ||
                      !is_aligned16(workspace)))
         return L32_ERR_WORKSPACE;
-    return static_cast<int>(rmsnorm_bwd(dy, h, weight, rms, dx, dweight, static_cast<float*>(workspace), rows, hidden,
+    return static_cast<int>(rmsnorm_bwd(dy, h, weight, rms, addend, dx, dweight, static_cast<float*>(workspace), rows, hidden,
                                         dtype, as_stream(stream)));
 }
 

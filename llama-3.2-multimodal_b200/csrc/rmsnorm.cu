@@ -15,6 +15,8 @@
 //              deterministic).
 #include "l32_internal.cuh"
 
+#include <cstdlib>
+
 namespace l32 {
 
 template <typename T>
@@ -184,11 +186,10 @@ __global__ void __launch_bounds__(256) add_rmsnorm_fwd_generic_kernel(
 // ring stages; the row reduction is one shuffle tree + one named barrier per row.  d_weight is accumulated in
 // registers over all rows of the CTA and leaves as ONE fp32 partial row per CTA (deterministic, no atomics).
 // ------------------------------------------------------------------------------------------------
-constexpr int kBwdConsumers = 512;
-constexpr int kBwdThreads = kBwdConsumers + 32;
+constexpr int kBwdConsumersMax = 512;
 constexpr int kBwdMaxStages = 12;
 constexpr int kBwdBarrierBytes = 2 * kBwdMaxStages * 8;
-constexpr int kBwdRedBytes = 2 * 16 * 16 * 4;   // [parity][group][warp of the group]
+constexpr int kBwdRedBytes = 2 * 16 * 16 * 4 * 2;   // [parity][group][row of the iteration (<= 2)][warp of the group]
 
 L32_DEVICE void bulk_load_row(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile(
@@ -203,16 +204,19 @@ L32_DEVICE uint4 lds_v4(const void* p) {
     return r;
 }
 
-template <typename T, int RT, int VPT>
-__global__ void __launch_bounds__(kBwdThreads, 1) rmsnorm_bwd_kernel(
+template <typename T, int RT, int VPT, bool kAddend, int kBwdConsumers, int RPI>
+__global__ void __launch_bounds__(kBwdConsumers + 32, 1) rmsnorm_bwd_kernel(
     const T* __restrict__ dy, const T* __restrict__ h, const T* __restrict__ weight, const float* __restrict__ rms,
-    T* __restrict__ dx, float* __restrict__ dw_partial, int64_t rows, int C, int stages) {
+    const T* __restrict__ addend, T* __restrict__ dx, float* __restrict__ dw_partial, int64_t rows, int C, int stages) {
     constexpr int G = kBwdConsumers / RT;
+    constexpr int kBwdThreads = kBwdConsumers + 32;
+    static_assert(kBwdConsumers % RT == 0 && G >= 1 && G <= 14, "row groups");
     extern __shared__ __align__(128) uint8_t bwd_smem[];
     const uint32_t row_bytes = static_cast<uint32_t>(C) * sizeof(T);
     const uint32_t stage_bytes = 2 * row_bytes;
     uint8_t* ring = bwd_smem;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + static_cast<size_t>(stages) * stage_bytes);
+    uint8_t* w_sm = ring + static_cast<size_t>(stages) * stage_bytes;          // gamma, raw T (row_bytes)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(w_sm + row_bytes);
     uint64_t* empty_bar = full_bar + kBwdMaxStages;
     float* red = reinterpret_cast<float*>(empty_bar + kBwdMaxStages);
 
@@ -227,6 +231,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) rmsnorm_bwd_kernel(
         }
         fence_mbar_init();
     }
+    // gamma lives in shared memory (raw 16-bit): the registers it would take (VPT * 8 fp32) are what allows four vectors
+    // per thread, i.e. half as many threads per row and twice as many rows in flight per SM
+    for (int v = tid; v < nvec; v += kBwdThreads)
+        *reinterpret_cast<uint4*>(w_sm + static_cast<size_t>(v) * 16) = __ldg(reinterpret_cast<const uint4*>(weight) + v);
     __syncthreads();
     pdl_launch_dependents();   // the d_weight column reduce may be scheduled; it waits for this grid to finish
     pdl_wait_prior_grid();     // dy / h / rms come from earlier kernels of the stream; dx may still be read by them
@@ -251,73 +259,150 @@ __global__ void __launch_bounds__(kBwdThreads, 1) rmsnorm_bwd_kernel(
     // ---------------------------------------------------------------------- consumers
     // Per element (p = dy*h):  dot' += p*w;  dw += p*rstd;  dx = (dy*w)*rstd - h*c2,  c2 = rstd^3 * dot' / C
     // -- algebraically the formulas above with rstd factored out of the row sums, 6 fp32 ops per element.
+    // The row is latency-bound (wait -> reduce -> barrier -> store), so what counts is how many rows an SM has in flight:
+    // dy / h stay PACKED in registers between the two passes (unpacking is a shift), which leaves room for VPT = 4.
     const int g = tid / RT;
     const int t = tid % RT;
-    float w[VPT][8], dwacc[VPT][8];
+    constexpr bool kWRegs = (VPT <= 2);   // two vectors per thread: gamma fits into registers next to everything else
+    float dwacc[VPT][8], wreg[kWRegs ? VPT : 1][8];
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
-        const int v = t + i * RT;
-        uint4 wv = make_uint4(0, 0, 0, 0);
-        if (v < nvec) wv = __ldg(reinterpret_cast<const uint4*>(weight) + v);
-        unpack8<T>(wv, w[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) dwacc[i][j] = 0.f;
+        if constexpr (kWRegs) {
+            const int v = t + i * RT;
+            unpack8<T>(v < nvec ? lds_v4(w_sm + static_cast<size_t>(v) * 16) : make_uint4(0, 0, 0, 0), wreg[i]);
+        }
     }
     const float invC = 1.0f / static_cast<float>(C);
-    float rms_next = (g < n_local) ? rms[static_cast<int64_t>(g) * gridDim.x + blockIdx.x] : 1.f;
 
-    for (int64_t i = g; i < n_local; i += G) {
-        const int s = static_cast<int>(i % stages);
-        const uint32_t use = static_cast<uint32_t>(i / stages);
-        const int64_t row = i * gridDim.x + blockIdx.x;
-        const float rstd = __frcp_rn(rms_next);
-        if (i + G < n_local) rms_next = rms[(i + G) * gridDim.x + blockIdx.x];   // prefetch for the next turn
-        mbar_wait(&full_bar[s], use & 1u);
-        const uint8_t* src = ring + static_cast<size_t>(s) * stage_bytes;
-        float gg[VPT][8], hh[VPT][8];
+    // One iteration of a row group handles RPI rows (i, i + G, ...): their wait -> reduce -> barrier -> store chains are
+    // independent, so the warp interleaves them (twice the rows in flight for VPT * 8 more registers per extra row).
+    float rms_next[RPI];
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+        const int64_t i = g + static_cast<int64_t>(r) * G;
+        rms_next[r] = (i < n_local) ? rms[i * gridDim.x + blockIdx.x] : 1.f;
+    }
+    for (int64_t i0 = g; i0 < n_local; i0 += static_cast<int64_t>(G) * RPI) {
+        uint4 graw[RPI][VPT], hraw[RPI][VPT];
+        float rstd[RPI], dot[RPI];
+        size_t base[RPI];
+        bool live[RPI];
+#pragma unroll
+        for (int r = 0; r < RPI; ++r) {
+            const int64_t i = i0 + static_cast<int64_t>(r) * G;
+            live[r] = i < n_local;
+            const int64_t row = (live[r] ? i : i0) * gridDim.x + blockIdx.x;
+            base[r] = static_cast<size_t>(row) * C;
+            rstd[r] = __frcp_rn(rms_next[r]);
+            const int64_t inext = i + static_cast<int64_t>(G) * RPI;   // prefetch for the next turn (a global load per row
+            if (inext < n_local) rms_next[r] = rms[inext * gridDim.x + blockIdx.x];   // must not sit in the row's chain)
+        }
+        uint4 av[kAddend ? RPI : 1][kAddend ? VPT : 1];
+        if constexpr (kAddend) {
+#pragma unroll
+            for (int r = 0; r < RPI; ++r)
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {
+                    const int v = t + k * RT;
+                    av[r][k] = make_uint4(0, 0, 0, 0);
+                    if (v < nvec && live[r]) av[r][k] = ld_stream_v4(addend + base[r] + (size_t)v * 8);
+                }
+        }
+#pragma unroll
+        for (int r = 0; r < RPI; ++r) {
+            const int64_t i = i0 + static_cast<int64_t>(r) * G;
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) {
+                graw[r][k] = make_uint4(0, 0, 0, 0);
+                hraw[r][k] = make_uint4(0, 0, 0, 0);
+            }
+            if (live[r]) {
+                const int s = static_cast<int>(i % stages);
+                const uint32_t use = static_cast<uint32_t>(i / stages);
+                mbar_wait(&full_bar[s], use & 1u);
+                const uint8_t* src = ring + static_cast<size_t>(s) * stage_bytes;
+#pragma unroll
+                for (int k = 0; k < VPT; ++k) {
+                    const int v = t + k * RT;
+                    if (v < nvec) {
+                        graw[r][k] = lds_v4(src + static_cast<size_t>(v) * 16);
+                        hraw[r][k] = lds_v4(src + row_bytes + static_cast<size_t>(v) * 16);
+                    }
+                }
+                __syncwarp();
+                if ((t & 31) == 0) mbar_arrive(&empty_bar[s]);   // stage may be refilled
+            }
+            dot[r] = 0.f;
+        }
 #pragma unroll
         for (int k = 0; k < VPT; ++k) {
             const int v = t + k * RT;
-            uint4 gv = make_uint4(0, 0, 0, 0), hv = make_uint4(0, 0, 0, 0);
-            if (v < nvec) {
-                gv = lds_v4(src + static_cast<size_t>(v) * 16);
-                hv = lds_v4(src + row_bytes + static_cast<size_t>(v) * 16);
-            }
-            unpack8<T>(gv, gg[k]);
-            unpack8<T>(hv, hh[k]);
-        }
-        __syncwarp();
-        if ((t & 31) == 0) mbar_arrive(&empty_bar[s]);   // stage may be refilled
-
-        float dot = 0.f;
+            float w[8];
+            if constexpr (kWRegs) {
 #pragma unroll
-        for (int k = 0; k < VPT; ++k) {
+                for (int j = 0; j < 8; ++j) w[j] = wreg[k][j];
+            } else {
+                unpack8<T>(v < nvec ? lds_v4(w_sm + static_cast<size_t>(v) * 16) : make_uint4(0, 0, 0, 0), w);
+            }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float pr = gg[k][j] * hh[k][j];
-                dot = fmaf(pr, w[k][j], dot);
-                dwacc[k][j] = fmaf(pr, rstd, dwacc[k][j]);
+            for (int r = 0; r < RPI; ++r) {
+                float gg[8], hh[8];
+                unpack8<T>(graw[r][k], gg);
+                unpack8<T>(hraw[r][k], hh);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float pr = gg[j] * hh[j];
+                    dot[r] = fmaf(pr, w[j], dot[r]);
+                    dwacc[k][j] = fmaf(pr, rstd[r], dwacc[k][j]);   // a dead row contributes zeros (graw = hraw = 0)
+                }
             }
         }
-        dot = warp_sum(dot);
+#pragma unroll
+        for (int r = 0; r < RPI; ++r) dot[r] = warp_sum(dot[r]);
         if constexpr (RT > 32) {
-            float* slot = red + ((static_cast<int>(i / G) & 1) * 16 + g) * 16;   // double-buffered: one barrier per row
-            if ((t & 31) == 0) slot[t >> 5] = dot;
+            // double-buffered: one barrier per iteration
+            float* slot = red + ((static_cast<int>(i0 / (G * RPI)) & 1) * 16 + g) * (16 * RPI);
+            if ((t & 31) == 0) {
+#pragma unroll
+                for (int r = 0; r < RPI; ++r) slot[r * 16 + (t >> 5)] = dot[r];
+            }
             named_bar_sync(1 + g, RT);
-            dot = 0.f;
 #pragma unroll
-            for (int k = 0; k < RT / 32; ++k) dot += slot[k];
+            for (int r = 0; r < RPI; ++r) {
+                dot[r] = 0.f;
+#pragma unroll
+                for (int k = 0; k < RT / 32; ++k) dot[r] += slot[r * 16 + k];
+            }
         }
-        const float c2 = dot * invC * rstd * rstd * rstd;
-        const size_t base = static_cast<size_t>(row) * C;
 #pragma unroll
-        for (int k = 0; k < VPT; ++k) {
-            const int v = t + k * RT;
-            if (v < nvec) {
-                float o[8];
+        for (int r = 0; r < RPI; ++r) {
+            if (!live[r]) continue;
+            const float c2 = dot[r] * invC * rstd[r] * rstd[r] * rstd[r];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = fmaf(-hh[k][j], c2, gg[k][j] * w[k][j] * rstd);
-                st_v4(dx + base + (size_t)v * 8, pack8<T>(o));
+            for (int k = 0; k < VPT; ++k) {
+                const int v = t + k * RT;
+                if (v < nvec) {
+                    float gg[8], hh[8], w[8], o[8];
+                    unpack8<T>(graw[r][k], gg);
+                    unpack8<T>(hraw[r][k], hh);
+                    if constexpr (kWRegs) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) w[j] = wreg[k][j];
+                    } else {
+                        unpack8<T>(lds_v4(w_sm + static_cast<size_t>(v) * 16), w);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] = fmaf(-hh[j], c2, gg[j] * w[j] * rstd[r]);
+                    if constexpr (kAddend) {   // dx += addend (a gradient that bypasses the norm, e.g. the block tail's "+ attn_out")
+                        float ad[8];
+                        unpack8<T>(av[r][k], ad);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] += ad[j];
+                    }
+                    st_v4(dx + base[r] + (size_t)v * 8, pack8<T>(o));
+                }
             }
         }
     }
@@ -367,7 +452,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) rmsnorm_bwd_kernel(
 // dw partial per CTA accumulated in global memory owned by that CTA (no atomics).
 template <typename T>
 __global__ void __launch_bounds__(256) rmsnorm_bwd_generic_kernel(
-    const T* dy, const T* h, const T* weight, const float* rms, T* dx, float* dw_partial, int64_t rows, int C) {
+    const T* dy, const T* h, const T* weight, const float* rms, const T* addend, T* dx, float* dw_partial, int64_t rows,
+    int C) {
     __shared__ float red[8];
     float* my_dw = dw_partial + (size_t)blockIdx.x * C;
     for (int i = threadIdx.x; i < C; i += 256) my_dw[i] = 0.f;
@@ -387,7 +473,9 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_generic_kernel(
         for (int i = threadIdx.x; i < C; i += 256) {
             const float gg = static_cast<float>(dy[base + i]);
             const float xh = static_cast<float>(h[base + i]) * rstd;
-            dx[base + i] = static_cast<T>((gg * static_cast<float>(weight[i]) - xh * c1) * rstd);
+            float o = (gg * static_cast<float>(weight[i]) - xh * c1) * rstd;
+            if (addend != nullptr) o += static_cast<float>(addend[base + i]);
+            dx[base + i] = static_cast<T>(o);
         }
         __syncthreads();
     }
@@ -477,16 +565,20 @@ static int bwd_grid(int64_t rows) {
     return static_cast<int>(rows < cap ? (rows < 1 ? 1 : rows) : cap);
 }
 
-template <typename T, int RT, int VPT>
-static cudaError_t launch_bwd_fast(const T* dy, const T* h, const T* weight, const float* rms, T* dx, float* partial,
-                                   int64_t rows, int C, int grid, cudaStream_t s) {
+template <typename T, int RT, int VPT, bool kAddend, int kBwdConsumers, int RPI>
+static cudaError_t launch_bwd_fast(const T* dy, const T* h, const T* weight, const float* rms, const T* addend, T* dx,
+                                   float* partial, int64_t rows, int C, int grid, cudaStream_t s) {
     constexpr int G = kBwdConsumers / RT;
-    const size_t stage_bytes = 2 * static_cast<size_t>(C) * sizeof(T);
-    int stages = static_cast<int>((200 * 1024) / stage_bytes);
+    const size_t row_bytes = static_cast<size_t>(C) * sizeof(T);
+    const size_t stage_bytes = 2 * row_bytes;
+    int stages = static_cast<int>((200 * 1024 - row_bytes) / stage_bytes);
     if (stages > kBwdMaxStages) stages = kBwdMaxStages;
-    if (stages < 2 || stages < G - 1) return cudaErrorInvalidConfiguration;   // the d_weight fold reuses the ring
-    const size_t smem = stages * stage_bytes + kBwdBarrierBytes + kBwdRedBytes;
-    auto* k = rmsnorm_bwd_kernel<T, RT, VPT>;
+    // the d_weight fold reuses the ring: (G - 1) fp32 rows must fit into it
+    if (stages < 2 || static_cast<size_t>(stages) * stage_bytes < static_cast<size_t>(G - 1) * C * sizeof(float))
+        return cudaErrorInvalidConfiguration;
+    const size_t smem = stages * stage_bytes + row_bytes + kBwdBarrierBytes + kBwdRedBytes;
+    static_assert(RPI >= 1 && RPI <= 2, "rows per iteration");
+    auto* k = rmsnorm_bwd_kernel<T, RT, VPT, kAddend, kBwdConsumers, RPI>;
     static bool configured_dev[kMaxDevices] = {};   // per instantiation and device
     bool& configured = configured_dev[current_device_slot()];
     if (!configured) {
@@ -496,7 +588,7 @@ static cudaError_t launch_bwd_fast(const T* dy, const T* h, const T* weight, con
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(kBwdThreads);
+    cfg.blockDim = dim3(kBwdConsumers + 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -504,7 +596,7 @@ static cudaError_t launch_bwd_fast(const T* dy, const T* h, const T* weight, con
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k, dy, h, weight, rms, dx, partial, rows, C, stages);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, dy, h, weight, rms, addend, dx, partial, rows, C, stages);
     if (e == cudaSuccess) count_launch();
     return e;
 }
@@ -515,26 +607,43 @@ size_t rmsnorm_bwd_workspace_bytes(int64_t rows, int C) {
     return static_cast<size_t>(num_sms()) * 2 * static_cast<size_t>(C) * sizeof(float);
 }
 
+template <typename T, int RT, int VPT, int NC = kBwdConsumersMax, int RPI = 1>
+static cudaError_t launch_bwd_sel(const T* dy, const T* h, const T* weight, const float* rms, const T* addend, T* dx,
+                                  float* partial, int64_t rows, int C, int grid, cudaStream_t s) {
+    if (addend != nullptr) return launch_bwd_fast<T, RT, VPT, true, NC, RPI>(dy, h, weight, rms, addend, dx, partial, rows, C, grid, s);
+    return launch_bwd_fast<T, RT, VPT, false, NC, RPI>(dy, h, weight, rms, addend, dx, partial, rows, C, grid, s);
+}
+
 template <typename T>
-static cudaError_t rmsnorm_bwd_t(const T* dy, const T* h, const T* weight, const float* rms, T* dx, T* dw,
+static cudaError_t rmsnorm_bwd_t(const T* dy, const T* h, const T* weight, const float* rms, const T* addend, T* dx, T* dw,
                                  float* workspace, int64_t rows, int C, cudaStream_t s) {
     if (rows == 0) {
         if (dw != nullptr) return cudaMemsetAsync(dw, 0, sizeof(T) * C, s);
         return cudaSuccess;
     }
-    const bool aligned = (C % 8 == 0) && is_aligned16(dy) && is_aligned16(h) && is_aligned16(weight) && is_aligned16(dx);
+    const bool aligned = (C % 8 == 0) && is_aligned16(dy) && is_aligned16(h) && is_aligned16(weight) && is_aligned16(dx) &&
+                         is_aligned16(addend);
     int grid;
     cudaError_t e;
     if (aligned && C <= 16384) {
         grid = bwd_grid(rows);
-        if (C <= 64 * 2 * 8) e = launch_bwd_fast<T, 64, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s);
-        else if (C <= 128 * 2 * 8) e = launch_bwd_fast<T, 128, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s);
-        else if (C <= 256 * 2 * 8) e = launch_bwd_fast<T, 256, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s);
-        else if (C <= 512 * 2 * 8) e = launch_bwd_fast<T, 512, 2>(dy, h, weight, rms, dx, workspace, rows, C, grid, s);
-        else e = launch_bwd_fast<T, 512, 4>(dy, h, weight, rms, dx, workspace, rows, C, grid, s);
+        // threads per row (RT) x 16-byte vectors per thread (VPT): as few threads per row as the registers allow, so that
+        // 512 / RT rows are in flight per SM (the per-row wait -> reduce -> barrier -> store chain is latency-bound)
+        static const int variant = [] { const char* v = getenv("L32_RMSBWD_VARIANT"); return v ? atoi(v) : 0; }();   // tuning knob
+        if (C <= 64 * 2 * 8) e = launch_bwd_sel<T, 64, 2>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
+        else if (C <= 128 * 2 * 8) e = launch_bwd_sel<T, 128, 2>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
+        else if (C <= 128 * 4 * 8) {
+            if (variant == 1) e = launch_bwd_sel<T, 128, 4, 256, 2>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
+            else if (variant == 2) e = launch_bwd_sel<T, 256, 2, 512, 2>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
+            else e = launch_bwd_sel<T, 128, 4, 384, 1>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
+        } else if (C <= 256 * 4 * 8) {
+            if (variant == 1) e = launch_bwd_sel<T, 256, 4, 256, 1>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
+            else if (variant == 2) e = launch_bwd_sel<T, 384, 3, 384, 1>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
+            else e = launch_bwd_sel<T, 512, 2, 512, 1>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
+        } else e = launch_bwd_sel<T, 512, 4, 512, 1>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
     } else {
         grid = 2 * bwd_grid(rows);
-        rmsnorm_bwd_generic_kernel<T><<<grid, 256, 0, s>>>(dy, h, weight, rms, dx, workspace, rows, C);
+        rmsnorm_bwd_generic_kernel<T><<<grid, 256, 0, s>>>(dy, h, weight, rms, addend, dx, workspace, rows, C);
         count_launch();
         e = cudaGetLastError();
     }
@@ -565,13 +674,14 @@ cudaError_t add_rmsnorm_fwd(const void* x, const void* residual, const void* wei
                                      (__half*)h_out, rms, rows, C, eps, s);
 }
 
-cudaError_t rmsnorm_bwd(const void* dy, const void* h, const void* weight, const float* rms, void* dx, void* dw,
-                        float* workspace, int64_t rows, int C, int dtype, cudaStream_t s) {
+cudaError_t rmsnorm_bwd(const void* dy, const void* h, const void* weight, const float* rms, const void* addend, void* dx,
+                        void* dw, float* workspace, int64_t rows, int C, int dtype, cudaStream_t s) {
     if (dtype == L32_BF16)
         return rmsnorm_bwd_t<__nv_bfloat16>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (const __nv_bfloat16*)weight, rms,
-                                            (__nv_bfloat16*)dx, (__nv_bfloat16*)dw, workspace, rows, C, s);
-    return rmsnorm_bwd_t<__half>((const __half*)dy, (const __half*)h, (const __half*)weight, rms, (__half*)dx, (__half*)dw,
-                                 workspace, rows, C, s);
+                                            (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, (__nv_bfloat16*)dw, workspace, rows,
+                                            C, s);
+    return rmsnorm_bwd_t<__half>((const __half*)dy, (const __half*)h, (const __half*)weight, rms, (const __half*)addend,
+                                 (__half*)dx, (__half*)dw, workspace, rows, C, s);
 }
 
 }  // namespace l32

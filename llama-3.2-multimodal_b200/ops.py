@@ -104,9 +104,10 @@ def add_rmsnorm_forward(x, weight, residual=None, eps=1e-5, *, want_h=False, wan
     return y.view(x.shape), rms, (h.view(x.shape) if h is not None else None)
 
 
-def rmsnorm_backward(grad_out, h, weight, rms, *, want_dweight=True):
-    """(dx, dweight|None) for y = rmsnorm(h) * weight, given rms = sqrt(mean(h^2) + eps) from the forward."""
-    _check_cuda(grad_out, h, weight, rms)
+def rmsnorm_backward(grad_out, h, weight, rms, *, want_dweight=True, addend=None):
+    """(dx, dweight|None) for y = rmsnorm(h) * weight, given rms = sqrt(mean(h^2) + eps) from the forward.
+    `addend` (shaped like h): dx = (norm backward) + addend, added in the kernel's store pass."""
+    _check_cuda(grad_out, h, weight, rms, addend)
     hidden = h.shape[-1]
     hc = h.contiguous()
     gc = grad_out.contiguous()
@@ -119,9 +120,15 @@ def rmsnorm_backward(grad_out, h, weight, rms, *, want_dweight=True):
     L = lib()
     ws_bytes = L.l32_rmsnorm_backward_workspace_bytes(rows, hidden)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=hc.device)
+    ad = None
+    if addend is not None:
+        ad = addend.contiguous()
+        if ad.shape != hc.shape or ad.dtype != hc.dtype:
+            raise L32Error("rmsnorm_backward: `addend` must be shaped and typed like h")
     with torch.cuda.device(hc.device):
-        check(L.l32_rmsnorm_backward(_ptr(gc), _ptr(hc), _ptr(w), _ptr(rms.contiguous()), _ptr(dx), _ptr(dw), _ptr(ws),
-                                     ws_bytes, rows, hidden, _dtype_code(hc), _stream(hc)), "l32_rmsnorm_backward")
+        check(L.l32_rmsnorm_backward_add(_ptr(gc), _ptr(hc), _ptr(w), _ptr(rms.contiguous()), _ptr(ad), _ptr(dx), _ptr(dw),
+                                         _ptr(ws), ws_bytes, rows, hidden, _dtype_code(hc), _stream(hc)),
+              "l32_rmsnorm_backward_add")
     return dx.view(h.shape), dw
 
 
