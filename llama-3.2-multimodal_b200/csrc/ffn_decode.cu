@@ -411,6 +411,7 @@ int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0
     int splits = 1;
     while (splits < 8 && row_blocks * splits < sms && nkb / (splits * 2) >= 4) splits *= 2;
     if (const int v = env_int("L32_DECODE_SPLITS", 0)) splits = v;
+    if (const int v = env_int(kEpi == DEC_SWIGLU ? "L32_DECODE_SPLITS_SWIGLU" : "L32_DECODE_SPLITS_LINEAR", 0)) splits = v;
     if (splits < 1 || splits > 8 || (splits & (splits - 1)) != 0 || splits > nkb) return L32_ERR_BAD_SHAPE;
     p.splits = splits;
     p.rotate = env_int("L32_DECODE_ROTATE", 1);
