@@ -28,6 +28,7 @@
 // (dgrad through W^T, wgrad through X^T) without any explicit transpose.
 #include "l32_internal.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -82,6 +83,8 @@ struct GemmKernelParams {
     int ffn_prefix;         // gate/up-only tiles at the head of every mixed round
     uint32_t idesc_dn;
     uint32_t* act_done;
+    int debug_flags;          // experiments only (L32_BWD_DEBUG): 1 = skip the output stores, 2 = skip the cache loads
+    CUtensorMap map_out[3];   // EPI_SWIGLU_BWD: d_gate / d_up / act as [m, n] tensors, box {16 cols, 32 rows}, 32-byte swizzle
     unsigned long long spin_timeout_ns;   // bound of every cross-SM / cross-GPU flag wait
 };
 
@@ -104,6 +107,13 @@ L32_DEVICE void load_tile(const CUtensorMap* map, uint8_t* dst, uint64_t* full_b
 
 L32_DEVICE void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// streaming read (read once, never again): do not keep it in L1, first to leave L2
+L32_DEVICE uint4 ld_global_stream_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
 }
 L32_DEVICE uint4 ld_global_nc_v4(const void* p) {
     uint4 r;
@@ -292,6 +302,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         tma_prefetch_desc(&p.map_b[0]);
         if (p.num_phases == 2) tma_prefetch_desc(&p.map_a[1]);
         if (p.num_phases == 2 || kEpi == EPI_SWIGLU || kTp) tma_prefetch_desc(&p.map_b[1]);
+        if constexpr (kEpi == EPI_SWIGLU_BWD) {
+            tma_prefetch_desc(&p.map_out[0]);
+            tma_prefetch_desc(&p.map_out[1]);
+            if (p.d[2] != nullptr) tma_prefetch_desc(&p.map_out[2]);
+        }
         if constexpr (kTp) {
             tma_prefetch_desc(&p.map_a_dn);
             tma_prefetch_desc(&p.map_b_dn);
@@ -442,6 +457,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const int n0 = tc.n_blk * (dn ? kAccCols : kTileNOut);
             const bool row_ok = row < p.m;
             const size_t row_off = static_cast<size_t>(row_ok ? row : 0) * tile_ldd;
+            // EPI_SWIGLU_BWD: the gate / up cache rows of step c + 2 (this warp's next step) are requested before step c is
+            // computed, the first ones before the accumulator is even complete (they do not depend on it)
+            auto load_gu = [&](int c, uint4 (&gq)[2], uint4 (&uq)[2]) {
+                const int col = n0 + c * 16;
+                const int nv = (row_ok && c < kAccCols / 16 && !(p.debug_flags & 2)) ? (p.n - col) : 0;
+                const uint8_t* gsrc = static_cast<const uint8_t*>(p.e[0]) + (row_off + col) * esz;
+                const uint8_t* usrc = static_cast<const uint8_t*>(p.e[1]) + (row_off + col) * esz;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    gq[j] = make_uint4(0, 0, 0, 0);
+                    uq[j] = make_uint4(0, 0, 0, 0);
+                    if (j * 8 < nv) {
+                        if (p.debug_flags & 8) {
+                            gq[j] = ld_global_nc_v4(gsrc + j * 16);
+                            uq[j] = ld_global_nc_v4(usrc + j * 16);
+                        } else {
+                            gq[j] = ld_global_stream_v4(gsrc + j * 16);
+                            uq[j] = ld_global_stream_v4(usrc + j * 16);
+                        }
+                    }
+                }
+            };
+            uint4 gq[2], uq[2], gn[2], un[2];
+            if constexpr (kEpi == EPI_SWIGLU_BWD) load_gu(static_cast<int>(eg), gq, uq);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * kAccCols;
@@ -565,20 +604,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     finish(g, u, n0 + c0, std::integral_constant<int, 16>{});
                 }
             } else if constexpr (kEpi == EPI_SWIGLU_BWD) {
+                // Five [M, I] tensors pass through this epilogue.  The three outputs leave through shared memory and TMA
+                // tensor stores (one 32-row x 16-column box per tensor per step: full 32-byte sectors, three requests
+                // instead of 96 per-lane 16-byte stores to 32 different rows); TMA clips the ragged edges.  The staging
+                // rows use the 32-byte swizzle of the tensor map (16-byte chunk index ^= bit 2 of the row), which also
+                // makes the lanes' st.shared conflict-free.
+                uint8_t* stg = epi_stage + (warp - 4) * (3 * 1024);
+                const int row0 = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM + q * 32;
+                const uint32_t sw = (lane >> 2) & 1u;
+                uint8_t* my = stg + lane * 32;
 #pragma unroll 1
-                for (int c = static_cast<int>(eg); c < kAccCols / 32; c += 2) {
-                    const int col = n0 + c * 32;
+                for (int c = static_cast<int>(eg); c < kAccCols / 16; c += 2) {
+                    const int col = n0 + c * 16;
                     if (col >= p.n) break;
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(taddr + c * 32, v);
-                    uint32_t gp[16], up[16];
-                    const int nv = row_ok ? (p.n - col) : 0;
-                    load_row32(static_cast<const uint8_t*>(p.e[0]) + (row_off + col) * esz, gp, nv);
-                    load_row32(static_cast<const uint8_t*>(p.e[1]) + (row_off + col) * esz, up, nv);
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(taddr + c * 16, v);
+                    load_gu(c + 2, gn, un);
                     tmem_ld_wait();
-                    uint32_t odg[16], odu[16], oact[16];
+                    const uint32_t gp[8] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w};
+                    const uint32_t up[8] = {uq[0].x, uq[0].y, uq[0].z, uq[0].w, uq[1].x, uq[1].y, uq[1].z, uq[1].w};
+                    uint32_t odg[8], odu[8], oact[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
+                    for (int j = 0; j < 8; ++j) {
                         const float2 g = Pack2<T>::unpack(gp[j]);
                         const float2 u = Pack2<T>::unpack(up[j]);
                         const float da0 = __uint_as_float(v[2 * j]), da1 = __uint_as_float(v[2 * j + 1]);
@@ -590,12 +637,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                         odu[j] = Pack2<T>::pack(da0 * silu0, da1 * silu1);
                         oact[j] = Pack2<T>::pack(silu0 * u.x, silu1 * u.y);
                     }
-                    if (row_ok) {
-                        store_row32(static_cast<uint8_t*>(p.d[0]) + (row_off + col) * esz, odg, p.n - col);
-                        store_row32(static_cast<uint8_t*>(p.d[1]) + (row_off + col) * esz, odu, p.n - col);
-                        if (p.d[2] != nullptr)
-                            store_row32(static_cast<uint8_t*>(p.d[2]) + (row_off + col) * esz, oact, p.n - col);
+                    if (lane == 0) bulk_store_wait_read();   // the previous step's tensor stores have read the staging rows
+                    __syncwarp();
+                    st_shared_v4(my + ((0u ^ sw) << 4), odg[0], odg[1], odg[2], odg[3]);
+                    st_shared_v4(my + ((1u ^ sw) << 4), odg[4], odg[5], odg[6], odg[7]);
+                    st_shared_v4(my + 1024 + ((0u ^ sw) << 4), odu[0], odu[1], odu[2], odu[3]);
+                    st_shared_v4(my + 1024 + ((1u ^ sw) << 4), odu[4], odu[5], odu[6], odu[7]);
+                    if (p.d[2] != nullptr) {
+                        st_shared_v4(my + 2048 + ((0u ^ sw) << 4), oact[0], oact[1], oact[2], oact[3]);
+                        st_shared_v4(my + 2048 + ((1u ^ sw) << 4), oact[4], oact[5], oact[6], oact[7]);
                     }
+                    fence_proxy_async_smem();   // generic-proxy st.shared -> async-proxy tensor store
+                    __syncwarp();
+                    if (lane == 0 && row0 < p.m && !(p.debug_flags & 1)) {
+                        const uint64_t hint = (p.debug_flags & 4) ? kEvictNormal : kEvictFirst;
+                        tma_store_2d_hint(&p.map_out[0], stg, col, row0, hint);
+                        tma_store_2d_hint(&p.map_out[1], stg + 1024, col, row0, hint);
+                        if (p.d[2] != nullptr) tma_store_2d_hint(&p.map_out[2], stg + 2048, col, row0, hint);
+                        tma_store_commit();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) { gq[j] = gn[j]; uq[j] = un[j]; }
                 }
             }
             // accumulator stage drained: hand it back to the MMA issuer of the leader CTA
@@ -618,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             acc ^= 1u;
             if (acc == 0) acc_phase ^= 1u;
         }
-        if (kEpi == EPI_STORE || kTp) bulk_store_wait_read();   // shared memory must outlive the last bulk stores
+        if (kEpi == EPI_STORE || kEpi == EPI_SWIGLU_BWD || kTp) bulk_store_wait_read();   // shared memory must outlive the last bulk stores
     }
 
     __syncwarp();
@@ -734,17 +796,38 @@ int num_sms() {
 
 int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                        uint32_t box_rows, uint32_t box_cols, int dtype) {
+    return make_tensor_map_2d_sw(map, ptr, rows, cols, ld_elems, box_rows, box_cols, dtype, 128);
+}
+
+// swizzle_bytes: 128 (box_cols = 64), 64 (box_cols = 32) or 32 (box_cols = 16) -- the box row is exactly one swizzle span
+int make_tensor_map_2d_sw(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                          uint32_t box_rows, uint32_t box_cols, int dtype, int swizzle_bytes) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (fn == nullptr) return L32_ERR_DRIVER;
     if (!is_aligned16(ptr) || (ld_elems % 8) != 0) return L32_ERR_BAD_ALIGN;
-    if (box_rows == 0 || box_rows > 256 || box_cols != 64) return L32_ERR_BAD_SHAPE;
+    if (box_rows == 0 || box_rows > 256 || static_cast<int>(box_cols) * 2 != swizzle_bytes) return L32_ERR_BAD_SHAPE;
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (sw == CU_TENSOR_MAP_SWIZZLE_NONE) return L32_ERR_BAD_SHAPE;
     const cuuint64_t gdim[2] = {cols, rows};
     const cuuint64_t gstride[1] = {ld_elems * 2};
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estride[2] = {1, 1};
     const CUtensorMapDataType dt = (dtype == L32_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+        // A thread that has not touched the runtime yet (e.g. autograd's backward thread calling this library first) has no
+        // current driver context although the process has a primary one: bind it through the runtime and retry once.
+        if (cudaFree(nullptr) == cudaSuccess)
+            r = fn(map, dt, 2, const_cast<void*>(ptr), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS && getenv("L32_DEBUG") != nullptr)
+        fprintf(stderr, "[l32] cuTensorMapEncodeTiled failed (%d): ptr %p rows %llu cols %llu ld %llu box %u x %u swizzle %d\n",
+                static_cast<int>(r), ptr, static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols),
+                static_cast<unsigned long long>(ld_elems), box_rows, box_cols, swizzle_bytes);
     return r == CUDA_SUCCESS ? L32_OK : L32_ERR_DRIVER;
 }
 
@@ -845,6 +928,7 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
     }
     kp.ag = g.ag;
     kp.spin_timeout_ns = spin_timeout_ns();
+    if (const char* env = getenv("L32_BWD_DEBUG")) kp.debug_flags = atoi(env);
     kp.rs = g.rs;
     if (g.ag.world > kMaxTpWorld || g.rs.world > kMaxTpWorld) return L32_ERR_BAD_SHAPE;
     if (g.ag.world > 1) {
@@ -874,6 +958,13 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
     if (swiglu_like) {
         for (int i = 0; i < 2; ++i) {
             int rc = make_tensor_map_2d(&kp.map_b[i], g.b[i].ptr, g.n, g.k[0], g.b[i].ld, n_act, kBlockK, g.dtype);
+            if (rc != L32_OK) return rc;
+        }
+    }
+    if (g.epilogue == EPI_SWIGLU_BWD) {
+        for (int i = 0; i < 3; ++i) {
+            if (g.d[i] == nullptr) continue;
+            int rc = make_tensor_map_2d_sw(&kp.map_out[i], g.d[i], g.m, g.n, g.ldd, 32, 16, g.dtype, 32);
             if (rc != L32_OK) return rc;
         }
     }

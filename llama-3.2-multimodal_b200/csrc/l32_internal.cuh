@@ -128,5 +128,7 @@ cudaError_t tp_reduce_partials(const void* slots, const uint32_t* flags, uint32_
 // ---- tensor-map helper (gemm_sm100.cu): 2-D row-major [rows, cols] 16-bit tensor, 128-byte swizzled box
 int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                        uint32_t box_rows, uint32_t box_cols, int dtype);
+int make_tensor_map_2d_sw(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                          uint32_t box_rows, uint32_t box_cols, int dtype, int swizzle_bytes);
 
 }  // namespace l32

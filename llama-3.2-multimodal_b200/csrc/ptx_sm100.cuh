@@ -200,6 +200,12 @@ L32_DEVICE void tma_store_2d(const CUtensorMap* map, const void* smem_src, int32
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// The same with an L2 eviction-priority hint (kEvictFirst for streaming outputs that nobody re-reads soon).
+L32_DEVICE void tma_store_2d_hint(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1, uint64_t hint) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(map),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(hint)
+                 : "memory");
+}
 L32_DEVICE void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 L32_DEVICE void tma_store_wait_read() {
