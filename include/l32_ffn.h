@@ -53,7 +53,8 @@ extern "C" {
 #define L32_ERR_NOT_RESIDENT (-7)
 
 /* ABI version of this header (bumped on any signature change).  2: tensor-parallel, LoRA and block-tail entry points.
- * 3: tensor-parallel backward; the all-gather entry points accept an A buffer distinct from the published one. */
+ * 3: tensor-parallel backward; the all-gather entry points accept an A buffer distinct from the published one;
+ *    l32_rmsnorm_backward_add, l32_block_tail_forward_ex, l32_linear_lora_forward / _backward. */
 L32_API int l32_abi_version(void);
 /* Number of CUDA kernels this library has launched in the calling process so far (monotonic). */
 L32_API unsigned long long l32_kernel_launch_count(void);
@@ -89,10 +90,12 @@ L32_API int l32_rmsnorm_backward(const void* dy, const void* h, const void* weig
                          void* dweight, void* workspace, size_t workspace_bytes, int64_t rows, int hidden,
                          int dtype, void* stream);
 /* Same, with dx = (norm backward) + addend: `addend` [rows, hidden] is a gradient that reaches the same tensor around the
- * norm -- the "+ attn_out" of the block tail (Model/model.py:273) -- added in the store pass instead of a separate kernel. */
+ * norm -- the "+ attn_out" of the block tail (Model/model.py:273) -- added in the store pass instead of a separate kernel.
+ *   dx_plain : optional [rows, hidden]; receives the norm backward WITHOUT the addend (the residual's gradient when the
+ *              residual and the normalised input's other summand need different gradients, Model/model.py:271-273). */
 L32_API int l32_rmsnorm_backward_add(const void* dy, const void* h, const void* weight, const float* rms, const void* addend,
-                                     void* dx, void* dweight, void* workspace, size_t workspace_bytes, int64_t rows,
-                                     int hidden, int dtype, void* stream);
+                                     void* dx, void* dx_plain, void* dweight, void* workspace, size_t workspace_bytes,
+                                     int64_t rows, int hidden, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SwiGLU forward: act = silu(x w_gate^T + b_gate) * (x w_up^T + b_up)
@@ -150,6 +153,20 @@ L32_API int l32_block_tail_forward(const void* attn_out, const void* residual, c
                                    const void* w_gate, const void* w_up, const void* w_down, void* out, void* normed_ws,
                                    void* act_ws, int64_t tokens, int hidden, int inter, int dtype, void* stream);
 
+/* The same with everything a training step and the NEXT block need (every extra pointer optional):
+ *   h_out, rms_out          : attn_out + residual (rounded to `dtype`; only written when residual != NULL) and the row
+ *                             statistic sqrt(mean(h^2) + eps) -- the operands of l32_rmsnorm_backward(_add);
+ *   gate_cache, up_cache    : both or neither, the operands of l32_ffn_backward;
+ *   next_norm_weight (+ next_eps, next_normed, next_rms): when given, the sum `out` is normalised once more with that weight
+ *                             -- the next block's norm1, or final_norm after the last block (Model/model.py:267, :346) --
+ *                             in the same call, while `out` is still L2-resident, so the next block starts from next_normed.
+ */
+L32_API int l32_block_tail_forward_ex(const void* attn_out, const void* residual, const void* norm_weight, float eps,
+                                      const void* w_gate, const void* w_up, const void* w_down, void* out, void* normed_ws,
+                                      void* act_ws, void* h_out, float* rms_out, void* gate_cache, void* up_cache,
+                                      const void* next_norm_weight, float next_eps, void* next_normed, float* next_rms,
+                                      int64_t tokens, int hidden, int inter, int dtype, void* stream);
+
 /* Whole feed-forward backward (down projection included).
  *   dy : [tokens, hidden].  Outputs (each optional): dx [tokens, hidden], dw_gate / dw_up [inter, hidden]
  *   (both or neither), dw_down [hidden, inter].
@@ -186,6 +203,26 @@ L32_API int l32_ffn_lora_backward(const void* dy, const void* x, const void* w_g
                                   const void* up_cache, void* dx, void* dw_gate, void* dw_up, void* dlora_a, void* dlora_bs,
                                   void* workspace, size_t workspace_bytes, int64_t tokens, int hidden, int inter, int rank,
                                   int dtype, void* stream);
+
+/* Any Linear_LORA layer (Model/model.py:107-121; the attention projections q/k/v/out of README.md:179-188 as well as
+ * w_down): y = x w^T + bias + (dropout(x) lora_a^T) lora_bs^T with the adapter as a second accumulation phase of the base
+ * GEMM.
+ *   x_lora : optional [tokens, in], the adapter's input dropout(x) (Model/model.py:121) when LoRA dropout is active -- the
+ *            mask is the caller's (exact nn.Dropout semantics); NULL = x itself.
+ *   lora_bs: [out, rank], already multiplied by alpha / rank;  t_out : [tokens, rank] receives dropout(x) lora_a^T.
+ */
+L32_API int l32_linear_lora_forward(const void* x, const void* x_lora, const void* w, const void* bias, const void* lora_a,
+                                    const void* lora_bs, void* y, void* t_out, int64_t tokens, int in_features,
+                                    int out_features, int rank, int dtype, void* stream);
+/* Backward with a frozen base weight: u = dy lora_bs (written to u_out [tokens, rank]);
+ *   dx      = dy w + u lora_a                    (dx_addend == NULL: ONE GEMM, two accumulation phases), or
+ *   dx      = dy w + dx_addend                   (LoRA dropout: the caller forms mask * (u lora_a) / (1 - p) and the epilogue
+ *                                                 of the base GEMM adds it);
+ *   dlora_a = u^T x_lora  [rank, in];  dlora_bs = dy^T t  [out, rank] (gradient w.r.t. the SCALED matrix).
+ * Every output is optional; u_out may be NULL only for a pure `dx = dy w + dx_addend` call (no dlora_a). */
+L32_API int l32_linear_lora_backward(const void* dy, const void* x_lora, const void* w, const void* lora_a, const void* lora_bs,
+                                     const void* t, const void* dx_addend, void* dx, void* dlora_a, void* dlora_bs, void* u_out,
+                                     int64_t tokens, int in_features, int out_features, int rank, int dtype, void* stream);
 
 /* General tiled GEMM used by the entry points above (exposed for tests, tuning and the tensor-parallel
  * host code):  D[m,n] = A[m,k] B[n,k]^T  (+ A1 B1^T when a1 != NULL).

@@ -3,6 +3,7 @@
 The directory name is not a Python identifier; import it as `llama32_b200` (alias package at the repo root).
 """
 from .modules import (  # noqa: F401
+    BlockTailFunction,
     FFNFunction,
     FFNLoRAFunction,
     FusedFeedForward,
@@ -11,9 +12,11 @@ from .modules import (  # noqa: F401
     LLAMARMSNorm,
     Linear_LORA,
     LinearFunction,
+    LinearLoRAFunction,
     RMSNormFunction,
     SwiGLUFunction,
     block_tail,
+    chain_block_norms,
     convert_feedforward_to_fused,
     convert_instances,
     patch_reference,
@@ -22,5 +25,5 @@ from .modules import (  # noqa: F401
 __all__ = [
     "FFNFunction", "FFNLoRAFunction", "FusedFeedForward", "FusedFeedforward", "FusedSwiGLU", "LLAMARMSNorm", "Linear_LORA",
     "LinearFunction", "RMSNormFunction", "SwiGLUFunction", "block_tail", "convert_feedforward_to_fused", "convert_instances",
-    "patch_reference",
+    "patch_reference", "BlockTailFunction", "LinearLoRAFunction", "chain_block_norms",
 ]

@@ -30,13 +30,17 @@ SIGNATURES = {
     "l32_add_rmsnorm_forward": (c_int, [c_void_p] * 6 + [c_int64, c_int, c_float, c_int, c_void_p]),
     "l32_rmsnorm_backward_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "l32_rmsnorm_backward": (c_int, [c_void_p] * 7 + [c_size_t, c_int64, c_int, c_int, c_void_p]),
-    "l32_rmsnorm_backward_add": (c_int, [c_void_p] * 8 + [c_size_t, c_int64, c_int, c_int, c_void_p]),
+    "l32_rmsnorm_backward_add": (c_int, [c_void_p] * 9 + [c_size_t, c_int64, c_int, c_int, c_void_p]),
     "l32_swiglu_forward": (c_int, [c_void_p] * 8 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_swiglu_backward_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "l32_swiglu_backward": (c_int, [c_void_p] * 10 + [c_size_t, c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_linear_forward": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_ffn_forward": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_block_tail_forward": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 6 + [c_int64, c_int, c_int, c_int, c_void_p]),
+    "l32_block_tail_forward_ex": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 11 + [c_float] + [c_void_p] * 2 +
+                                  [c_int64, c_int, c_int, c_int, c_void_p]),
+    "l32_linear_lora_forward": (c_int, [c_void_p] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    "l32_linear_lora_backward": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "l32_ffn_backward_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "l32_ffn_backward": (c_int, [c_void_p] * 12 + [c_size_t, c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_ffn_lora_forward": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),

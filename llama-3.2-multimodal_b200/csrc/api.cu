@@ -126,13 +126,13 @@ size_t l32_rmsnorm_backward_workspace_bytes(int64_t rows, int hidden) {
 
 int l32_rmsnorm_backward(const void* dy, const void* h, const void* weight, const float* rms, void* dx, void* dweight,
                          void* workspace, size_t workspace_bytes, int64_t rows, int hidden, int dtype, void* stream) {
-    return l32_rmsnorm_backward_add(dy, h, weight, rms, nullptr, dx, dweight, workspace, workspace_bytes, rows, hidden, dtype,
-                                    stream);
+    return l32_rmsnorm_backward_add(dy, h, weight, rms, nullptr, dx, nullptr, dweight, workspace, workspace_bytes, rows, hidden,
+                                    dtype, stream);
 }
 
 int l32_rmsnorm_backward_add(const void* dy, const void* h, const void* weight, const float* rms, const void* addend, void* dx,
-                             void* dweight, void* workspace, size_t workspace_bytes, int64_t rows, int hidden, int dtype,
-                             void* stream) {
+                             void* dx_plain, void* dweight, void* workspace, size_t workspace_bytes, int64_t rows, int hidden,
+                             int dtype, void* stream) {
     if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
     if (rows < 0 || hidden <= 0) return L32_ERR_BAD_SHAPE;
     if (dy == nullptr || h == nullptr || weight == nullptr || rms == nullptr || dx == nullptr) {
@@ -141,8 +141,8 @@ int l32_rmsnorm_backward_add(const void* dy, const void* h, const void* weight, 
     if (rows > 0 && (workspace == nullptr || workspace_bytes < rmsnorm_bwd_workspace_bytes(rows, hidden) ||
                      !is_aligned16(workspace)))
         return L32_ERR_WORKSPACE;
-    return static_cast<int>(rmsnorm_bwd(dy, h, weight, rms, addend, dx, dweight, static_cast<float*>(workspace), rows, hidden,
-                                        dtype, as_stream(stream)));
+    return static_cast<int>(rmsnorm_bwd(dy, h, weight, rms, addend, dx, dx_plain, dweight, static_cast<float*>(workspace), rows,
+                                        hidden, dtype, as_stream(stream)));
 }
 
 int l32_swiglu_forward(const void* x, const void* w_gate, const void* w_up, const void* b_gate, const void* b_up,
@@ -186,17 +186,38 @@ int l32_linear_forward(const void* a, const void* w, const void* bias, void* y, 
 int l32_block_tail_forward(const void* attn_out, const void* residual, const void* norm_weight, float eps, const void* w_gate,
                            const void* w_up, const void* w_down, void* out, void* normed_ws, void* act_ws, int64_t tokens,
                            int hidden, int inter, int dtype, void* stream) {
+    return l32_block_tail_forward_ex(attn_out, residual, norm_weight, eps, w_gate, w_up, w_down, out, normed_ws, act_ws, nullptr,
+                                     nullptr, nullptr, nullptr, nullptr, 0.f, nullptr, nullptr, tokens, hidden, inter, dtype,
+                                     stream);
+}
+
+int l32_block_tail_forward_ex(const void* attn_out, const void* residual, const void* norm_weight, float eps, const void* w_gate,
+                              const void* w_up, const void* w_down, void* out, void* normed_ws, void* act_ws, void* h_out,
+                              float* rms_out, void* gate_cache, void* up_cache, const void* next_norm_weight, float next_eps,
+                              void* next_normed, float* next_rms, int64_t tokens, int hidden, int inter, int dtype,
+                              void* stream) {
     if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
     if (!shapes_ok(tokens, hidden, inter)) return L32_ERR_BAD_SHAPE;
     if (tokens == 0) return L32_OK;
     if (attn_out == nullptr || norm_weight == nullptr || w_gate == nullptr || w_up == nullptr || w_down == nullptr || out == nullptr)
         return L32_ERR_NULL;
     if (normed_ws == nullptr || act_ws == nullptr) return L32_ERR_WORKSPACE;
-    int rc = l32_add_rmsnorm_forward(attn_out, residual, norm_weight, normed_ws, nullptr, nullptr, tokens, hidden, eps, dtype, stream);
+    if ((gate_cache == nullptr) != (up_cache == nullptr)) return L32_ERR_NULL;
+    if (next_norm_weight != nullptr && next_normed == nullptr) return L32_ERR_NULL;
+    // norm2(attn_out, residual)  [+ h, rms for the backward]
+    int rc = l32_add_rmsnorm_forward(attn_out, residual, norm_weight, normed_ws, residual != nullptr ? h_out : nullptr, rms_out,
+                                     tokens, hidden, eps, dtype, stream);
     if (rc != L32_OK) return rc;
-    rc = l32_swiglu_forward(normed_ws, w_gate, w_up, nullptr, nullptr, act_ws, nullptr, nullptr, tokens, hidden, inter, dtype, stream);
+    // fused gate/up + SiLU*mul  [+ caches]
+    rc = l32_swiglu_forward(normed_ws, w_gate, w_up, nullptr, nullptr, act_ws, gate_cache, up_cache, tokens, hidden, inter, dtype,
+                            stream);
     if (rc != L32_OK) return rc;
-    return linear_forward_add(act_ws, w_down, nullptr, attn_out, out, tokens, inter, hidden, dtype, stream);
+    // down projection whose epilogue adds attn_out: out = attn_out + ff_out  (Model/model.py:273)
+    rc = linear_forward_add(act_ws, w_down, nullptr, attn_out, out, tokens, inter, hidden, dtype, stream);
+    if (rc != L32_OK || next_norm_weight == nullptr) return rc;
+    // chained: the next block's norm1 (or final_norm) of the sum, while `out` is still in L2 (Model/model.py:267, :346)
+    return l32_add_rmsnorm_forward(out, nullptr, next_norm_weight, next_normed, nullptr, next_rms, tokens, hidden, next_eps, dtype,
+                                   stream);
 }
 
 namespace {
@@ -468,6 +489,101 @@ int l32_ffn_lora_backward(const void* dy, const void* x, const void* w_gate, con
         if (rc != L32_OK) return rc;
     }
     if (dlora_a != nullptr) rc = wgrad(u, rank, act, inter, dlora_a, t, dtype, s);   // [rank, inter] = u^T act
+    return rc;
+}
+
+int l32_linear_lora_forward(const void* x, const void* x_lora, const void* w, const void* bias, const void* lora_a,
+                            const void* lora_bs, void* y, void* t_out, int64_t tokens, int in_features, int out_features, int rank,
+                            int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, in_features, out_features) || rank <= 0 || rank > 64 || (rank % 8) != 0) return L32_ERR_BAD_SHAPE;
+    if (tokens == 0) return L32_OK;
+    if (x == nullptr || w == nullptr || lora_a == nullptr || lora_bs == nullptr || y == nullptr || t_out == nullptr) return L32_ERR_NULL;
+    cudaStream_t s = as_stream(stream);
+    const int t = static_cast<int>(tokens);
+    // t = dropout(x) lora_a^T  [tokens, rank]
+    GemmProblem g = blank(t, rank, dtype);
+    g.k[0] = in_features;
+    g.a[0] = op(x_lora != nullptr ? x_lora : x, in_features, 0);
+    g.b[0] = op(lora_a, in_features, 0);
+    g.epilogue = EPI_STORE;
+    g.d[0] = t_out;
+    g.ldd = rank;
+    int rc = gemm_sm100(g, s);
+    if (rc != L32_OK) return rc;
+    // y = x w^T + t lora_bs^T (+ bias): one kernel, two accumulation phases (K = in_features, then K = rank)
+    g = blank(t, out_features, dtype);
+    g.num_phases = 2;
+    g.k[0] = in_features;
+    g.k[1] = rank;
+    g.a[0] = op(x, in_features, 0);
+    g.b[0] = op(w, in_features, 0);
+    g.a[1] = op(t_out, rank, 0);
+    g.b[1] = op(lora_bs, rank, 0);
+    g.epilogue = EPI_STORE;
+    g.d[0] = y;
+    g.bias[0] = bias;
+    g.ldd = out_features;
+    return gemm_sm100(g, s);
+}
+
+int l32_linear_lora_backward(const void* dy, const void* x_lora, const void* w, const void* lora_a, const void* lora_bs,
+                             const void* t_saved, const void* dx_addend, void* dx, void* dlora_a, void* dlora_bs, void* u_out,
+                             int64_t tokens, int in_features, int out_features, int rank, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, in_features, out_features) || rank <= 0 || rank > 64 || (rank % 8) != 0) return L32_ERR_BAD_SHAPE;
+    cudaStream_t s = as_stream(stream);
+    if (tokens == 0) {
+        cudaError_t e = cudaSuccess;
+        if (dlora_a != nullptr) e = cudaMemsetAsync(dlora_a, 0, static_cast<size_t>(rank) * in_features * 2, s);
+        if (e == cudaSuccess && dlora_bs != nullptr) e = cudaMemsetAsync(dlora_bs, 0, static_cast<size_t>(out_features) * rank * 2, s);
+        return static_cast<int>(e);
+    }
+    if (dy == nullptr || w == nullptr || lora_a == nullptr || lora_bs == nullptr) return L32_ERR_NULL;
+    if ((dlora_a != nullptr && x_lora == nullptr) || (dlora_bs != nullptr && t_saved == nullptr)) return L32_ERR_NULL;
+    // u is needed by dlora_a and by the fused (no-dropout) dx; a pure "dx = dy w + addend" call may leave it out
+    if (u_out == nullptr && (dlora_a != nullptr || (dx != nullptr && dx_addend == nullptr))) return L32_ERR_NULL;
+    const int t = static_cast<int>(tokens);
+    GemmProblem g;
+    int rc = L32_OK;
+    if (u_out != nullptr) {
+        // u = dy lora_bs  [tokens, rank]   (lora_bs [out, rank] consumed as an MN-major B operand)
+        g = blank(t, rank, dtype);
+        g.k[0] = out_features;
+        g.a[0] = op(dy, out_features, 0);
+        g.b[0] = op(lora_bs, rank, 1);
+        g.epilogue = EPI_STORE;
+        g.d[0] = u_out;
+        g.ldd = rank;
+        rc = gemm_sm100(g, s);
+        if (rc != L32_OK) return rc;
+    }
+    if (dx != nullptr) {
+        // no dropout: dx = dy w + u lora_a in ONE kernel (two accumulation phases, both weights consumed MN-major);
+        // with dropout the caller passes the masked adapter term as `dx_addend` and the epilogue adds it: dx = dy w + addend
+        g = blank(t, in_features, dtype);
+        g.k[0] = out_features;
+        g.a[0] = op(dy, out_features, 0);
+        g.b[0] = op(w, in_features, 1);
+        if (dx_addend == nullptr) {
+            g.num_phases = 2;
+            g.k[1] = rank;
+            g.a[1] = op(u_out, rank, 0);
+            g.b[1] = op(lora_a, in_features, 1);
+        } else {
+            g.e[0] = dx_addend;
+        }
+        g.epilogue = EPI_STORE;
+        g.d[0] = dx;
+        g.ldd = in_features;
+        rc = gemm_sm100(g, s);
+        if (rc != L32_OK) return rc;
+    }
+    if (dlora_bs != nullptr) {   // [out, rank] = dy^T t
+        rc = wgrad(dy, out_features, t_saved, rank, dlora_bs, t, dtype, s);
+        if (rc != L32_OK) return rc;
+    }
+    if (dlora_a != nullptr) rc = wgrad(u_out, rank, x_lora, in_features, dlora_a, t, dtype, s);   // [rank, in] = u^T dropout(x)
     return rc;
 }
 

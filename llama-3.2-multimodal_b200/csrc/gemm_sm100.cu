@@ -108,12 +108,10 @@ L32_DEVICE void load_tile(const CUtensorMap* map, uint8_t* dst, uint64_t* full_b
 L32_DEVICE void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// streaming read (read once, never again): do not keep it in L1, first to leave L2
-L32_DEVICE uint4 ld_global_stream_v4(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
+// 32-byte streaming read (one full sector per lane in ONE request; read once: first to leave L2).  32-byte aligned address.
+L32_DEVICE void ld_global_stream_v8(const void* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
 }
 L32_DEVICE uint4 ld_global_nc_v4(const void* p) {
     uint4 r;
@@ -459,23 +457,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const size_t row_off = static_cast<size_t>(row_ok ? row : 0) * tile_ldd;
             // EPI_SWIGLU_BWD: the gate / up cache rows of step c + 2 (this warp's next step) are requested before step c is
             // computed, the first ones before the accumulator is even complete (they do not depend on it)
+            // 32-byte loads need 32-byte aligned rows: row pitch a multiple of 16 elements and 32-byte aligned bases
+            const bool wide_ok = (kEpi == EPI_SWIGLU_BWD) && (p.ldd % 16) == 0 &&
+                                 ((reinterpret_cast<uintptr_t>(p.e[0]) | reinterpret_cast<uintptr_t>(p.e[1])) & 31u) == 0;
             auto load_gu = [&](int c, uint4 (&gq)[2], uint4 (&uq)[2]) {
                 const int col = n0 + c * 16;
                 const int nv = (row_ok && c < kAccCols / 16 && !(p.debug_flags & 2)) ? (p.n - col) : 0;
                 const uint8_t* gsrc = static_cast<const uint8_t*>(p.e[0]) + (row_off + col) * esz;
                 const uint8_t* usrc = static_cast<const uint8_t*>(p.e[1]) + (row_off + col) * esz;
+                if (nv >= 16 && wide_ok && !(p.debug_flags & 8)) {
+                    ld_global_stream_v8(gsrc, gq[0], gq[1]);
+                    ld_global_stream_v8(usrc, uq[0], uq[1]);
+                    return;
+                }
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     gq[j] = make_uint4(0, 0, 0, 0);
                     uq[j] = make_uint4(0, 0, 0, 0);
                     if (j * 8 < nv) {
-                        if (p.debug_flags & 8) {
-                            gq[j] = ld_global_nc_v4(gsrc + j * 16);
-                            uq[j] = ld_global_nc_v4(usrc + j * 16);
-                        } else {
-                            gq[j] = ld_global_stream_v4(gsrc + j * 16);
-                            uq[j] = ld_global_stream_v4(usrc + j * 16);
-                        }
+                        gq[j] = ld_global_nc_v4(gsrc + j * 16);
+                        uq[j] = ld_global_nc_v4(usrc + j * 16);
                     }
                 }
             };

@@ -28,7 +28,8 @@ inline int current_device_slot() {
 cudaError_t add_rmsnorm_fwd(const void* x, const void* residual, const void* weight, void* y, void* h_out, float* rms,
                             int64_t rows, int C, float eps, int dtype, cudaStream_t s);
 cudaError_t rmsnorm_bwd(const void* dy, const void* h, const void* weight, const float* rms, const void* addend, void* dx,
-                        void* dw, float* workspace, int64_t rows, int C, int dtype, cudaStream_t s);   // dx (+= addend)
+                        void* dx_plain, void* dw, float* workspace, int64_t rows, int C, int dtype,
+                        cudaStream_t s);   // dx = norm backward (+ addend); dx_plain: optional, the norm backward without it
 size_t rmsnorm_bwd_workspace_bytes(int64_t rows, int C);
 
 // ---- gemm_sm100.cu : D[M,N] = sum_p A_p[M,K_p] * B_p[N,K_p]^T on tcgen05, fused epilogues

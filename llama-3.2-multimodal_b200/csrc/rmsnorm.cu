@@ -207,7 +207,8 @@ L32_DEVICE uint4 lds_v4(const void* p) {
 template <typename T, int RT, int VPT, bool kAddend, int kBwdConsumers, int RPI>
 __global__ void __launch_bounds__(kBwdConsumers + 32, 1) rmsnorm_bwd_kernel(
     const T* __restrict__ dy, const T* __restrict__ h, const T* __restrict__ weight, const float* __restrict__ rms,
-    const T* __restrict__ addend, T* __restrict__ dx, float* __restrict__ dw_partial, int64_t rows, int C, int stages) {
+    const T* __restrict__ addend, T* __restrict__ dx, T* __restrict__ dx_plain, float* __restrict__ dw_partial,
+    int64_t rows, int C, int stages) {
     constexpr int G = kBwdConsumers / RT;
     constexpr int kBwdThreads = kBwdConsumers + 32;
     static_assert(kBwdConsumers % RT == 0 && G >= 1 && G <= 14, "row groups");
@@ -396,6 +397,7 @@ __global__ void __launch_bounds__(kBwdConsumers + 32, 1) rmsnorm_bwd_kernel(
 #pragma unroll
                     for (int j = 0; j < 8; ++j) o[j] = fmaf(-hh[j], c2, gg[j] * w[j] * rstd[r]);
                     if constexpr (kAddend) {   // dx += addend (a gradient that bypasses the norm, e.g. the block tail's "+ attn_out")
+                        if (dx_plain != nullptr) st_v4(dx_plain + base[r] + (size_t)v * 8, pack8<T>(o));   // and the plain one
                         float ad[8];
                         unpack8<T>(av[r][k], ad);
 #pragma unroll
@@ -452,8 +454,8 @@ __global__ void __launch_bounds__(kBwdConsumers + 32, 1) rmsnorm_bwd_kernel(
 // dw partial per CTA accumulated in global memory owned by that CTA (no atomics).
 template <typename T>
 __global__ void __launch_bounds__(256) rmsnorm_bwd_generic_kernel(
-    const T* dy, const T* h, const T* weight, const float* rms, const T* addend, T* dx, float* dw_partial, int64_t rows,
-    int C) {
+    const T* dy, const T* h, const T* weight, const float* rms, const T* addend, T* dx, T* dx_plain, float* dw_partial,
+    int64_t rows, int C) {
     __shared__ float red[8];
     float* my_dw = dw_partial + (size_t)blockIdx.x * C;
     for (int i = threadIdx.x; i < C; i += 256) my_dw[i] = 0.f;
@@ -474,7 +476,10 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_generic_kernel(
             const float gg = static_cast<float>(dy[base + i]);
             const float xh = static_cast<float>(h[base + i]) * rstd;
             float o = (gg * static_cast<float>(weight[i]) - xh * c1) * rstd;
-            if (addend != nullptr) o += static_cast<float>(addend[base + i]);
+            if (addend != nullptr) {
+                if (dx_plain != nullptr) dx_plain[base + i] = static_cast<T>(o);
+                o += static_cast<float>(addend[base + i]);
+            }
             dx[base + i] = static_cast<T>(o);
         }
         __syncthreads();
@@ -567,7 +572,7 @@ static int bwd_grid(int64_t rows) {
 
 template <typename T, int RT, int VPT, bool kAddend, int kBwdConsumers, int RPI>
 static cudaError_t launch_bwd_fast(const T* dy, const T* h, const T* weight, const float* rms, const T* addend, T* dx,
-                                   float* partial, int64_t rows, int C, int grid, cudaStream_t s) {
+                                   T* dx_plain, float* partial, int64_t rows, int C, int grid, cudaStream_t s) {
     constexpr int G = kBwdConsumers / RT;
     const size_t row_bytes = static_cast<size_t>(C) * sizeof(T);
     const size_t stage_bytes = 2 * row_bytes;
@@ -596,7 +601,7 @@ static cudaError_t launch_bwd_fast(const T* dy, const T* h, const T* weight, con
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k, dy, h, weight, rms, addend, dx, partial, rows, C, stages);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, dy, h, weight, rms, addend, dx, dx_plain, partial, rows, C, stages);
     if (e == cudaSuccess) count_launch();
     return e;
 }
@@ -609,20 +614,21 @@ size_t rmsnorm_bwd_workspace_bytes(int64_t rows, int C) {
 
 template <typename T, int RT, int VPT, int NC = kBwdConsumersMax, int RPI = 1>
 static cudaError_t launch_bwd_sel(const T* dy, const T* h, const T* weight, const float* rms, const T* addend, T* dx,
-                                  float* partial, int64_t rows, int C, int grid, cudaStream_t s) {
-    if (addend != nullptr) return launch_bwd_fast<T, RT, VPT, true, NC, RPI>(dy, h, weight, rms, addend, dx, partial, rows, C, grid, s);
-    return launch_bwd_fast<T, RT, VPT, false, NC, RPI>(dy, h, weight, rms, addend, dx, partial, rows, C, grid, s);
+                                  T* dx_plain, float* partial, int64_t rows, int C, int grid, cudaStream_t s) {
+    if (addend != nullptr) return launch_bwd_fast<T, RT, VPT, true, NC, RPI>(dy, h, weight, rms, addend, dx, dx_plain, partial, rows, C, grid, s);
+    return launch_bwd_fast<T, RT, VPT, false, NC, RPI>(dy, h, weight, rms, addend, dx, dx_plain, partial, rows, C, grid, s);
 }
 
 template <typename T>
-static cudaError_t rmsnorm_bwd_t(const T* dy, const T* h, const T* weight, const float* rms, const T* addend, T* dx, T* dw,
+static cudaError_t rmsnorm_bwd_t(const T* dy, const T* h, const T* weight, const float* rms, const T* addend, T* dx,
+                                 T* dx_plain, T* dw,
                                  float* workspace, int64_t rows, int C, cudaStream_t s) {
     if (rows == 0) {
         if (dw != nullptr) return cudaMemsetAsync(dw, 0, sizeof(T) * C, s);
         return cudaSuccess;
     }
     const bool aligned = (C % 8 == 0) && is_aligned16(dy) && is_aligned16(h) && is_aligned16(weight) && is_aligned16(dx) &&
-                         is_aligned16(addend);
+                         is_aligned16(addend) && is_aligned16(dx_plain);
     int grid;
     cudaError_t e;
     if (aligned && C <= 16384) {
@@ -630,20 +636,20 @@ static cudaError_t rmsnorm_bwd_t(const T* dy, const T* h, const T* weight, const
         // threads per row (RT) x 16-byte vectors per thread (VPT): as few threads per row as the registers allow, so that
         // 512 / RT rows are in flight per SM (the per-row wait -> reduce -> barrier -> store chain is latency-bound)
         static const int variant = [] { const char* v = getenv("L32_RMSBWD_VARIANT"); return v ? atoi(v) : 0; }();   // tuning knob
-        if (C <= 64 * 2 * 8) e = launch_bwd_sel<T, 64, 2>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
-        else if (C <= 128 * 2 * 8) e = launch_bwd_sel<T, 128, 2>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
+        if (C <= 64 * 2 * 8) e = launch_bwd_sel<T, 64, 2>(dy, h, weight, rms, addend, dx, dx_plain, workspace, rows, C, grid, s);
+        else if (C <= 128 * 2 * 8) e = launch_bwd_sel<T, 128, 2>(dy, h, weight, rms, addend, dx, dx_plain, workspace, rows, C, grid, s);
         else if (C <= 128 * 4 * 8) {
-            if (variant == 1) e = launch_bwd_sel<T, 128, 4, 256, 2>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
-            else if (variant == 2) e = launch_bwd_sel<T, 256, 2, 512, 2>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
-            else e = launch_bwd_sel<T, 128, 4, 384, 1>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
+            if (variant == 1) e = launch_bwd_sel<T, 128, 4, 256, 2>(dy, h, weight, rms, addend, dx, dx_plain, workspace, rows, C, grid, s);
+            else if (variant == 2) e = launch_bwd_sel<T, 256, 2, 512, 2>(dy, h, weight, rms, addend, dx, dx_plain, workspace, rows, C, grid, s);
+            else e = launch_bwd_sel<T, 128, 4, 384, 1>(dy, h, weight, rms, addend, dx, dx_plain, workspace, rows, C, grid, s);
         } else if (C <= 256 * 4 * 8) {
-            if (variant == 1) e = launch_bwd_sel<T, 256, 4, 256, 1>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
-            else if (variant == 2) e = launch_bwd_sel<T, 384, 3, 384, 1>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
-            else e = launch_bwd_sel<T, 512, 2, 512, 1>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
-        } else e = launch_bwd_sel<T, 512, 4, 512, 1>(dy, h, weight, rms, addend, dx, workspace, rows, C, grid, s);
+            if (variant == 1) e = launch_bwd_sel<T, 256, 4, 256, 1>(dy, h, weight, rms, addend, dx, dx_plain, workspace, rows, C, grid, s);
+            else if (variant == 2) e = launch_bwd_sel<T, 384, 3, 384, 1>(dy, h, weight, rms, addend, dx, dx_plain, workspace, rows, C, grid, s);
+            else e = launch_bwd_sel<T, 512, 2, 512, 1>(dy, h, weight, rms, addend, dx, dx_plain, workspace, rows, C, grid, s);
+        } else e = launch_bwd_sel<T, 512, 4, 512, 1>(dy, h, weight, rms, addend, dx, dx_plain, workspace, rows, C, grid, s);
     } else {
         grid = 2 * bwd_grid(rows);
-        rmsnorm_bwd_generic_kernel<T><<<grid, 256, 0, s>>>(dy, h, weight, rms, addend, dx, workspace, rows, C);
+        rmsnorm_bwd_generic_kernel<T><<<grid, 256, 0, s>>>(dy, h, weight, rms, addend, dx, dx_plain, workspace, rows, C);
         count_launch();
         e = cudaGetLastError();
     }
@@ -675,13 +681,14 @@ cudaError_t add_rmsnorm_fwd(const void* x, const void* residual, const void* wei
 }
 
 cudaError_t rmsnorm_bwd(const void* dy, const void* h, const void* weight, const float* rms, const void* addend, void* dx,
-                        void* dw, float* workspace, int64_t rows, int C, int dtype, cudaStream_t s) {
+                        void* dx_plain, void* dw, float* workspace, int64_t rows, int C, int dtype, cudaStream_t s) {
+    if (addend == nullptr) dx_plain = nullptr;
     if (dtype == L32_BF16)
         return rmsnorm_bwd_t<__nv_bfloat16>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)h, (const __nv_bfloat16*)weight, rms,
-                                            (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, (__nv_bfloat16*)dw, workspace, rows,
-                                            C, s);
+                                            (const __nv_bfloat16*)addend, (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_plain,
+                                            (__nv_bfloat16*)dw, workspace, rows, C, s);
     return rmsnorm_bwd_t<__half>((const __half*)dy, (const __half*)h, (const __half*)weight, rms, (const __half*)addend,
-                                 (__half*)dx, (__half*)dw, workspace, rows, C, s);
+                                 (__half*)dx, (__half*)dx_plain, (__half*)dw, workspace, rows, C, s);
 }
 
 }  // namespace l32

@@ -24,6 +24,7 @@ from . import ops
 __all__ = [
     "RMSNormFunction", "LLAMARMSNorm", "SwiGLUFunction", "FusedSwiGLU", "LinearFunction", "Linear_LORA", "FFNFunction", "FFNLoRAFunction",
     "FusedFeedforward", "FusedFeedForward", "convert_feedforward_to_fused", "patch_reference", "convert_instances", "block_tail",
+    "BlockTailFunction", "LinearLoRAFunction", "chain_block_norms",
 ]
 
 
@@ -71,6 +72,12 @@ class LLAMARMSNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones(dim))
 
     def forward(self, x, residual=None):
+        if residual is None:
+            # the previous block's tail may already have normalised this very tensor with this very module
+            # (block_tail(..., next_norm=self) attaches the result): nothing left to do
+            pre = getattr(x, "_l32_prenormed", None)
+            if pre is not None and pre[0] is self and pre[2] == x._version:   # ... and nobody has written to x since
+                return pre[1]
         if ops.supported(x):
             return RMSNormFunction.apply(x, self.weight, self.eps, residual)
         # reference semantics for fp32 / CPU inputs (Model/model.py:166-171)
@@ -208,11 +215,53 @@ def _linear(x, weight, bias=None):
     return F.linear(x, weight, bias)
 
 
+class LinearLoRAFunction(torch.autograd.Function):
+    """y = x W^T + bias + scale * (dropout(x) A^T) B^T for a frozen base W (reference Model/model.py:107-121): the adapter is
+    a second accumulation phase (K = rank) of the base GEMM, forward and backward; with LoRA dropout the mask is drawn here
+    (nn.Dropout semantics: Bernoulli(1 - p) keep mask, kept values scaled by 1 / (1 - p)) and stays fused -- forward feeds
+    dropout(x) to the rank-r GEMM only, backward adds the masked adapter gradient in the base GEMM's epilogue."""
+
+    @classmethod
+    def apply(cls, x, weight, bias, lora_a, lora_b, scale, p_drop):
+        if not _wants_grad(x, lora_a, lora_b):
+            xl = F.dropout(x, p_drop, True) if p_drop > 0.0 else None
+            return ops.linear_lora_forward(x, weight, lora_a, lora_b * scale, bias, xl)[0]
+        return super().apply(x, weight, bias, lora_a, lora_b, scale, p_drop)
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, lora_a, lora_b, scale, p_drop):
+        lora_bs = lora_b * scale
+        mask = xl = None
+        if p_drop > 0.0:
+            mask = torch.empty_like(x).bernoulli_(1.0 - p_drop).mul_(1.0 / (1.0 - p_drop))   # keep mask, pre-scaled
+            xl = x * mask
+        y, t = ops.linear_lora_forward(x, weight, lora_a, lora_bs, bias, xl)
+        ctx.save_for_backward(xl if xl is not None else x, weight, lora_a, lora_bs, t, mask)
+        ctx.scale, ctx.x_shape = scale, x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        xl, weight, lora_a, lora_bs, t, mask = ctx.saved_tensors
+        nx, nw, nb, na, nlb, _, _ = ctx.needs_input_grad
+        if nw:
+            raise RuntimeError("LinearLoRAFunction: the base weight is frozen under LoRA (Model/model.py:117)")
+        fn = None
+        if mask is not None:
+            in_f = weight.shape[1]
+            fn = lambda u: ops.gemm(u, lora_a, b_mn_major=True).view(-1, in_f) * mask.reshape(-1, in_f)   # mask * (u A)
+        dx, dla, dlbs = ops.linear_lora_backward(grad_y, xl, weight, lora_a, lora_bs, t, want_dx=nx, want_dlora=(na or nlb),
+                                                 dx_addend_fn=fn)
+        db = grad_y.reshape(-1, grad_y.shape[-1]).float().sum(0).to(weight.dtype) if nb else None
+        dlb = (dlbs * ctx.scale) if (dlbs is not None and nlb) else None
+        return (dx.view(ctx.x_shape) if dx is not None else None), None, db, (dla if na else None), dlb, None, None
+
+
 class Linear_LORA(nn.Module):
     """Drop-in for reference Model/model.py:107-121: frozen base + (alpha/rank) * B(A(dropout(x))).
 
-    The base projection runs on the tcgen05 GEMM; the rank-r side path stays in PyTorch (O(r) work).
-    """
+    16-bit CUDA tensors with a frozen base: base projection and the rank-r adapter run as ONE tcgen05 GEMM with two
+    accumulation phases (LinearLoRAFunction), dropout included.  Anything else evaluates the reference's expression."""
 
     def __init__(self, in_dim: int, out_dim: int, rank: int, alpha: float, dropout: float):
         super().__init__()
@@ -226,7 +275,19 @@ class Linear_LORA(nn.Module):
         self.lora_a.weight.requires_grad = True
         self.lora_b.weight.requires_grad = True
 
+    def _fusable(self, x):
+        w = self.linear.weight
+        return (ops.supported(x) and w.is_cuda and not w.requires_grad and w.dtype == x.dtype and
+                self.lora_a.weight.dtype == x.dtype and self.lora_b.weight.dtype == x.dtype and
+                self.rank % 8 == 0 and self.rank <= 64 and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0 and
+                x.numel() // max(1, x.shape[-1]) > 0)
+
     def forward(self, x):
+        if self._fusable(x):
+            p = self.dropout.p if (self.training and isinstance(self.dropout, nn.Dropout)) else 0.0
+            if p < 1.0:
+                return LinearLoRAFunction.apply(x, self.linear.weight, self.linear.bias, self.lora_a.weight, self.lora_b.weight,
+                                                self.alpha / self.rank, float(p))
         base = _linear(x, self.linear.weight, self.linear.bias)
         return base + (self.alpha / self.rank) * self.lora_b(self.lora_a(self.dropout(x)))
 
@@ -332,24 +393,91 @@ class FusedFeedforward(nn.Module):
         return wd(sw(x))
 
 
-def block_tail(norm2, ff, attn_out, residual):
+class BlockTailFunction(torch.autograd.Function):
+    """out = attn_out + ff(norm2(attn_out, residual))  [, next_normed = next_norm(out)] -- the tail of the reference's
+    TransformerBlock.forward (Model/model.py:270-273) and, optionally, the next block's norm1 / final_norm (:267, :346) --
+    as one differentiable op: forward is ONE C call (l32_block_tail_forward_ex), backward is the FFN backward (d_act GEMM
+    with the SiLU' epilogue, two-phase dX, wgrads) between two RMSNorm backwards whose store passes absorb the two
+    "gradient around the norm" additions (d_out into the next norm's dx, d_out into norm2's dx for attn_out)."""
+
+    @staticmethod
+    def forward(ctx, attn_out, residual, norm_w, eps, w_gate, w_up, w_down, next_w, next_eps):
+        r = ops.block_tail_forward(attn_out, residual, norm_w, eps, w_gate, w_up, w_down, train=True, next_norm_weight=next_w,
+                                   next_eps=next_eps)
+        ctx.save_for_backward(r["h"], r["rms"], r["normed"], r["gate"], r["up"], norm_w, w_gate, w_up, w_down,
+                              r["out"] if next_w is not None else None, next_w, r["next_rms"])
+        ctx.has_residual = residual is not None
+        if next_w is None:
+            return r["out"]
+        return r["out"], r["next_normed"]
+
+    @staticmethod
+    def backward(ctx, d_out, d_next=None):
+        h, rms, normed, gate, up, norm_w, w_gate, w_up, w_down, out, next_w, next_rms = ctx.saved_tensors
+        na, nr, nnw, _, ng, nu, nd, nnext, _ = ctx.needs_input_grad
+        d_next_w = None
+        if next_w is not None:
+            # gradient of the chained norm, with the gradient that reaches `out` directly added in its store pass
+            d_out, d_next_w = ops.rmsnorm_backward(d_next, out, next_w, next_rms, want_dweight=nnext, addend=d_out)
+            if d_next_w is not None and d_next_w.dtype != next_w.dtype:
+                d_next_w = d_next_w.to(next_w.dtype)
+        d_out = d_out.contiguous()
+        d_normed, dwg, dwu, dwd, _, _ = ops.ffn_backward(d_out, normed, w_gate, w_up, w_down, gate, up, want_dx=True,
+                                                         want_dw_gate_up=(ng or nu), want_dw_down=nd)
+        # d_attn_out = d_out + norm2 backward; d_residual = norm2 backward alone
+        want_res = bool(ctx.has_residual and nr)
+        res = ops.rmsnorm_backward(d_normed, h, norm_w, rms, want_dweight=nnw, addend=d_out, want_plain=want_res)
+        d_attn, d_norm_w, d_h = res if want_res else (res[0], res[1], None)
+        if d_norm_w is not None and d_norm_w.dtype != norm_w.dtype:
+            d_norm_w = d_norm_w.to(norm_w.dtype)
+        return ((d_attn if na else None), (d_h if (ctx.has_residual and nr) else None), d_norm_w, None,
+                (dwg if ng else None), (dwu if nu else None), dwd, d_next_w, None)
+
+
+def block_tail(norm2, ff, attn_out, residual, next_norm=None):
     """`attn_out + ff(norm2(attn_out, residual=residual))` -- the tail of the reference's TransformerBlock.forward
-    (Model/model.py:270-273).  For inference on 16-bit CUDA tensors it is one C call (Add-RMSNorm, fused gate/up GEMM,
-    down GEMM whose epilogue adds attn_out); otherwise (training, fp32, CPU, LoRA / biases) the modules are composed
-    exactly as the reference does."""
+    (Model/model.py:270-273).  On 16-bit CUDA tensors with a plain `w_down` it is one C call (Add-RMSNorm, fused gate/up
+    GEMM, down GEMM whose epilogue adds attn_out), with or without autograd (BlockTailFunction).  `next_norm`: the
+    LLAMARMSNorm that will consume the result next (the following block's norm1, or final_norm): its output is computed in
+    the same call and attached to the returned tensor, where LLAMARMSNorm.forward picks it up.  Otherwise (fp32, CPU,
+    LoRA / biases) the modules are composed exactly as the reference does."""
     sw, wd = ff.swiglu, ff.w_down
-    if (ops.supported(attn_out) and isinstance(wd, nn.Linear) and wd.bias is None and sw.b_gate is None and
-            sw.w_gate.dtype == attn_out.dtype and wd.weight.dtype == attn_out.dtype and
-            not _wants_grad(attn_out, residual, norm2.weight, sw.w_gate, sw.w_up, wd.weight)):
-        return ops.block_tail_forward(attn_out, residual, norm2.weight, norm2.eps, sw.w_gate, sw.w_up, wd.weight)
-    return attn_out + ff(norm2(attn_out, residual=residual))
+    fusable = (ops.supported(attn_out) and isinstance(wd, nn.Linear) and wd.bias is None and sw.b_gate is None and
+               sw.w_gate.dtype == attn_out.dtype and wd.weight.dtype == attn_out.dtype and
+               (residual is None or (residual.shape == attn_out.shape and residual.dtype == attn_out.dtype)) and
+               attn_out.numel() > 0)
+    if not fusable:
+        return attn_out + ff(norm2(attn_out, residual=residual))
+    nw = next_norm.weight if isinstance(next_norm, LLAMARMSNorm) else None
+    neps = next_norm.eps if nw is not None else 0.0
+    if _wants_grad(attn_out, residual, norm2.weight, sw.w_gate, sw.w_up, wd.weight, nw):
+        res = BlockTailFunction.apply(attn_out, residual, norm2.weight, norm2.eps, sw.w_gate, sw.w_up, wd.weight, nw, neps)
+        out, nn_ = res if nw is not None else (res, None)
+    else:
+        res = ops.block_tail_forward(attn_out, residual, norm2.weight, norm2.eps, sw.w_gate, sw.w_up, wd.weight,
+                                     next_norm_weight=nw, next_eps=neps)
+        out, nn_ = (res["out"], res["next_normed"]) if nw is not None else (res, None)
+    if nn_ is not None:
+        out._l32_prenormed = (next_norm, nn_, out._version)
+    return out
 
 
 def _transformer_block_forward(self, hidden_states, attention_mask=None, position_ids=None, kv_cache=None):
-    """Same computation as the reference's TransformerBlock.forward (Model/model.py:265-273) with the tail fused."""
-    normed = self.norm1(hidden_states)
+    """Same computation as the reference's TransformerBlock.forward (Model/model.py:265-273) with the tail fused and
+    chained into the norm that consumes the block's output (`_l32_next_norm`, wired by `chain_block_norms`)."""
+    normed = self.norm1(hidden_states)          # picks up the previous block's chained result when there is one
     attn_out = self.att(normed, attention_mask=attention_mask, position_ids=position_ids, kv_cache=kv_cache)
-    return block_tail(self.norm2, self.ff, attn_out, hidden_states)
+    return block_tail(self.norm2, self.ff, attn_out, hidden_states, next_norm=getattr(self, "_l32_next_norm", None))
+
+
+def chain_block_norms(blocks, final_norm=None):
+    """Tell every decoder block which norm consumes its output: the next block's norm1, and `final_norm` after the last
+    one (reference Model/model.py:341-346 runs `for layer in self.layers` then `self.final_norm`).  Stored outside the module
+    tree (no new state_dict keys, no parameter sharing)."""
+    blocks = list(blocks)
+    for i, blk in enumerate(blocks):
+        nxt = blocks[i + 1].norm1 if i + 1 < len(blocks) else final_norm
+        object.__setattr__(blk, "_l32_next_norm", nxt if isinstance(nxt, LLAMARMSNorm) else None)
 
 
 FusedFeedForward = FusedFeedforward   # the reference spells it both ways (FusedSwiglu.py:94 vs model.py:210)
@@ -410,4 +538,10 @@ def convert_instances(root: nn.Module) -> nn.Module:
                 m.intermediate_size = m.swiglu.intermediate_size
         elif name == "Linear_LORA" and not isinstance(m, Linear_LORA):
             m.__class__ = Linear_LORA
+    # chain every stack of decoder blocks into the norm that follows it (a `layers` ModuleList next to a `final_norm`)
+    for m in root.modules():
+        layers = getattr(m, "layers", None)
+        if isinstance(layers, nn.ModuleList) and len(layers) and all(hasattr(b, "norm1") and hasattr(b, "norm2") and hasattr(b, "ff")
+                                                                    for b in layers):
+            chain_block_norms(layers, getattr(m, "final_norm", None))
     return root

@@ -104,9 +104,10 @@ def add_rmsnorm_forward(x, weight, residual=None, eps=1e-5, *, want_h=False, wan
     return y.view(x.shape), rms, (h.view(x.shape) if h is not None else None)
 
 
-def rmsnorm_backward(grad_out, h, weight, rms, *, want_dweight=True, addend=None):
+def rmsnorm_backward(grad_out, h, weight, rms, *, want_dweight=True, addend=None, want_plain=False):
     """(dx, dweight|None) for y = rmsnorm(h) * weight, given rms = sqrt(mean(h^2) + eps) from the forward.
-    `addend` (shaped like h): dx = (norm backward) + addend, added in the kernel's store pass."""
+    `addend` (shaped like h): dx = (norm backward) + addend, added in the kernel's store pass; with `want_plain` the
+    return value is (dx, dweight|None, dx_plain) where dx_plain is the norm backward without the addend."""
     _check_cuda(grad_out, h, weight, rms, addend)
     hidden = h.shape[-1]
     hc = h.contiguous()
@@ -125,10 +126,13 @@ def rmsnorm_backward(grad_out, h, weight, rms, *, want_dweight=True, addend=None
         ad = addend.contiguous()
         if ad.shape != hc.shape or ad.dtype != hc.dtype:
             raise L32Error("rmsnorm_backward: `addend` must be shaped and typed like h")
+    dxp = torch.empty_like(hc) if (want_plain and ad is not None) else None
     with torch.cuda.device(hc.device):
-        check(L.l32_rmsnorm_backward_add(_ptr(gc), _ptr(hc), _ptr(w), _ptr(rms.contiguous()), _ptr(ad), _ptr(dx), _ptr(dw),
-                                         _ptr(ws), ws_bytes, rows, hidden, _dtype_code(hc), _stream(hc)),
+        check(L.l32_rmsnorm_backward_add(_ptr(gc), _ptr(hc), _ptr(w), _ptr(rms.contiguous()), _ptr(ad), _ptr(dx), _ptr(dxp),
+                                         _ptr(dw), _ptr(ws), ws_bytes, rows, hidden, _dtype_code(hc), _stream(hc)),
               "l32_rmsnorm_backward_add")
+    if want_plain:
+        return dx.view(h.shape), dw, (dxp.view(h.shape) if dxp is not None else dx.view(h.shape))
     return dx.view(h.shape), dw
 
 
@@ -232,10 +236,14 @@ def ffn_forward(x, w_gate, w_up, w_down, b_gate=None, b_up=None, b_down=None, *,
     return y.view(x.shape), gate, up
 
 
-def block_tail_forward(attn_out, residual, norm_weight, eps, w_gate, w_up, w_down):
+def block_tail_forward(attn_out, residual, norm_weight, eps, w_gate, w_up, w_down, *, train=False, next_norm_weight=None,
+                       next_eps=1e-5):
     """out = attn_out + ff(rmsnorm(attn_out + residual) * norm_weight): the decoder-block tail in one C call
-    (reference Model/model.py:270-273), the final add fused into the down-GEMM epilogue.  Inference only."""
-    _check_cuda(attn_out, residual, norm_weight, w_gate, w_up, w_down)
+    (reference Model/model.py:270-273), the final add fused into the down-GEMM epilogue.
+    train: also return what the backward needs.  next_norm_weight: also return rmsnorm(out) * next_norm_weight -- the next
+    block's norm1 / final_norm (Model/model.py:267, :346) -- computed in the same call.
+    Returns out, or a dict(out, normed, h, rms, gate, up, next_normed, next_rms) when train or next_norm_weight is given."""
+    _check_cuda(attn_out, residual, norm_weight, w_gate, w_up, w_down, next_norm_weight)
     a2, tokens = _flat_tokens(attn_out)
     wg, wu, wd = _weight(w_gate, w_gate.dtype), _weight(w_up, w_up.dtype), _weight(w_down, w_down.dtype)
     hidden, inter = _check_ffn_weights(a2, wg, wu, wd)
@@ -243,14 +251,88 @@ def block_tail_forward(attn_out, residual, norm_weight, eps, w_gate, w_up, w_dow
     if r2 is not None and r2.shape != a2.shape:
         raise L32Error(f"residual shape {tuple(residual.shape)} != attn_out shape {tuple(attn_out.shape)}")
     w = _weight(norm_weight, a2.dtype)
-    out = torch.empty_like(a2)
-    normed = torch.empty_like(a2)
-    act = torch.empty(tokens, inter, dtype=a2.dtype, device=a2.device)
+    nw = None if next_norm_weight is None else _weight(next_norm_weight, a2.dtype)
+    new = lambda *shape, dt=a2.dtype: torch.empty(*shape, dtype=dt, device=a2.device)
+    out, normed, act = torch.empty_like(a2), torch.empty_like(a2), new(tokens, inter)
+    h = torch.empty_like(a2) if (train and r2 is not None) else None
+    rms = new(tokens, dt=torch.float32) if train else None
+    gate = new(tokens, inter) if train else None
+    up = new(tokens, inter) if train else None
+    nn = torch.empty_like(a2) if nw is not None else None
+    nrms = new(tokens, dt=torch.float32) if (nw is not None and train) else None
     with torch.cuda.device(a2.device):
-        check(lib().l32_block_tail_forward(_ptr(a2), _ptr(r2), _ptr(w), float(eps), _ptr(wg), _ptr(wu), _ptr(wd), _ptr(out),
-                                           _ptr(normed), _ptr(act), tokens, hidden, inter, _dtype_code(a2), _stream(a2)),
-              "l32_block_tail_forward")
-    return out.view(attn_out.shape)
+        check(lib().l32_block_tail_forward_ex(_ptr(a2), _ptr(r2), _ptr(w), float(eps), _ptr(wg), _ptr(wu), _ptr(wd), _ptr(out),
+                                              _ptr(normed), _ptr(act), _ptr(h), _ptr(rms), _ptr(gate), _ptr(up), _ptr(nw),
+                                              float(next_eps), _ptr(nn), _ptr(nrms), tokens, hidden, inter, _dtype_code(a2),
+                                              _stream(a2)), "l32_block_tail_forward_ex")
+    if not train and nw is None:
+        return out.view(attn_out.shape)
+    shp = attn_out.shape
+    return dict(out=out.view(shp), normed=normed.view(shp), h=(h.view(shp) if h is not None else (attn_out if train else None)),
+                rms=rms, gate=gate, up=up, next_normed=(nn.view(shp) if nn is not None else None), next_rms=nrms)
+
+
+def linear_lora_forward(x, weight, lora_a, lora_bs, bias=None, x_lora=None):
+    """y = x weight^T + bias + (x_lora lora_a^T) lora_bs^T, adapter fused into the base GEMM (lora_bs pre-scaled by
+    alpha / rank; x_lora = dropout(x) or None for x).  Returns (y, t [tokens, rank])."""
+    _check_cuda(x, weight, lora_a, lora_bs, bias, x_lora)
+    x2, tokens = _flat_tokens(x)
+    w = _weight(weight, weight.dtype)
+    out_f, in_f = w.shape
+    la, lb = lora_a.contiguous(), lora_bs.contiguous()
+    rank = la.shape[0]
+    if (x2.shape[1] != in_f or tuple(la.shape) != (rank, in_f) or tuple(lb.shape) != (out_f, rank) or
+            any(t.dtype != x2.dtype for t in (w, la, lb))):
+        raise L32Error(f"linear_lora: x[..., {x2.shape[1]}] {x2.dtype}, weight{tuple(w.shape)} {w.dtype}, lora_a{tuple(la.shape)} "
+                       f"{la.dtype}, lora_b{tuple(lb.shape)} {lb.dtype}")
+    xl = None
+    if x_lora is not None:
+        xl = x_lora.contiguous().view(-1, in_f)
+        if xl.shape != x2.shape or xl.dtype != x2.dtype:
+            raise L32Error("linear_lora: x_lora must be shaped and typed like x")
+    y = torch.empty(tokens, out_f, dtype=x2.dtype, device=x2.device)
+    t = torch.empty(tokens, rank, dtype=x2.dtype, device=x2.device)
+    b = None if bias is None else _weight(bias, x2.dtype)
+    with torch.cuda.device(x2.device):
+        check(lib().l32_linear_lora_forward(_ptr(x2), _ptr(xl), _ptr(w), _ptr(b), _ptr(la), _ptr(lb), _ptr(y), _ptr(t), tokens,
+                                            in_f, out_f, rank, _dtype_code(x2), _stream(x2)), "l32_linear_lora_forward")
+    return y.view(*x.shape[:-1], out_f), t
+
+
+def linear_lora_backward(grad_y, x_lora, weight, lora_a, lora_bs, t, *, want_dx=True, want_dlora=True, dx_addend_fn=None):
+    """(dx|None, dlora_a|None, dlora_bs|None) for linear_lora_forward with a frozen base weight.
+    dx_addend_fn(u) -> [tokens, in]: LoRA dropout -- the caller turns u = dy lora_bs into the masked adapter gradient
+    mask * (u lora_a) / (1 - p), which the base GEMM's epilogue adds; None = no dropout (adapter fused as a second phase)."""
+    _check_cuda(grad_y, x_lora, weight, lora_a, lora_bs, t)
+    w = _weight(weight, weight.dtype)
+    out_f, in_f = w.shape
+    la, lb = lora_a.contiguous(), lora_bs.contiguous()
+    rank = la.shape[0]
+    gy = grad_y.contiguous().view(-1, out_f)
+    if gy.dtype != w.dtype:
+        gy = gy.to(w.dtype)
+    tokens = gy.shape[0]
+    xl = x_lora.contiguous().view(-1, in_f)
+    new = lambda *shape: torch.empty(*shape, dtype=w.dtype, device=w.device)
+    u = new(tokens, rank)
+    dla = torch.empty_like(la) if want_dlora else None
+    dlb = torch.empty_like(lb) if want_dlora else None
+    L = lib()
+    args = (tokens, in_f, out_f, rank, _dtype_code(gy), _stream(gy))
+    with torch.cuda.device(gy.device):
+        if dx_addend_fn is None or not want_dx:
+            dx = new(tokens, in_f) if want_dx else None
+            check(L.l32_linear_lora_backward(_ptr(gy), _ptr(xl), _ptr(w), _ptr(la), _ptr(lb), _ptr(t.contiguous()), None, _ptr(dx),
+                                             _ptr(dla), _ptr(dlb), _ptr(u), *args), "l32_linear_lora_backward")
+        else:
+            # pass 1: u and the adapter gradients; the caller masks u lora_a; pass 2: dx = dy w + addend
+            check(L.l32_linear_lora_backward(_ptr(gy), _ptr(xl), _ptr(w), _ptr(la), _ptr(lb), _ptr(t.contiguous()), None, None,
+                                             _ptr(dla), _ptr(dlb), _ptr(u), *args), "l32_linear_lora_backward")
+            addend = dx_addend_fn(u).contiguous().view(tokens, in_f)
+            dx = new(tokens, in_f)
+            check(L.l32_linear_lora_backward(_ptr(gy), None, _ptr(w), _ptr(la), _ptr(lb), None, _ptr(addend), _ptr(dx), None, None,
+                                             None, *args), "l32_linear_lora_backward")
+    return dx, dla, dlb
 
 
 def ffn_backward(grad_y, x, w_gate, w_up, w_down, gate_cache, up_cache, *, want_dx=True, want_dw_gate_up=True,

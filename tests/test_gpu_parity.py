@@ -594,3 +594,146 @@ def test_reference_cuda_rmsnorm_ab():
     close(y, out_ref, (4e-3, 2.0 ** -8), "ours vs reference kernel")
     close(rms, rms_ref, (1e-3, 1e-3), "rms")
     assert O.rel_l2(y.float().cpu(), oracle) <= O.rel_l2(out_ref.float().cpu(), oracle) * 1.05
+
+
+# ----------------------------------------------------------------------------------------------- f1 / f2 rows of SURVEY 8(f)
+@pytest.mark.parametrize("tokens,hidden,inter,with_res,chained", [
+    (320, 256, 688, True, False), (320, 256, 688, True, True), (1000, 512, 1024, False, True), (64, 256, 688, True, True)])
+def test_block_tail_autograd_and_chained_norm(tokens, hidden, inter, with_res, chained):
+    """BlockTailFunction: out = attn_out + ff(norm2(attn_out, residual)) [+ the next block's norm1 in the same call],
+    forward and every gradient against autograd over the reference's expressions (Model/model.py:267-273, :346)."""
+    s = O.synthetic_ffn(tokens, hidden, inter, seed=tokens + inter)
+    g = torch.Generator().manual_seed(5)
+    gamma2 = O.bf16_representable(1 + 0.1 * torch.randn(hidden, generator=g))
+    d_next = O.bf16_representable(torch.randn(tokens, hidden, generator=g))
+    norm2 = L.LLAMARMSNorm(hidden, eps=1e-5).to(DEV, torch.bfloat16)
+    nxt = L.LLAMARMSNorm(hidden, eps=1e-5).to(DEV, torch.bfloat16)
+    ff = L.FusedFeedforward(hidden, inter).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        norm2.weight.copy_(dev(s["gamma"])); nxt.weight.copy_(dev(gamma2))
+        ff.swiglu.w_gate.copy_(dev(s["w_gate"])); ff.swiglu.w_up.copy_(dev(s["w_up"])); ff.w_down.weight.copy_(dev(s["w_down"]))
+    a = dev(s["x"]).requires_grad_(True)
+    r = dev(s["residual"]).requires_grad_(True) if with_res else None
+    out = L.block_tail(norm2, ff, a, r, next_norm=nxt if chained else None)
+    loss_terms = [(out, dev(s["dy"]))]
+    if chained:
+        assert getattr(out, "_l32_prenormed", None) is not None and out._l32_prenormed[0] is nxt
+        nn_ = nxt(out)                                   # consumed from the attachment, no second kernel
+        assert nn_ is out._l32_prenormed[1]
+        loss_terms.append((nn_, dev(d_next)))
+    torch.autograd.backward([t for t, _ in loss_terms], [gr for _, gr in loss_terms])
+    # oracle
+    leaves = {k: s[k].clone().requires_grad_(True) for k in ("x", "residual", "gamma", "w_gate", "w_up", "w_down")}
+    g2 = gamma2.clone().requires_grad_(True)
+    normed = O.add_rmsnorm(leaves["x"], leaves["gamma"], 1e-5, leaves["residual"] if with_res else None)
+    out_r = leaves["x"] + O.feedforward(normed, leaves["w_gate"], leaves["w_up"], leaves["w_down"])
+    terms = [(out_r, s["dy"])]
+    if chained:
+        terms.append((O.add_rmsnorm(out_r, g2, 1e-5), d_next))
+    torch.autograd.backward([t for t, _ in terms], [gr for _, gr in terms])
+    close(out, out_r, FWD, "block out")
+    if chained:
+        close(nn_, terms[1][0], FWD, "chained next norm")
+        close(nxt.weight.grad, g2.grad, BWD, "d next gamma")
+    close(a.grad, leaves["x"].grad, BWD, "d attn_out")
+    if with_res:
+        close(r.grad, leaves["residual"].grad, BWD, "d residual")
+    close(norm2.weight.grad, leaves["gamma"].grad, BWD, "d gamma")
+    close(ff.swiglu.w_gate.grad, leaves["w_gate"].grad, BWD, "dw_gate")
+    close(ff.swiglu.w_up.grad, leaves["w_up"].grad, BWD, "dw_up")
+    close(ff.w_down.weight.grad, leaves["w_down"].grad, BWD, "dw_down")
+
+
+def test_chained_stack_equals_unchained_stack():
+    """A stack of blocks wired with chain_block_norms gives bit-identical results to the same stack without the wiring (the
+    chained norm is the same kernel on the same bytes), in inference and under autograd."""
+    torch.manual_seed(3)
+    hidden, inter, tokens, nblocks = 256, 688, 200, 3
+
+    class Blk(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.norm1, self.norm2 = L.LLAMARMSNorm(hidden, 1e-5), L.LLAMARMSNorm(hidden, 1e-5)
+            self.ff = L.FusedFeedforward(hidden, inter)
+            self.mix = torch.nn.Linear(hidden, hidden, bias=False)       # stand-in for attention (not on this path)
+
+        def forward(self, hs):
+            attn_out = self.mix(self.norm1(hs))
+            return L.block_tail(self.norm2, self.ff, attn_out, hs, next_norm=getattr(self, "_l32_next_norm", None))
+
+    blocks = torch.nn.ModuleList([Blk() for _ in range(nblocks)]).to(DEV, torch.bfloat16)
+    final = L.LLAMARMSNorm(hidden, 1e-5).to(DEV, torch.bfloat16)
+    for m in list(blocks.modules()) + [final]:
+        if isinstance(m, L.LLAMARMSNorm):
+            with torch.no_grad():
+                m.weight.add_(0.1 * torch.randn_like(m.weight))
+    x = torch.randn(tokens, hidden, device=DEV).bfloat16()
+
+    def run(x_in):
+        hs = x_in
+        for b in blocks:
+            hs = b(hs)
+        return final(hs)
+
+    results = {}
+    for mode in ("plain", "chained"):
+        if mode == "chained":
+            L.chain_block_norms(blocks, final)
+        with torch.no_grad():
+            y_inf = run(x)
+        xin = x.clone().requires_grad_(True)
+        for p in list(blocks.parameters()) + list(final.parameters()):
+            p.grad = None
+        run(xin).backward(torch.ones_like(x))
+        results[mode] = (y_inf, xin.grad.clone(), blocks[0].ff.swiglu.w_gate.grad.clone(), final.weight.grad.clone())
+    for a, b, what in zip(results["plain"], results["chained"], ("y", "dx", "dw_gate[0]", "d final gamma")):
+        if what == "y":
+            assert torch.equal(a, b), what
+        else:
+            close(b, a, BWD, what)      # same math; the fused addends round once instead of twice (bf16, three blocks deep)
+
+
+@pytest.mark.parametrize("tokens,in_f,out_f,rank,p_drop,bias", [
+    (300, 256, 512, 16, 0.0, False), (1030, 512, 256, 8, 0.0, True), (256, 4096, 1024, 16, 0.05, False), (77, 256, 256, 64, 0.25, False)])
+def test_linear_lora_fused_any_projection(tokens, in_f, out_f, rank, p_drop, bias):
+    """Linear_LORA on any projection (q/k/v/out of the attention as well as w_down): base GEMM + rank-r adapter as ONE
+    kernel with two accumulation phases, LoRA dropout included, against autograd over Model/model.py:120-121."""
+    g = torch.Generator().manual_seed(tokens + rank)
+    bf = O.bf16_representable
+    x32, dy32 = bf(torch.randn(tokens, in_f, generator=g)), bf(torch.randn(tokens, out_f, generator=g))
+    w32 = bf((torch.rand(out_f, in_f, generator=g) * 2 - 1) / in_f ** 0.5)
+    a32 = bf(torch.randn(rank, in_f, generator=g) / in_f ** 0.5)
+    b32 = bf(0.05 * torch.randn(out_f, rank, generator=g))
+    bias32 = bf(0.1 * torch.randn(out_f, generator=g)) if bias else None
+    alpha = 32.0
+    lo = L.Linear_LORA(in_f, out_f, rank=rank, alpha=alpha, dropout=p_drop).to(DEV, torch.bfloat16)
+    if bias:
+        lo.linear.bias = torch.nn.Parameter(dev(bias32), requires_grad=False)
+    with torch.no_grad():
+        lo.linear.weight.copy_(dev(w32)); lo.lora_a.weight.copy_(dev(a32)); lo.lora_b.weight.copy_(dev(b32))
+    lo.train()
+    x = dev(x32).requires_grad_(True)
+    torch.manual_seed(99)
+    y = lo(x)
+    y.backward(dev(dy32))
+    # the mask the layer drew: same generator state, same shape / dtype / device
+    mask = torch.ones(tokens, in_f)
+    if p_drop > 0:
+        torch.manual_seed(99)
+        mask = (torch.empty_like(x).bernoulli_(1.0 - p_drop).float() / (1.0 - p_drop)).cpu()
+        assert 0.5 * p_drop < (mask == 0).float().mean().item() < 1.5 * p_drop + 0.02
+    xs, As, Bs = x32.clone().requires_grad_(True), a32.clone().requires_grad_(True), b32.clone().requires_grad_(True)
+    yr = torch.nn.functional.linear(xs, w32, bias32) + (alpha / rank) * torch.nn.functional.linear(
+        torch.nn.functional.linear(xs * mask, As), Bs)
+    yr.backward(dy32)
+    tol_f, tol_b = (1e-2, 2.0 ** -6), (1.5e-2, 2.0 ** -5)
+    close(y, yr, tol_f, "lora linear y")
+    close(x.grad, xs.grad, tol_b, "dx")
+    close(lo.lora_a.weight.grad, As.grad, tol_b, "dlora_a")
+    close(lo.lora_b.weight.grad, Bs.grad, tol_b, "dlora_b")
+    assert lo.linear.weight.grad is None
+    # eval mode: no dropout, no autograd -> inference path of the same kernels
+    lo.eval()
+    with torch.no_grad():
+        ye = lo(dev(x32))
+    close(ye, torch.nn.functional.linear(x32, w32, bias32) + (alpha / rank) * (x32 @ a32.t()) @ b32.t(), tol_f, "eval y")
