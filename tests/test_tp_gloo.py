@@ -14,6 +14,11 @@ from llama32_b200.tp import shard_range
 def test_shard_ranges_cover_and_align():
     for inter in (14336, 28672, 688, 104, 1000):
         for world in (1, 2, 4, 8):
+            if (inter, world) == (104, 8):   # 13 columns per rank round up to 16: the last rank would own nothing -> rejected
+                import pytest
+                with pytest.raises(ValueError):
+                    [shard_range(inter, world, r) for r in range(world)]
+                continue
             spans = [shard_range(inter, world, r) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == inter
             for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
