@@ -11,6 +11,24 @@ import torch.distributed as dist  # noqa: E402
 from llama32_b200.tp import FusedTensorParallelBlock, TpRankBuffers  # noqa: E402
 
 
+def nvlink_kib(index):
+    """Sum of the NVLink data counters of one GPU (KiB transmitted, KiB received) from `nvidia-smi nvlink -gt d`; None if
+    the tool / counters are unavailable.  Read before and after the timed loop: the difference is the NVLink traffic of the
+    loop as the hardware counted it (evidence for the bytes the fused kernels move, next to their algorithmic figure)."""
+    import re
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, text=True, timeout=20).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return None
+    tx = [int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+    rx = [int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+    if not tx or not rx:
+        return None
+    return sum(tx), sum(rx)
+
+
 def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "11b"
     tokens = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
@@ -42,6 +60,9 @@ def main():
     # phases give the steady-state per-phase times on each rank's GPU timeline.
     dist.barrier()
     torch.cuda.synchronize()
+    nv0 = nvlink_kib(local)
+    dist.barrier()            # reading the counters takes a different time on every rank: start the loop together
+    torch.cuda.synchronize()
     evs = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -63,6 +84,12 @@ def main():
         evs.append(ev)
     e1.record()
     torch.cuda.synchronize()
+    nv1 = nvlink_kib(local)
+    if nv0 is not None and nv1 is not None:
+        hidden_b = hidden * 2
+        alg = (world - 1) * (tokens // world) * hidden_b          # pulled per step (all-gather) = pushed per step (reduce-scatter)
+        print(f"[nvlink] rank {rank}: tx {(nv1[0] - nv0[0]) / iters / 1024:.1f} MiB/step rx {(nv1[1] - nv0[1]) / iters / 1024:.1f} MiB/step "
+              f"(algorithmic: {alg / 2 ** 20:.1f} MiB pulled + {alg / 2 ** 20:.1f} MiB pushed per step per rank)", flush=True)
     total = e0.elapsed_time(e1) / iters
     for ev in evs:
         for k in range(4):
