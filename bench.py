@@ -458,6 +458,37 @@ def extra_numbers(dev, peaks):
                                                  "frac_of_bf16_burst_peak": fl / t / 1e12 / peaks["bf16_tflops"]}
     del norm, ffn, lo, x, r, dy
     torch.cuda.empty_cache()
+
+    # ---- lm_head + shifted cross entropy at the 11B sizes: 8192 tokens, hidden 4096, vocab 128 256
+    V = 128256
+    head = torch.nn.Linear(H, V, bias=False).to(dev, dt)
+    hs = rnd(4, 2048, H)
+    labels = torch.randint(0, V, (4, 2048), device=dev, generator=gen)
+    fl = 2.0 * T * H * V
+
+    def ours_fwd():
+        with torch.no_grad():
+            L.lm_head_loss(head, hs, labels)
+
+    def eager_fwd():
+        with torch.no_grad():
+            logits = head(hs)
+            torch.nn.functional.cross_entropy(logits[..., :-1, :].reshape(-1, V), labels[..., 1:].reshape(-1), ignore_index=-100)
+
+    def ours_train():
+        x_ = hs.detach().requires_grad_(True)
+        head.weight.grad = None
+        L.lm_head_loss(head, x_, labels)[1].backward()
+    t_f = _time_cuda(ours_fwd, 5, warm=2)
+    t_e = _time_cuda(eager_fwd, 5, warm=2)
+    t_t = _time_cuda(ours_train, 5, warm=2)
+    out["lm_head_ce_11b_8192tok"] = {"fwd_ms": t_f * 1e3, "fwd_TFLOPs": fl / t_f / 1e12, "fwd_frac_of_bf16_burst_peak": fl / t_f / 1e12 / peaks["bf16_tflops"],
+                                     "fwd_ms_torch_eager": t_e * 1e3, "fwd_speedup_vs_torch_eager": t_e / t_f,
+                                     "fwd_bwd_ms": t_t * 1e3, "fwd_bwd_TFLOPs": 3 * fl / t_t / 1e12,
+                                     "what": "logits (bf16, stored) + mean shifted cross entropy in one tcgen05 GEMM whose epilogue gathers "
+                                             "the softmax statistics (Model/model.py:429-438); eager = nn.Linear + F.cross_entropy in bf16"}
+    del head, hs, labels
+    torch.cuda.empty_cache()
     return out
 
 

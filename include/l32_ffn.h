@@ -54,7 +54,7 @@ extern "C" {
 
 /* ABI version of this header (bumped on any signature change).  2: tensor-parallel, LoRA and block-tail entry points.
  * 3: tensor-parallel backward; the all-gather entry points accept an A buffer distinct from the published one;
- *    l32_rmsnorm_backward_add, l32_block_tail_forward_ex, l32_linear_lora_forward / _backward. */
+ *    l32_rmsnorm_backward_add, l32_block_tail_forward_ex, l32_linear_lora_forward / _backward, l32_lm_head_ce_*. */
 L32_API int l32_abi_version(void);
 /* Number of CUDA kernels this library has launched in the calling process so far (monotonic). */
 L32_API unsigned long long l32_kernel_launch_count(void);
@@ -223,6 +223,30 @@ L32_API int l32_linear_lora_forward(const void* x, const void* x_lora, const voi
 L32_API int l32_linear_lora_backward(const void* dy, const void* x_lora, const void* w, const void* lora_a, const void* lora_bs,
                                      const void* t, const void* dx_addend, void* dx, void* dlora_a, void* dlora_bs, void* u_out,
                                      int64_t tokens, int in_features, int out_features, int rank, int dtype, void* stream);
+
+/* lm_head + cross entropy.
+ * Replaces: `logits = self.language_model.lm_head(hidden_states)` followed by
+ *           `nn.CrossEntropyLoss(ignore_index)(shift_logits.view(-1, V), shift_labels.view(-1))`, Model/model.py:429-438
+ *           (lm_head = nn.Linear(hidden, vocab, bias=False), Model/model.py:354, tied to tok_emb by tie_weights, :363-364).
+ * ONE tcgen05 GEMM whose epilogue stores the logits (16-bit, the model's output) and gathers each row's softmax statistics
+ * per 256-column tile, then two tiny reductions: no fp32 [tokens, vocab] tensor and no second pass over the logits.
+ *   labels        : [tokens] int64, ALREADY SHIFTED by the caller (row (b, s) carries labels[b, s + 1], the last position
+ *                   of every sequence carries ignore_index); values outside [0, vocab) never match;
+ *   logits        : [tokens, vocab] in `dtype`;  lse : [tokens] fp32 log-sum-exp of the stored (rounded) logits;
+ *   loss_rows     : [tokens] fp32, lse - logit[label] (0 for ignored rows);
+ *   loss_and_count: [2] fp32 = { mean of loss_rows over the valid rows (nan when there is none, like torch), #valid rows };
+ *   workspace     : l32_lm_head_ce_workspace_bytes(tokens, vocab) bytes.
+ */
+L32_API size_t l32_lm_head_ce_workspace_bytes(int64_t tokens, int vocab);
+L32_API int l32_lm_head_ce_forward(const void* hidden_states, const void* w, const int64_t* labels, long long ignore_index,
+                                   void* logits, float* lse, float* loss_rows, float* loss_and_count, void* workspace,
+                                   size_t workspace_bytes, int64_t tokens, int hidden, int vocab, int dtype, void* stream);
+/* Backward: dlogits = (softmax(logits) - onehot(labels)) * grad_loss / #valid (from the stored logits and lse; `dlogits` may
+ * alias `logits`; grad_loss = DEVICE pointer to the fp32 upstream gradient of the scalar loss, NULL = 1), d_hidden = dlogits w (optional), dw = dlogits^T hidden_states (optional, [vocab, hidden]). */
+L32_API int l32_lm_head_ce_backward(const void* logits, const float* lse, const int64_t* labels, long long ignore_index,
+                                    const float* loss_and_count, const float* grad_loss, const void* hidden_states, const void* w,
+                                    void* dlogits, void* d_hidden, void* dw, int64_t tokens, int hidden, int vocab, int dtype,
+                                    void* stream);
 
 /* General tiled GEMM used by the entry points above (exposed for tests, tuning and the tensor-parallel
  * host code):  D[m,n] = A[m,k] B[n,k]^T  (+ A1 B1^T when a1 != NULL).

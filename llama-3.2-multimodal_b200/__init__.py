@@ -10,6 +10,7 @@ from .modules import (  # noqa: F401
     FusedFeedforward,
     FusedSwiGLU,
     LLAMARMSNorm,
+    LMHeadCEFunction,
     Linear_LORA,
     LinearFunction,
     LinearLoRAFunction,
@@ -19,11 +20,13 @@ from .modules import (  # noqa: F401
     chain_block_norms,
     convert_feedforward_to_fused,
     convert_instances,
+    lm_head_loss,
     patch_reference,
+    shift_labels,
 )
 
 __all__ = [
     "FFNFunction", "FFNLoRAFunction", "FusedFeedForward", "FusedFeedforward", "FusedSwiGLU", "LLAMARMSNorm", "Linear_LORA",
     "LinearFunction", "RMSNormFunction", "SwiGLUFunction", "block_tail", "convert_feedforward_to_fused", "convert_instances",
-    "patch_reference", "BlockTailFunction", "LinearLoRAFunction", "chain_block_norms",
+    "patch_reference", "BlockTailFunction", "LinearLoRAFunction", "chain_block_norms", "LMHeadCEFunction", "lm_head_loss", "shift_labels",
 ]

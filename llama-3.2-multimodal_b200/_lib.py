@@ -41,6 +41,11 @@ SIGNATURES = {
                                   [c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_linear_lora_forward": (c_int, [c_void_p] * 8 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "l32_linear_lora_backward": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    "l32_lm_head_ce_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "l32_lm_head_ce_forward": (c_int, [c_void_p] * 3 + [ctypes.c_longlong] + [c_void_p] * 5 + [c_size_t, c_int64, c_int, c_int, c_int,
+                                                                                             c_void_p]),
+    "l32_lm_head_ce_backward": (c_int, [c_void_p] * 3 + [ctypes.c_longlong, c_void_p, c_void_p] + [c_void_p] * 5 +
+                                [c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_ffn_backward_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "l32_ffn_backward": (c_int, [c_void_p] * 12 + [c_size_t, c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_ffn_lora_forward": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),

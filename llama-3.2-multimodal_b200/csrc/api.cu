@@ -587,6 +587,79 @@ int l32_linear_lora_backward(const void* dy, const void* x_lora, const void* w, 
     return rc;
 }
 
+size_t l32_lm_head_ce_workspace_bytes(int64_t tokens, int vocab) {
+    if (tokens < 0 || vocab <= 0) return 0;
+    const size_t tiles_n = static_cast<size_t>((vocab + 255) / 256);
+    return align256(static_cast<size_t>(tokens) * tiles_n * 8) + align256(static_cast<size_t>(tokens) * 4);
+}
+
+int l32_lm_head_ce_forward(const void* hidden_states, const void* w, const int64_t* labels, long long ignore_index, void* logits,
+                           float* lse, float* loss_rows, float* loss_and_count, void* workspace, size_t workspace_bytes,
+                           int64_t tokens, int hidden, int vocab, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, vocab)) return L32_ERR_BAD_SHAPE;
+    if (tokens == 0) return L32_OK;
+    if (hidden_states == nullptr || w == nullptr || labels == nullptr || logits == nullptr || lse == nullptr ||
+        loss_rows == nullptr || loss_and_count == nullptr)
+        return L32_ERR_NULL;
+    if (workspace == nullptr || workspace_bytes < l32_lm_head_ce_workspace_bytes(tokens, vocab) || !is_aligned16(workspace))
+        return L32_ERR_WORKSPACE;
+    const int tiles_n = (vocab + 255) / 256;
+    void* partials = workspace;
+    float* target = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + align256(static_cast<size_t>(tokens) * tiles_n * 8));
+    // logits = hidden_states w^T with the softmax statistics gathered in the epilogue (no second pass over [tokens, vocab])
+    GemmProblem g = blank(static_cast<int>(tokens), vocab, dtype);
+    g.k[0] = hidden;
+    g.a[0] = op(hidden_states, hidden, 0);
+    g.b[0] = op(w, hidden, 0);
+    g.epilogue = EPI_CE;
+    g.d[0] = logits;
+    g.ldd = vocab;
+    g.cta_group = 2;      // the statistics are laid out per 256-column tile of the paired kernel
+    g.ce.labels = reinterpret_cast<const long long*>(labels);
+    g.ce.partials = partials;
+    g.ce.target = target;
+    int rc = gemm_sm100(g, as_stream(stream));
+    if (rc != L32_OK) return rc;
+    return static_cast<int>(ce_reduce(partials, target, reinterpret_cast<const long long*>(labels), ignore_index, tokens, tiles_n,
+                                      vocab, lse, loss_rows, loss_and_count, as_stream(stream)));
+}
+
+int l32_lm_head_ce_backward(const void* logits, const float* lse, const int64_t* labels, long long ignore_index,
+                            const float* loss_and_count, const float* grad_loss, const void* hidden_states, const void* w,
+                            void* dlogits,
+                            void* d_hidden, void* dw, int64_t tokens, int hidden, int vocab, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (!shapes_ok(tokens, hidden, vocab)) return L32_ERR_BAD_SHAPE;
+    cudaStream_t s = as_stream(stream);
+    if (tokens == 0) {
+        if (dw != nullptr) return static_cast<int>(cudaMemsetAsync(dw, 0, static_cast<size_t>(vocab) * hidden * 2, s));
+        return L32_OK;
+    }
+    if (logits == nullptr || lse == nullptr || labels == nullptr || loss_and_count == nullptr || dlogits == nullptr)
+        return L32_ERR_NULL;
+    if ((d_hidden != nullptr && w == nullptr) || (dw != nullptr && hidden_states == nullptr)) return L32_ERR_NULL;
+    if (!is_aligned16(logits) || !is_aligned16(dlogits)) return L32_ERR_BAD_ALIGN;
+    cudaError_t e = ce_backward_logits(logits, lse, reinterpret_cast<const long long*>(labels), ignore_index, loss_and_count,
+                                       grad_loss, dlogits, tokens, vocab, dtype, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int t = static_cast<int>(tokens);
+    int rc = L32_OK;
+    if (d_hidden != nullptr) {   // d_hidden = dlogits w   (w [vocab, hidden] consumed as an MN-major B operand)
+        GemmProblem g = blank(t, hidden, dtype);
+        g.k[0] = vocab;
+        g.a[0] = op(dlogits, vocab, 0);
+        g.b[0] = op(w, hidden, 1);
+        g.epilogue = EPI_STORE;
+        g.d[0] = d_hidden;
+        g.ldd = hidden;
+        rc = gemm_sm100(g, s);
+        if (rc != L32_OK) return rc;
+    }
+    if (dw != nullptr) rc = wgrad(dlogits, vocab, hidden_states, hidden, dw, t, dtype, s);   // [vocab, hidden] = dlogits^T h
+    return rc;
+}
+
 int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t ldb, int b_mn_major, const void* a1,
              int64_t lda1, const void* b1, int64_t ldb1, void* d, int64_t ldd, int m, int n, int k, int k1, int dtype,
              int cta_group, int max_ctas, void* stream) {

@@ -83,6 +83,9 @@ struct GemmKernelParams {
     int ffn_prefix;         // gate/up-only tiles at the head of every mixed round
     uint32_t idesc_dn;
     uint32_t* act_done;
+    const long long* ce_labels;   // EPI_CE: target column of every row (int64; anything outside [0, n) never matches)
+    float2* ce_partials;          // EPI_CE: [m][tiles_n] (max, sum of exp(v - max)) of the tile's columns of that row
+    float* ce_target;             // EPI_CE: [m] logit of the target column (written by the tile that holds it)
     int debug_flags;          // experiments only (L32_BWD_DEBUG): 1 = skip the output stores, 2 = skip the cache loads
     CUtensorMap map_out[3];   // EPI_SWIGLU_BWD: d_gate / d_up / act as [m, n] tensors, box {16 cols, 32 rows}, 32-byte swizzle
     unsigned long long spin_timeout_ns;   // bound of every cross-SM / cross-GPU flag wait
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     constexpr int kStages = Cfg::kStages;
     constexpr bool kTp = (kEpi == EPI_FFN_TP);
     const int kTileNOut = (kEpi == EPI_SWIGLU || kTp) ? p.n_act : 256;   // output columns per (gate/up) tile
-    constexpr int kEpiWarps = (kEpi == EPI_STORE) ? 4 : 8;        // epilogue warps per CTA that take part
+    constexpr int kEpiWarps = (kEpi == EPI_STORE || kEpi == EPI_CE) ? 4 : 8;        // epilogue warps per CTA that take part
     // bytes the pair's TMA loads deliver per ring stage (EPI_SWIGLU stages n_act gate + n_act up weight rows)
     const uint32_t stage_tx_full = static_cast<uint32_t>(Cfg::kStageBytes * kCtaGroup);
     const uint32_t stage_tx = (kEpi == EPI_SWIGLU || kTp) ? static_cast<uint32_t>(kCtaGroup * Cfg::kABytes + 2 * p.n_act * 128)
@@ -447,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         for (int t = cluster_id; t < num_tiles; t += num_clusters) {
             const TileCoord tc = get_tile(t);
             const bool dn = kTp && tc.prob == 1;
-            const bool store_tile = (kEpi == EPI_STORE) || dn;
+            const bool store_tile = (kEpi == EPI_STORE) || (kEpi == EPI_CE) || dn;
             const bool swiglu_tile = (kEpi == EPI_SWIGLU) || (kTp && !dn);
             const int tile_n = dn ? p.n_dn : p.n;                              // valid output columns of this problem
             const size_t tile_ldd = static_cast<size_t>(dn ? p.n_dn : p.ldd);  // and its row pitch
@@ -507,6 +510,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                     }
                 }
                 const uint8_t* add_row = (!kTp && p.e[0] != nullptr) ? static_cast<const uint8_t*>(p.e[0]) + row_off * esz : nullptr;
+                // EPI_CE (lm_head + cross entropy): besides storing the logits, every row keeps a running (max, sum of exp) over
+                // the tile's columns -- of the values ROUNDED to the storage type, so that the softmax the backward forms from
+                // the stored logits sums to one -- and the tile that holds the row's target column records that logit.
+                float ce_m = -INFINITY, ce_s = 0.f, ce_t = 0.f;
+                bool ce_hit = false;
+                long long ce_lab = -1;
+                if constexpr (kEpi == EPI_CE) {
+                    if (row_ok) ce_lab = p.ce_labels[row];
+                }
 #pragma unroll 1
                 for (int c = 0; c < kAccCols / 128; ++c) {
                     const int col = n0 + c * 128;
@@ -529,6 +541,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                             }
                             o[j] = Pack2<T>::pack(lo, hi);
                         }
+                        if constexpr (kEpi == EPI_CE) {
+                            float r[32];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float2 f = Pack2<T>::unpack(o[j]);
+                                r[2 * j] = f.x; r[2 * j + 1] = f.y;
+                            }
+                            float cm = -INFINITY;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (pcol + j < tile_n) cm = fmaxf(cm, r[j]);
+                            const float nm = fmaxf(ce_m, cm);
+                            float acc = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (pcol + j < tile_n) acc += __expf(r[j] - nm);
+                            ce_s = ce_s * __expf(ce_m - nm) + acc;   // first chunk: ce_s = 0, exp(-inf) = 0
+                            ce_m = nm;
+                            const long long d = ce_lab - pcol;
+                            if (d >= 0 && d < 32 && ce_lab < tile_n) {
+                                ce_hit = true;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) if (j == static_cast<int>(d)) ce_t = r[j];
+                            }
+                        }
                         if (add_row != nullptr && row_ok) {   // fused "+ addend" (block tail: attn_out + ff_out, model.py:273)
                             uint32_t ad[16];
                             load_row32(add_row + static_cast<size_t>(pcol) * esz, ad, tile_n - pcol);
@@ -548,6 +583,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                         bulk_store_row(d_row + static_cast<size_t>(col) * esz, my_row, static_cast<uint32_t>(ncols) * static_cast<uint32_t>(esz));
                     }
                     bulk_store_commit();
+                }
+                if constexpr (kEpi == EPI_CE) {
+                    if (row_ok) {
+                        p.ce_partials[static_cast<size_t>(row) * p.tiles_n + tc.n_blk] = make_float2(ce_m, ce_s);
+                        if (ce_hit) p.ce_target[row] = ce_t;
+                    }
                 }
               }
             } else if (swiglu_tile) {
@@ -681,7 +722,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             acc ^= 1u;
             if (acc == 0) acc_phase ^= 1u;
         }
-        if (kEpi == EPI_STORE || kEpi == EPI_SWIGLU_BWD || kTp) bulk_store_wait_read();   // shared memory must outlive the last bulk stores
+        if (kEpi == EPI_STORE || kEpi == EPI_CE || kEpi == EPI_SWIGLU_BWD || kTp) bulk_store_wait_read();   // shared memory must outlive the last bulk stores
     }
 
     __syncwarp();
@@ -771,6 +812,7 @@ template <int kCtaGroup, typename T>
 int launch_epi(const GemmKernelParams& kp, int epi, int num_tiles, int max_ctas, cudaStream_t s) {
     switch (epi) {
         case EPI_STORE: return launch<kCtaGroup, EPI_STORE, T>(kp, num_tiles, max_ctas, s);
+        case EPI_CE: return launch<kCtaGroup, EPI_CE, T>(kp, num_tiles, max_ctas, s);
         case EPI_SWIGLU: return launch<kCtaGroup, EPI_SWIGLU, T>(kp, num_tiles, max_ctas, s);
         case EPI_SWIGLU_BWD: return launch<kCtaGroup, EPI_SWIGLU_BWD, T>(kp, num_tiles, max_ctas, s);
         case EPI_FFN_TP:
@@ -961,6 +1003,13 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
             int rc = make_tensor_map_2d(&kp.map_b[i], g.b[i].ptr, g.n, g.k[0], g.b[i].ld, n_act, kBlockK, g.dtype);
             if (rc != L32_OK) return rc;
         }
+    }
+    if (g.epilogue == EPI_CE) {
+        if (g.ce.labels == nullptr || g.ce.partials == nullptr || g.ce.target == nullptr) return L32_ERR_NULL;
+        if (g.e[0] != nullptr || g.bias[0] != nullptr || g.rs.world > 0 || g.ag.world > 0) return L32_ERR_BAD_SHAPE;
+        kp.ce_labels = g.ce.labels;
+        kp.ce_partials = static_cast<float2*>(g.ce.partials);
+        kp.ce_target = g.ce.target;
     }
     if (g.epilogue == EPI_SWIGLU_BWD) {
         for (int i = 0; i < 3; ++i) {

@@ -37,6 +37,8 @@ enum : int {
     EPI_STORE = 0,       // D -> d[0]                                     (tile 128*cta_group x 256)
     EPI_SWIGLU = 1,      // b[0]=gate weights, b[1]=up weights; act = silu(g)*u -> d[0]; optional g -> d[1], u -> d[2]
     EPI_SWIGLU_BWD = 2,  // D = d_act; e[0]=gate cache, e[1]=up cache; d_gate -> d[0], d_up -> d[1], optional act -> d[2]
+    EPI_CE = 4,          // EPI_STORE (logits -> d[0]) + per-row, per-column-tile softmax statistics and the target logit
+                         // (GemmProblem::ce): lm_head + cross entropy without a second pass over the logits
     EPI_FFN_TP = 3,      // tensor-parallel feed-forward in ONE kernel: the EPI_SWIGLU problem (act -> d[0]) and the down
                          // projection of that act (GemmProblem::dn, reduce-scatter epilogue) share the persistent tile loop,
                          // the down tiles of one group of rows interleaved with the gate/up tiles of the next group
@@ -82,6 +84,13 @@ struct TpFfnDown {
     uint32_t* act_done;     // [ceil(m / 256)] arrival counters, ZERO on entry: epilogue warps that finished act tiles
 };
 
+// EPI_CE: lm_head + cross entropy.  partials: [m][ceil(n / 256)] float2 (max, sum exp(v - max)); target: [m] floats.
+struct CeOutputs {
+    const long long* labels;   // [m] int64 target column per row (out-of-range = no target, e.g. ignore_index)
+    void* partials;
+    float* target;
+};
+
 struct GemmProblem {
     int m, n;               // D is [m, n]; for EPI_SWIGLU n = intermediate size (act columns)
     int num_phases;         // 1, or 2 for D = A0*B0^T + A1*B1^T (EPI_SWIGLU: must be 1)
@@ -101,6 +110,7 @@ struct GemmProblem {
     TpAllGather ag;         // ag.world == 0: off
     TpReduceScatter rs;     // rs.world == 0: off (EPI_STORE and the down half of EPI_FFN_TP)
     TpFfnDown dn;           // EPI_FFN_TP only
+    CeOutputs ce;           // EPI_CE only
 };
 int gemm_sm100(const GemmProblem& p, cudaStream_t s);   // returns L32_* / cudaError_t
 void debug_tile_order(int t, int tiles_m, int tiles_n, int group, int m_rotate, int il_world, int il_tpc, int il_rank, int* out3);
@@ -117,6 +127,13 @@ int ffn_decode_swiglu(const void* x, const void* w_gate, const void* w_up, const
                       void* gate_cache, void* up_cache, int tokens, int hidden, int inter, int dtype, cudaStream_t s);
 int ffn_decode_linear(const void* a, const void* w, const void* bias, const void* addend, void* y, int tokens,
                       int in_features, int out_features, int dtype, cudaStream_t s);
+
+// ---- lmhead.cu : cross-entropy reductions around the EPI_CE GEMM
+cudaError_t ce_reduce(const void* partials, const float* target, const long long* labels, long long ignore_index, int64_t rows,
+                      int tiles_n, int vocab, float* lse, float* loss_rows, float* loss_and_count, cudaStream_t s);
+cudaError_t ce_backward_logits(const void* logits, const float* lse, const long long* labels, long long ignore_index,
+                               const float* loss_and_count, const float* grad_loss, void* dlogits, int64_t rows, int vocab,
+                               int dtype, cudaStream_t s);
 
 // ---- tp.cu : tensor-parallel glue (cross-GPU flags, reduction of the partial slots)
 cudaError_t tp_signal(void* const* peer_flags, int world, int index, uint32_t value, uint32_t* zero8, cudaStream_t s);

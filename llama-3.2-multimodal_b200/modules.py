@@ -24,7 +24,7 @@ from . import ops
 __all__ = [
     "RMSNormFunction", "LLAMARMSNorm", "SwiGLUFunction", "FusedSwiGLU", "LinearFunction", "Linear_LORA", "FFNFunction", "FFNLoRAFunction",
     "FusedFeedforward", "FusedFeedForward", "convert_feedforward_to_fused", "patch_reference", "convert_instances", "block_tail",
-    "BlockTailFunction", "LinearLoRAFunction", "chain_block_norms",
+    "BlockTailFunction", "LinearLoRAFunction", "chain_block_norms", "LMHeadCEFunction", "lm_head_loss", "shift_labels",
 ]
 
 
@@ -480,6 +480,78 @@ def chain_block_norms(blocks, final_norm=None):
         object.__setattr__(blk, "_l32_next_norm", nxt if isinstance(nxt, LLAMARMSNorm) else None)
 
 
+# ------------------------------------------------------------------------------------------------ lm_head + loss
+def shift_labels(labels, ignore_index=-100):
+    """Row-aligned targets for `shift_logits = logits[..., :-1, :]` / `shift_labels = labels[..., 1:]` (reference
+    Model/model.py:432-433): position (b, s) is scored against labels[b, s + 1]; the last position of every sequence has no
+    target.  Same shape as `labels`."""
+    out = torch.full_like(labels, ignore_index)
+    out[..., :-1] = labels[..., 1:]
+    return out
+
+
+class LMHeadCEFunction(torch.autograd.Function):
+    """(loss, logits) = lm_head + mean cross entropy over the non-ignored rows (reference Model/model.py:429-438) on the
+    tcgen05 GEMM whose epilogue gathers the softmax statistics.  `logits` is returned for the caller's output dict and is
+    not differentiable here (the reference's training recipe back-propagates the loss only)."""
+
+    @staticmethod
+    def forward(ctx, hidden_states, weight, labels_shifted, ignore_index):
+        r = ops.lm_head_ce_forward(hidden_states, weight, labels_shifted, ignore_index)
+        ctx.save_for_backward(hidden_states, weight, labels_shifted, r["logits"], r["lse"], r["loss_and_count"])
+        ctx.ignore_index = ignore_index
+        ctx.mark_non_differentiable(r["logits"])
+        return r["loss"], r["logits"]
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_logits):
+        hidden_states, weight, labels_shifted, logits, lse, lc = ctx.saved_tensors
+        nh, nw, _, _ = ctx.needs_input_grad
+        # the upstream gradient of the scalar loss stays on the device (no host synchronisation): the dlogits kernel reads it
+        dh, dw, _ = ops.lm_head_ce_backward(logits, lse, labels_shifted, ctx.ignore_index, lc, grad_loss, hidden_states, weight,
+                                            want_dhidden=nh, want_dweight=nw)
+        return dh, dw, None, None
+
+
+def lm_head_loss(lm_head, hidden_states, labels=None, ignore_index=-100):
+    """`logits = lm_head(hidden_states)` and, with labels, the shifted cross entropy of the reference's
+    MllamaForConditionalGeneration.forward (Model/model.py:429-438).  Returns (logits, loss|None).
+    16-bit CUDA tensors with a bias-free head run the fused GEMM + CE kernels; anything else evaluates the reference's own
+    expressions."""
+    w = lm_head.weight
+    fused = (labels is not None and ops.supported(hidden_states) and w.is_cuda and w.dtype == hidden_states.dtype and
+             getattr(lm_head, "bias", None) is None and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0 and hidden_states.numel() > 0)
+    if not fused:
+        logits = lm_head(hidden_states)
+        loss = None
+        if labels is not None:
+            sl = logits[..., :-1, :].contiguous()
+            tl = labels[..., 1:].contiguous()
+            loss = nn.CrossEntropyLoss(ignore_index=ignore_index)(sl.view(-1, sl.size(-1)), tl.view(-1))
+        return logits, loss
+    loss, logits = LMHeadCEFunction.apply(hidden_states, w, shift_labels(labels, ignore_index), ignore_index)
+    return logits, loss
+
+
+def _mllama_forward(self, input_ids=None, pixel_values=None, attention_mask=None, position_ids=None, image_mask=None,
+                    labels=None, kv_cache=None, **kwargs):
+    """The reference's MllamaForConditionalGeneration.forward (Model/model.py:398-440) with its last eight lines -- lm_head and
+    the shifted CrossEntropyLoss -- replaced by `lm_head_loss`; everything before is the reference's own code path."""
+    image_features = None
+    if pixel_values is not None:
+        image_features = self.multi_modal_projector(self.vision_model(pixel_values))
+    inputs_embeds = None
+    if input_ids is not None:
+        inputs_embeds = self.language_model.model.get_input_embeddings()(input_ids)
+    if image_features is not None and inputs_embeds is not None:
+        inputs_embeds, attention_mask = self._merge_input_ids_with_image_features(image_features, inputs_embeds, input_ids,
+                                                                                  attention_mask)
+    hidden_states = self.language_model.model(input_embeds=inputs_embeds, attention_mask=attention_mask,
+                                              position_ids=position_ids, kv_cache=kv_cache)
+    logits, loss = lm_head_loss(self.language_model.lm_head, hidden_states, labels, getattr(self, "ignore_index", -100))
+    return {"logits": logits, "loss": loss, "hidden_states": hidden_states, "kv_cache": kv_cache}
+
+
 FusedFeedForward = FusedFeedforward   # the reference spells it both ways (FusedSwiglu.py:94 vs model.py:210)
 
 
@@ -516,6 +588,8 @@ def patch_reference(model_module, swiglu_module=None, fuse_block_tail=True):
     model_module.HAS_RMSNORM_EXT = True
     if fuse_block_tail and hasattr(model_module, "TransformerBlock"):
         model_module.TransformerBlock.forward = _transformer_block_forward
+    if fuse_block_tail and hasattr(model_module, "MllamaForConditionalGeneration"):
+        model_module.MllamaForConditionalGeneration.forward = _mllama_forward
     if swiglu_module is not None:
         swiglu_module.SwiGLUFunction = SwiGLUFunction
         swiglu_module.FusedSwiGLU = FusedSwiGLU
@@ -539,9 +613,10 @@ def convert_instances(root: nn.Module) -> nn.Module:
         elif name == "Linear_LORA" and not isinstance(m, Linear_LORA):
             m.__class__ = Linear_LORA
     # chain every stack of decoder blocks into the norm that follows it (a `layers` ModuleList next to a `final_norm`)
+    # (the reference's Llama3Model keeps them in `trf_blocks`, Model/model.py:296-299)
     for m in root.modules():
-        layers = getattr(m, "layers", None)
-        if isinstance(layers, nn.ModuleList) and len(layers) and all(hasattr(b, "norm1") and hasattr(b, "norm2") and hasattr(b, "ff")
-                                                                    for b in layers):
-            chain_block_norms(layers, getattr(m, "final_norm", None))
+        for child in m.children():
+            if (isinstance(child, nn.ModuleList) and len(child) and
+                    all(hasattr(b, "norm1") and hasattr(b, "norm2") and hasattr(b, "ff") for b in child)):
+                chain_block_norms(child, getattr(m, "final_norm", None))
     return root

@@ -414,6 +414,57 @@ def ffn_lora_backward(grad_y, x, w_gate, w_up, w_down, lora_a, lora_bs, t, gate_
     return (dx.view(x.shape) if dx is not None else None), dwg, dwu, dla, dlb
 
 
+# --------------------------------------------------------------------------------------------- lm_head + cross entropy
+def lm_head_ce_forward(hidden_states, weight, labels_shifted, ignore_index=-100):
+    """logits = hidden_states weight^T and the mean cross entropy against `labels_shifted` (int64, one per token row, already
+    shifted; ignore_index rows do not count) in one GEMM + two tiny reductions.
+    Returns dict(logits [.., vocab], loss (0-dim fp32), lse [tokens], loss_rows [tokens], loss_and_count [2])."""
+    _check_cuda(hidden_states, weight, labels_shifted)
+    h2, tokens = _flat_tokens(hidden_states)
+    w = _weight(weight, weight.dtype)
+    vocab, hidden = w.shape
+    if h2.shape[1] != hidden or w.dtype != h2.dtype:
+        raise L32Error(f"lm_head: hidden_states[..., {h2.shape[1]}] {h2.dtype} vs weight{tuple(w.shape)} {w.dtype}")
+    lab = labels_shifted.contiguous().view(-1)
+    if lab.dtype != torch.int64 or lab.numel() != tokens:
+        raise L32Error(f"lm_head: labels must be int64 with one entry per token row ({lab.dtype}, {lab.numel()} vs {tokens})")
+    dev = h2.device
+    logits = torch.empty(tokens, vocab, dtype=h2.dtype, device=dev)
+    lse = torch.empty(tokens, dtype=torch.float32, device=dev)
+    loss_rows = torch.empty(tokens, dtype=torch.float32, device=dev)
+    lc = torch.empty(2, dtype=torch.float32, device=dev)
+    L = lib()
+    ws_bytes = L.l32_lm_head_ce_workspace_bytes(tokens, vocab)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(L.l32_lm_head_ce_forward(_ptr(h2), _ptr(w), _ptr(lab), int(ignore_index), _ptr(logits), _ptr(lse), _ptr(loss_rows),
+                                       _ptr(lc), _ptr(ws), ws_bytes, tokens, hidden, vocab, _dtype_code(h2), _stream(h2)),
+              "l32_lm_head_ce_forward")
+    return dict(logits=logits.view(*hidden_states.shape[:-1], vocab), loss=lc[0], lse=lse, loss_rows=loss_rows, loss_and_count=lc)
+
+
+def lm_head_ce_backward(logits, lse, labels_shifted, ignore_index, loss_and_count, grad_loss, hidden_states, weight, *,
+                        want_dhidden=True, want_dweight=True, in_place=False):
+    """(d_hidden|None, d_weight|None, dlogits) of the mean cross entropy scaled by `grad_loss` (fp32 device scalar or None)."""
+    _check_cuda(logits, lse, labels_shifted, hidden_states, weight)
+    h2, tokens = _flat_tokens(hidden_states)
+    w = _weight(weight, weight.dtype)
+    vocab, hidden = w.shape
+    lg = logits.contiguous().view(tokens, vocab)
+    lab = labels_shifted.contiguous().view(-1)
+    dlogits = lg if in_place else torch.empty_like(lg)
+    dh = torch.empty_like(h2) if want_dhidden else None
+    dw = torch.empty_like(w) if want_dweight else None
+    gl = None
+    if grad_loss is not None:
+        gl = grad_loss.detach().to(device=h2.device, dtype=torch.float32).reshape(1).contiguous()
+    with torch.cuda.device(h2.device):
+        check(lib().l32_lm_head_ce_backward(_ptr(lg), _ptr(lse), _ptr(lab), int(ignore_index), _ptr(loss_and_count), _ptr(gl),
+                                            _ptr(h2), _ptr(w), _ptr(dlogits), _ptr(dh), _ptr(dw), tokens, hidden, vocab,
+                                            _dtype_code(h2), _stream(h2)), "l32_lm_head_ce_backward")
+    return (dh.view(hidden_states.shape) if dh is not None else None), dw, dlogits
+
+
 def gemm(a, b, *, a_mn_major=False, b_mn_major=False, a1=None, b1=None, cta_group=0, max_ctas=0):
     """D[m,n] = A B^T (+ A1 B1^T).  K-major operand: tensor [rows, k]; MN-major operand: tensor [k, rows]."""
     _check_cuda(a, b, a1, b1)

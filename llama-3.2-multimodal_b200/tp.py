@@ -53,6 +53,26 @@ def shard_ffn_weights(w_gate, w_up, w_down, world: int, rank: int):
     return w_gate[lo:hi], w_up[lo:hi], w_down[:, lo:hi].contiguous()
 
 
+def shard_state_dict_for_rank(state, world: int, rank: int):
+    """Load-time packing: the reference's loader builds a full `converted_state` and hands it to
+    load_state_dict (Model/utils.py:149-166); under tensor parallelism a rank only needs its slice of every feed-forward
+    weight.  This cuts `*.swiglu.w_gate` / `*.swiglu.w_up` (row slices) and `*.w_down.weight` (column slice, made contiguous)
+    down to rank `rank`'s shard while the tensors are still on the host (or memory-mapped safetensors slices), so the full
+    matrices never reach the device and FusedTensorParallelBlock(..., presharded=True) takes them as they are.
+    Every other entry is passed through untouched.  Returns a new dict."""
+    out = {}
+    for name, t in state.items():
+        if name.endswith("swiglu.w_gate") or name.endswith("swiglu.w_up"):
+            lo, hi = shard_range(t.shape[0], world, rank)
+            out[name] = t[lo:hi].contiguous()
+        elif name.endswith("w_down.weight") or name.endswith("w_down.linear.weight"):
+            lo, hi = shard_range(t.shape[1], world, rank)
+            out[name] = t[:, lo:hi].contiguous()
+        else:
+            out[name] = t
+    return out
+
+
 class TensorParallelFFN(torch.nn.Module):
     """Drop-in for FusedFeedforward.forward on `group`: same input, same (replicated) output."""
 
@@ -220,8 +240,9 @@ class FusedTensorParallelBlock:
     """norm2(x, residual) -> feed-forward of one rank, collectives fused into the GEMM kernels (see above).
     Inference: forward().  Training: forward_train() / backward(), or `apply()` which wires both into autograd."""
 
-    def __init__(self, gamma, eps, w_gate, w_up, w_down, bufs: TpRankBuffers, one_kernel: bool = False):
-        """gamma [H]; w_gate / w_up / w_down are the FULL matrices ([I,H], [I,H], [H,I]); the shard is taken here.
+    def __init__(self, gamma, eps, w_gate, w_up, w_down, bufs: TpRankBuffers, one_kernel: bool = False, presharded: bool = False):
+        """gamma [H]; w_gate / w_up / w_down are the FULL matrices ([I,H], [I,H], [H,I]); the shard is taken here -- unless
+        `presharded`: then they already are this rank's shard ([I/p,H], [I/p,H], [H,I/p], see shard_state_dict_for_rank).
         one_kernel: run gate/up and down as ONE persistent kernel (l32_tp_ffn_forward_fused) instead of two.  Measured
         at 8 GPUs: equal within 2-5 % either way -- the two-kernel path already hides both
         collectives -- so the simpler two-kernel path is the default."""
@@ -229,7 +250,10 @@ class FusedTensorParallelBlock:
         self.one_kernel = one_kernel
         self.eps = eps
         self.gamma = gamma
-        wg, wu, wd = shard_ffn_weights(w_gate, w_up, w_down, bufs.world, bufs.rank)
+        if presharded:
+            wg, wu, wd = w_gate, w_up, w_down.contiguous()
+        else:
+            wg, wu, wd = shard_ffn_weights(w_gate, w_up, w_down, bufs.world, bufs.rank)
         self.w_gate, self.w_up, self.w_down = wg.contiguous(), wu.contiguous(), wd
         self._epoch = 0
         self._act = None

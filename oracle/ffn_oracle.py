@@ -11,6 +11,7 @@ not a 16-bit CUDA tensor (which, for the FFN, is always: SURVEY.md section 0.1):
     feedforward   <- FusedFeedforward.forward                  reference Model/model.py:216-217
     block_hot_path<- TransformerBlock.forward lines norm2/ff   reference Model/model.py:270-273
     linear_lora   <- Linear_LORA.forward                       reference Model/model.py:120-121
+    lm_head_shifted_ce <- MllamaForConditionalGeneration.forward tail   reference Model/model.py:429-438
 The arithmetic itself lives in the third-party dependency torch (reference setup.py:47 `torch>=2.0.0`;
 installed here: 2.11.0+cu128): F.linear, F.silu, rsqrt, mean.  Gradients: the reference's own backward
 functions cannot run on any path, so the gradient oracle is autograd over these
@@ -70,6 +71,18 @@ def block_hot_path(attn_out, hidden_states, norm2_weight, eps, w_gate, w_up, w_d
     normed = add_rmsnorm(attn_out, norm2_weight, eps, residual=hidden_states)
     ff_out = feedforward(normed, w_gate, w_up, w_down)
     return normed, ff_out, attn_out + ff_out
+
+
+def lm_head_shifted_ce(hidden_states, lm_head_weight, labels, ignore_index=-100):
+    """reference Model/model.py:429-438: logits = lm_head(hidden_states) (nn.Linear, bias=False, model.py:354);
+    shift_logits = logits[..., :-1, :]; shift_labels = labels[..., 1:]; CrossEntropyLoss(ignore_index) over the flattened rows.
+    Returns (logits, loss)."""
+    logits = F.linear(hidden_states, lm_head_weight)
+    shift_logits = logits[..., :-1, :].contiguous()
+    shift_labels = labels[..., 1:].contiguous()
+    loss = torch.nn.CrossEntropyLoss(ignore_index=ignore_index)(shift_logits.view(-1, shift_logits.size(-1)),
+                                                                shift_labels.view(-1))
+    return logits, loss
 
 
 # ------------------------------------------------------------------------------------------------ gradients

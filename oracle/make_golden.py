@@ -174,7 +174,38 @@ def golden_mllama_cfg1():
          source="reference Model/model.py:398-440 MllamaForConditionalGeneration.forward, config 1")
 
 
+def golden_lm_head_loss():
+    """The tail of the reference's own MllamaForConditionalGeneration.forward (Model/model.py:429-438): logits and the
+    shifted cross-entropy loss of the config-1 model WITH labels (some of them ignore_index)."""
+    torch.manual_seed(2025)
+    vision_cfg = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, image_size=28,
+                      patch_size=14)
+    text_cfg = dict(vocab_size=512, hidden_size=256, n_heads=8, n_layers=2, hidden_dim=688, n_kv_groups=2,
+                    dtype=torch.float32)
+    cfg = M.MLLAMAConfig(vision_config=vision_cfg, text_config=text_cfg, projection_dim=256, image_token_index=511)
+    model = M.MllamaForConditionalGeneration(cfg).eval()
+    with torch.no_grad():
+        model.language_model.lm_head.weight.copy_(rep(model.language_model.lm_head.weight))
+    ids = torch.randint(0, 500, (3, 24))
+    labels = ids.clone()
+    labels[:, :5] = model.ignore_index
+    labels[1, 17:] = model.ignore_index
+    with torch.no_grad():
+        out = model(input_ids=ids, attention_mask=torch.ones_like(ids), labels=labels)
+    hs = rep(out["hidden_states"])
+    # the same tail on bf16-representable hidden states (what the fixture stores), through the reference's own modules
+    with torch.no_grad():
+        logits = model.language_model.lm_head(hs)
+        loss = torch.nn.CrossEntropyLoss(ignore_index=model.ignore_index)(
+            logits[..., :-1, :].contiguous().view(-1, logits.size(-1)), labels[..., 1:].contiguous().view(-1))
+    save("lm_head_ce_cfg1.npz", hidden_states=hs, lm_head_weight_bits=bits(model.language_model.lm_head.weight), labels=labels,
+         ignore_index=np.int64(model.ignore_index), logits=logits, loss=np.float32(loss.item()),
+         model_loss_unrounded_hidden=np.float32(out["loss"].item()),
+         source="reference Model/model.py:429-438 (lm_head + shifted CrossEntropyLoss), config-1 MLLAMA, labels with ignore_index")
+
+
 if __name__ == "__main__":
+    golden_lm_head_loss()
     golden_rmsnorm()
     golden_ffn()
     golden_block()

@@ -737,3 +737,47 @@ def test_linear_lora_fused_any_projection(tokens, in_f, out_f, rank, p_drop, bia
     with torch.no_grad():
         ye = lo(dev(x32))
     close(ye, torch.nn.functional.linear(x32, w32, bias32) + (alpha / rank) * (x32 @ a32.t()) @ b32.t(), tol_f, "eval y")
+
+
+# ----------------------------------------------------------------------------------------------- f4: lm_head + shifted CE
+def test_lm_head_ce_vs_reference_outputs():
+    """Fused lm_head + shifted cross entropy against the reference's own logits and loss (fixture from Model/model.py:429-438)."""
+    g = load_golden("lm_head_ce_cfg1.npz")
+    head = torch.nn.Linear(256, 512, bias=False).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        head.weight.copy_(dev(g["lm_head_weight"]))
+    hs = dev(g["hidden_states"])
+    labels = g["labels"].to(DEV)
+    logits, loss = L.lm_head_loss(head, hs, labels, int(g["ignore_index"]))
+    close(logits, g["logits"], FWD, "logits")
+    assert abs(loss.item() - g["loss"]) <= 5e-3 * abs(g["loss"]), (loss.item(), g["loss"])
+    # without labels: plain logits, no loss
+    lg2, none = L.lm_head_loss(head, hs, None)
+    assert none is None and lg2.shape == logits.shape
+
+
+@pytest.mark.parametrize("batch,seq,hidden,vocab,frac_ignored", [(2, 160, 256, 1000, 0.2), (3, 100, 512, 2056, 0.0), (1, 700, 384, 520, 0.9),
+                                                                 (2, 64, 256, 128256, 0.1)])
+def test_lm_head_ce_forward_backward_vs_oracle(batch, seq, hidden, vocab, frac_ignored):
+    """Loss, logits, d_hidden and d_weight of the fused head against autograd over the reference's expressions; vocabularies
+    that are not a multiple of the 256-column tile, rows without a target, and the real 128 256-entry vocabulary."""
+    gen = torch.Generator().manual_seed(vocab + seq)
+    bf = O.bf16_representable
+    hs32 = bf(torch.randn(batch, seq, hidden, generator=gen))
+    w32 = bf(torch.randn(vocab, hidden, generator=gen) / hidden ** 0.5)
+    labels = torch.randint(0, vocab, (batch, seq), generator=gen)
+    labels[torch.rand(batch, seq, generator=gen) < frac_ignored] = -100
+    labels[0, 1] = 7                                    # at least one valid target
+    head = torch.nn.Linear(hidden, vocab, bias=False).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        head.weight.copy_(dev(w32))
+    hs = dev(hs32).requires_grad_(True)
+    logits, loss = L.lm_head_loss(head, hs, labels.to(DEV))
+    (loss * 3.0).backward()                              # a non-unit upstream gradient (read on the device, no sync)
+    hr, wr = hs32.clone().requires_grad_(True), w32.clone().requires_grad_(True)
+    logits_r, loss_r = O.lm_head_shifted_ce(hr, wr, labels)
+    (loss_r * 3.0).backward()
+    close(logits, logits_r, FWD, "logits")
+    assert abs(loss.item() - loss_r.item()) <= 5e-3 * abs(loss_r.item()), (loss.item(), loss_r.item())
+    close(hs.grad, hr.grad, (2e-2, 2.0 ** -5), "d_hidden")
+    close(head.weight.grad, wr.grad, (2e-2, 2.0 ** -5), "d_lm_head_weight")

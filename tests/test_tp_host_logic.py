@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from llama32_b200.tp import FusedTensorParallelBlock, TpRankBuffers, shard_ffn_weights, shard_range
+from llama32_b200.tp import FusedTensorParallelBlock, TpRankBuffers, shard_ffn_weights, shard_range, shard_state_dict_for_rank
 
 
 @pytest.mark.parametrize("inter,world", [(14336, 8), (28672, 8), (14336, 3), (688, 2), (1152, 3), (104, 4), (16, 2)])
@@ -60,3 +60,22 @@ def test_rows_of_covers_every_row_once(tokens, world):
         assert 0 <= lo <= hi <= tokens and hi - lo <= per == TpRankBuffers.slot_rows_for(tokens, world)
         covered += list(range(lo, hi))
     assert covered == list(range(tokens))
+
+
+def test_load_time_packing_matches_device_side_sharding():
+    """shard_state_dict_for_rank (host, load time) == shard_ffn_weights (device side) for every rank; other keys untouched."""
+    torch.manual_seed(1)
+    state = {"language_model.model.trf_blocks.0.ff.swiglu.w_gate": torch.randn(512, 64),
+             "language_model.model.trf_blocks.0.ff.swiglu.w_up": torch.randn(512, 64),
+             "language_model.model.trf_blocks.0.ff.w_down.weight": torch.randn(64, 512),
+             "language_model.model.trf_blocks.0.norm2.weight": torch.randn(64),
+             "language_model.lm_head.weight": torch.randn(100, 64)}
+    pre = "language_model.model.trf_blocks.0."
+    for world in (2, 4):
+        for rank in range(world):
+            sh = shard_state_dict_for_rank(state, world, rank)
+            g, u, d = shard_ffn_weights(state[pre + "ff.swiglu.w_gate"], state[pre + "ff.swiglu.w_up"], state[pre + "ff.w_down.weight"],
+                                        world, rank)
+            assert torch.equal(sh[pre + "ff.swiglu.w_gate"], g) and torch.equal(sh[pre + "ff.swiglu.w_up"], u)
+            assert torch.equal(sh[pre + "ff.w_down.weight"], d) and sh[pre + "ff.w_down.weight"].is_contiguous()
+            assert sh[pre + "norm2.weight"] is state[pre + "norm2.weight"] and sh["language_model.lm_head.weight"] is state["language_model.lm_head.weight"]
