@@ -54,7 +54,8 @@ extern "C" {
 
 /* ABI version of this header (bumped on any signature change).  2: tensor-parallel, LoRA and block-tail entry points.
  * 3: tensor-parallel backward; the all-gather entry points accept an A buffer distinct from the published one;
- *    l32_rmsnorm_backward_add, l32_block_tail_forward_ex, l32_linear_lora_forward / _backward, l32_lm_head_ce_*. */
+ *    l32_rmsnorm_backward_add, l32_block_tail_forward_ex, l32_linear_lora_forward / _backward, l32_lm_head_ce_*,
+ *    l32_rope_kv_append, l32_gqa_attention_forward. */
 L32_API int l32_abi_version(void);
 /* Number of CUDA kernels this library has launched in the calling process so far (monotonic). */
 L32_API unsigned long long l32_kernel_launch_count(void);
@@ -247,6 +248,29 @@ L32_API int l32_lm_head_ce_backward(const void* logits, const float* lse, const 
                                     const float* loss_and_count, const float* grad_loss, const void* hidden_states, const void* w,
                                     void* dlogits, void* d_hidden, void* dw, int64_t tokens, int hidden, int vocab, int dtype,
                                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Grouped-query attention with a preallocated KV cache.
+ * Replaces: GroupQueryAttention.forward between the projections, Model/model.py:238-253 -- RoPE (apply_rotary_pos_emb,
+ *           :195-198, angles of LLAMARotaryEmbedding :176-186), KVCache.update (:21-29, one torch.cat per layer per step),
+ *           repeat_kv (:124-132), the materialised [B, heads, S, S] scores + dense additive mask + softmax + P V (:246-252).
+ * Layouts: q, ctx : [batch, q_len, heads * head_dim] (what W_query / out_proj produce / consume, no transposes);
+ *          k_new, v_new : [batch, q_len, kv_heads * head_dim];  cache_k, cache_v : [batch, kv_heads, max_len, head_dim],
+ *          ZERO-INITIALISED by the caller (rows past the current length are multiplied by zero probabilities).
+ */
+/* RoPE on q (in place) and on k_new while it is stored at cache_k[:, :, past_len : past_len + q_len]; v_new is stored next
+ * to it.  position_ids : [batch, q_len] int64 absolute positions (pass them explicitly in decode: the reference's default
+ * restarts at 0 every step).  rope_base = config.rope_base (500000).  Angles in fp32. */
+L32_API int l32_rope_kv_append(void* q, const void* k_new, const void* v_new, const int64_t* position_ids, void* cache_k,
+                               void* cache_v, int batch, int q_len, int heads, int kv_heads, int head_dim, int max_len,
+                               int past_len, float rope_base, int dtype, void* stream);
+/* ctx = softmax(q k^T / sqrt(head_dim) + mask) v over keys [0, kv_len) of the cache, flash-style on tcgen05 (scores never
+ * leave the SM).  Query i of the call sits at position past_len + i.  causal != 0: key j is visible iff j <= past_len + i
+ * (the reference's triu(-inf, 1) mask, Model/model.py:314-317); key_keep: optional [batch, kv_len] bytes, 0 = padded key
+ * (the reference's padding term, :318).  A row without any visible key yields zeros.  head_dim 64 or 128. */
+L32_API int l32_gqa_attention_forward(const void* q, const void* cache_k, const void* cache_v, const uint8_t* key_keep,
+                                      void* ctx, int batch, int q_len, int heads, int kv_heads, int head_dim, int max_len,
+                                      int kv_len, int past_len, int causal, int dtype, void* stream);
 
 /* General tiled GEMM used by the entry points above (exposed for tests, tuning and the tensor-parallel
  * host code):  D[m,n] = A[m,k] B[n,k]^T  (+ A1 B1^T when a1 != NULL).

@@ -9,6 +9,8 @@ from .modules import (  # noqa: F401
     FusedFeedForward,
     FusedFeedforward,
     FusedSwiGLU,
+    GroupQueryAttention,
+    KVCache,
     LLAMARMSNorm,
     LMHeadCEFunction,
     Linear_LORA,
@@ -28,5 +30,5 @@ from .modules import (  # noqa: F401
 __all__ = [
     "FFNFunction", "FFNLoRAFunction", "FusedFeedForward", "FusedFeedforward", "FusedSwiGLU", "LLAMARMSNorm", "Linear_LORA",
     "LinearFunction", "RMSNormFunction", "SwiGLUFunction", "block_tail", "convert_feedforward_to_fused", "convert_instances",
-    "patch_reference", "BlockTailFunction", "LinearLoRAFunction", "chain_block_norms", "LMHeadCEFunction", "lm_head_loss", "shift_labels",
+    "patch_reference", "BlockTailFunction", "LinearLoRAFunction", "chain_block_norms", "LMHeadCEFunction", "lm_head_loss", "shift_labels", "GroupQueryAttention", "KVCache",
 ]

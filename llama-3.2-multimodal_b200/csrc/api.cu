@@ -660,6 +660,34 @@ int l32_lm_head_ce_backward(const void* logits, const float* lse, const int64_t*
     return rc;
 }
 
+int l32_rope_kv_append(void* q, const void* k_new, const void* v_new, const int64_t* position_ids, void* cache_k, void* cache_v,
+                       int batch, int q_len, int heads, int kv_heads, int head_dim, int max_len, int past_len, float rope_base,
+                       int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (batch < 0 || q_len < 0 || heads <= 0 || kv_heads <= 0 || (heads % kv_heads) != 0 || head_dim <= 0 || (head_dim % 2) != 0 ||
+        max_len <= 0 || past_len < 0 || past_len + q_len > max_len || !(rope_base > 1.0f))
+        return L32_ERR_BAD_SHAPE;
+    if (batch == 0 || q_len == 0) return L32_OK;
+    if (q == nullptr || k_new == nullptr || v_new == nullptr || position_ids == nullptr || cache_k == nullptr || cache_v == nullptr)
+        return L32_ERR_NULL;
+    return rope_kv_append(q, k_new, v_new, reinterpret_cast<const long long*>(position_ids), cache_k, cache_v, batch, q_len, heads,
+                          kv_heads, head_dim, max_len, past_len, rope_base, dtype, as_stream(stream));
+}
+
+int l32_gqa_attention_forward(const void* q, const void* cache_k, const void* cache_v, const uint8_t* key_keep, void* ctx, int batch,
+                              int q_len, int heads, int kv_heads, int head_dim, int max_len, int kv_len, int past_len, int causal,
+                              int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (batch < 0 || q_len < 0 || heads <= 0 || kv_heads <= 0 || (heads % kv_heads) != 0 || (head_dim != 64 && head_dim != 128) ||
+        max_len <= 0 || kv_len < 0 || kv_len > max_len || past_len < 0)
+        return L32_ERR_BAD_SHAPE;
+    if (batch == 0 || q_len == 0) return L32_OK;
+    if (q == nullptr || cache_k == nullptr || cache_v == nullptr || ctx == nullptr) return L32_ERR_NULL;
+    if (!is_aligned16(q) || !is_aligned16(cache_k) || !is_aligned16(cache_v) || !is_aligned16(ctx)) return L32_ERR_BAD_ALIGN;
+    return gqa_attention(q, cache_k, cache_v, key_keep, ctx, batch, q_len, heads, kv_heads, head_dim, max_len, kv_len, past_len,
+                         causal, dtype, as_stream(stream));
+}
+
 int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t ldb, int b_mn_major, const void* a1,
              int64_t lda1, const void* b1, int64_t ldb1, void* d, int64_t ldd, int m, int n, int k, int k1, int dtype,
              int cta_group, int max_ctas, void* stream) {

@@ -1,0 +1,415 @@
+// K7/K8: grouped-query attention with a preallocated KV cache for sm_100a.
+//
+// Replaces GroupQueryAttention.forward between the projections (reference Model/model.py:238-253): RoPE on q / k
+// (apply_rotary_pos_emb, :195-198; cos / sin from position_ids, LLAMARotaryEmbedding :176-186), the KV cache update
+// (KVCache.update, :21-29 -- a torch.cat per layer per step), repeat_kv copies (:124-132), the materialised
+// [B, heads, S, S] score tensor, the dense additive mask and the softmax / PV products (:246-252).
+//
+//   rope_kv_append_kernel   RoPE on q in place and on k while it is written into the cache; v copied next to it.  The cache
+//                           is preallocated [batch, kv_heads, max_len, head_dim]: appending is a store at `past_len`, not a
+//                           reallocation.  Angles are computed in fp32 from position_ids (explicit positions also fix the
+//                           reference's decode bug, SURVEY.md 0.9: `_prepare_position_ids` restarts at 0 for every step).
+//   gqa_attention_kernel    flash-style forward: one CTA = one (batch, query head, 128-query tile); the key / value tiles of the
+//                           head's KV group stream through shared memory (TMA, double-buffered), S = Q K^T and P V run on
+//                           tcgen05 with the accumulators in TMEM, the online softmax runs in registers (one query row per
+//                           thread = one TMEM lane), scores never leave the SM.  Causal tiles beyond the diagonal are never
+//                           visited.  head_dim 64 or 128.
+// Masking = the reference's additive mask restated as predicates: causal (key position <= query position; the reference's
+// triu(-inf, 1), model.py:314-317), key padding (model.py:318, as a per-key keep byte) and the cache length.
+#include "l32_internal.cuh"
+
+#include <cstring>
+
+namespace l32 {
+namespace {
+
+constexpr int kQTile = 128;      // query rows per CTA = TMEM lanes = threads
+constexpr int kKvTile = 64;      // keys per iteration (one 128-byte swizzle atom of P)
+constexpr int kAttThreads = 128;
+constexpr int kUmmaKAtt = 16;
+
+struct AttnParams {
+    CUtensorMap map_q;   // [batch * q_len, heads * head_dim], box {64, 128}
+    CUtensorMap map_k;   // [batch * kv_heads * max_len, head_dim], box {64, 64}
+    CUtensorMap map_v;   // same tensor shape as K, box {64, 64}
+    void* out;           // [batch * q_len, heads * head_dim]
+    const uint8_t* keep; // optional [batch, kv_len]: 0 = padded key (never attended)
+    int batch, q_len, heads, kv_heads, max_len, kv_len, past_len, causal;
+    float scale_log2;    // log2(e) / sqrt(head_dim)
+    uint32_t idesc_s, idesc_o;
+};
+
+L32_DEVICE float fast_exp2(float x) {
+    float y;
+    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int kD, typename T>
+__global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid_constant__ AttnParams p) {
+    constexpr int kDAtoms = kD / 64;                       // 64-element (128-byte) column blocks of a head
+    constexpr int kQBytes = kQTile * kD * 2;
+    constexpr int kKBytes = kKvTile * kD * 2;              // also the V tile
+    constexpr int kPBytes = kQTile * kKvTile * 2;
+    // 128-byte-swizzled tiles need 1024-byte alignment; the kernel has no static shared memory, so the dynamic window
+    // starts aligned (checked: a misaligned base traps instead of corrupting tiles)
+    extern __shared__ __align__(1024) uint8_t att_smem[];
+    if ((smem_u32(att_smem) & 1023u) != 0) __trap();
+    uint8_t* sq = att_smem;
+    uint8_t* sk = sq + kQBytes;                            // 2 stages
+    uint8_t* sv = sk + 2 * kKBytes;                        // 2 stages
+    uint8_t* sp = sv + 2 * kKBytes;
+    uint64_t* bar_q = reinterpret_cast<uint64_t*>(sp + kPBytes);
+    uint64_t* bar_k = bar_q + 1;                           // [2] K tile landed
+    uint64_t* bar_v = bar_k + 2;                           // [2] V tile landed
+    uint64_t* bar_s = bar_v + 2;                           // S = Q K^T complete
+    uint64_t* bar_o = bar_s + 1;                           // P V complete (P and the V stage may be reused)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
+
+    const int tid = threadIdx.x;
+    const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int q0 = blockIdx.x * kQTile;
+    const int head = blockIdx.y;
+    const int b = blockIdx.z;
+    const int kvh = head / (p.heads / p.kv_heads);
+
+    if (tid == 0) {
+        tma_prefetch_desc(&p.map_q);
+        tma_prefetch_desc(&p.map_k);
+        tma_prefetch_desc(&p.map_v);
+        mbar_init(bar_q, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_k[i], 1);
+            mbar_init(&bar_v[i], 1);
+        }
+        mbar_init(bar_s, 1);
+        mbar_init(bar_o, 1);
+        fence_mbar_init();
+    }
+    constexpr uint32_t kTmemCols = (kKvTile + kD) <= 128 ? 128u : 256u;
+    if (warp == 1) {
+        tmem_alloc<1>(tmem_slot, kTmemCols);
+        tmem_relinquish<1>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const uint32_t tmem_s = tmem_base;             // S: columns [0, 64)
+    const uint32_t tmem_o = tmem_base + kKvTile;   // P V: columns [64, 64 + kD)
+    pdl_launch_dependents();
+    pdl_wait_prior_grid();
+
+    // keys this query tile can see: [0, hi)
+    const int q_last = min(q0 + kQTile, p.q_len) - 1;
+    int hi = p.kv_len;
+    if (p.causal) hi = min(hi, p.past_len + q_last + 1);
+    const int ntiles = (hi + kKvTile - 1) / kKvTile;
+    const int kv_row0 = (b * p.kv_heads + kvh) * p.max_len;
+
+    // K tile, K-major: [64 keys][64 dims] per column block;  V tile: the same boxes, consumed as an MN-major B operand
+    auto load_k = [&](int t) {
+        const int s = t & 1;
+        mbar_arrive_expect_tx(&bar_k[s], kKBytes);
+#pragma unroll
+        for (int a = 0; a < kDAtoms; ++a)
+            tma_load_2d(sk + s * kKBytes + a * (kKvTile * 128), &p.map_k, &bar_k[s], a * 64, kv_row0 + t * kKvTile, kEvictNormal);
+    };
+    auto load_v = [&](int t) {
+        const int s = t & 1;
+        mbar_arrive_expect_tx(&bar_v[s], kKBytes);
+#pragma unroll
+        for (int a = 0; a < kDAtoms; ++a)
+            tma_load_2d(sv + s * kKBytes + a * (kKvTile * 128), &p.map_v, &bar_v[s], a * 64, kv_row0 + t * kKvTile, kEvictNormal);
+    };
+    if (tid == 0) {
+        mbar_arrive_expect_tx(bar_q, kQBytes);
+#pragma unroll
+        for (int a = 0; a < kDAtoms; ++a)
+            tma_load_2d(sq + a * (kQTile * 128), &p.map_q, bar_q, head * kD + a * 64, b * p.q_len + q0, kEvictNormal);
+        if (ntiles > 0) {
+            load_k(0);
+            load_v(0);
+        }
+    }
+
+    // one query row per thread = one TMEM lane
+    const int qi = q0 + tid;                       // query index inside the sequence
+    const int qpos = p.past_len + qi;              // its absolute position
+    const bool row_ok = qi < p.q_len;
+    float o[kD];
+#pragma unroll
+    for (int j = 0; j < kD; ++j) o[j] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    const uint32_t lane_off = (warp * 32u) << 16;
+    const uint8_t* keep_row = p.keep != nullptr ? p.keep + static_cast<size_t>(b) * p.kv_len : nullptr;
+    auto visible = [&](int key) {
+        bool ok = key < p.kv_len && (!p.causal || key <= qpos);
+        if (ok && keep_row != nullptr) ok = keep_row[key] != 0;
+        return ok;
+    };
+    auto fold_pv = [&]() {                          // o += (P V of the previous tile), straight from TMEM
+#pragma unroll
+        for (int c = 0; c < kD / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[c * 32 + j] += __uint_as_float(v[j]);
+        }
+    };
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        const int j0 = t * kKvTile;
+        if (tid == 0) {
+            // K stage (t + 1) & 1 was last read by S of tile t - 1, complete long ago; V needs P V of tile t - 1 (below)
+            if (t + 1 < ntiles) {
+                load_k(t + 1);
+                if (t == 0) load_v(1);
+            }
+            if (t == 0) mbar_wait(bar_q, 0);
+            mbar_wait(&bar_k[s], (t >> 1) & 1u);
+            tc_fence_after();
+            // S[128, 64] = Q[128, kD] K[64, kD]^T
+            const uint32_t q_addr = smem_u32(sq), k_addr = smem_u32(sk + s * kKBytes);
+#pragma unroll
+            for (int kk = 0; kk < kD / kUmmaKAtt; ++kk) {
+                const uint32_t qoff = (kk / 4) * (kQTile * 128) + (kk % 4) * 32;      // column block, then 32 B per K step
+                const uint32_t koff = (kk / 4) * (kKvTile * 128) + (kk % 4) * 32;
+                umma_f16<1>(tmem_s, make_smem_desc_sw128(q_addr + qoff, 0, 1024), make_smem_desc_sw128(k_addr + koff, 0, 1024),
+                            p.idesc_s, kk > 0 ? 1u : 0u);
+            }
+            umma_commit<1>(bar_s);
+        }
+        mbar_wait(bar_s, t & 1u);
+        tc_fence_after();
+        // ---- pass 1 over this row's 64 scores: the tile maximum (scores stay in TMEM, they are read again in pass 2)
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_s + lane_off + hf * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (visible(j0 + hf * 32 + j)) tmax = fmaxf(tmax, __uint_as_float(v[j]) * p.scale_log2);
+        }
+        const float m_new = fmaxf(m, tmax);
+        const bool dead = (m_new == -INFINITY);                       // nothing visible so far
+        const float alpha = dead ? 1.f : fast_exp2(m - m_new);       // m = -inf: exp2(-inf) = 0 (o and l are 0 anyway)
+        // ---- the previous tile's P V: wait, fold into the running output, free the V stage
+        if (t > 0) {
+            mbar_wait(bar_o, (t - 1) & 1u);
+            tc_fence_after();
+            fold_pv();
+            if (tid == 0 && t + 1 < ntiles) load_v(t + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < kD; ++j) o[j] *= alpha;
+        // ---- pass 2: probabilities (rounded to the storage type: the row sum uses what the MMA will see) -> P in shared
+        // memory, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of 16 bytes per row
+        float psum = 0.f;
+        uint8_t* prow = sp + tid * 128;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_s + lane_off + hf * 32, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int key = j0 + hf * 32 + 2 * j;
+                const float p0 = (!dead && visible(key)) ? fast_exp2(__uint_as_float(v[2 * j]) * p.scale_log2 - m_new) : 0.f;
+                const float p1 = (!dead && visible(key + 1)) ? fast_exp2(__uint_as_float(v[2 * j + 1]) * p.scale_log2 - m_new) : 0.f;
+                pk[j] = Pack2<T>::pack(p0, p1);
+                const float2 pr = Pack2<T>::unpack(pk[j]);
+                psum += pr.x + pr.y;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(prow + (((hf * 4 + c) ^ (tid & 7)) << 4)) =
+                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        l = l * alpha + psum;
+        m = m_new;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();                                // every row of P is in place; every thread is done with S and with P V
+        if (tid == 0) {
+            tc_fence_after();
+            mbar_wait(&bar_v[s], (t >> 1) & 1u);
+            tc_fence_after();
+            // O_tile[128, kD] = P[128, 64] V[64, kD]   (V consumed MN-major: [64 keys][kD])
+            const uint32_t p_addr = smem_u32(sp), v_addr = smem_u32(sv + s * kKBytes);
+#pragma unroll
+            for (int kk = 0; kk < kKvTile / kUmmaKAtt; ++kk)
+                umma_f16<1>(tmem_o, make_smem_desc_sw128(p_addr + kk * 32, 0, 1024),
+                            make_smem_desc_sw128(v_addr + kk * (kUmmaKAtt * 128), kKvTile * 128, 1024), p.idesc_o, kk > 0 ? 1u : 0u);
+            umma_commit<1>(bar_o);
+        }
+    }
+    if (ntiles > 0) {
+        mbar_wait(bar_o, (ntiles - 1) & 1u);
+        tc_fence_after();
+        fold_pv();
+    }
+    if (row_ok) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;     // a row without any visible key gives zeros
+        T* dst = static_cast<T*>(p.out) + (static_cast<size_t>(b) * p.q_len + qi) * (static_cast<size_t>(p.heads) * kD) + head * kD;
+#pragma unroll
+        for (int c = 0; c < kD / 8; ++c) {
+            uint4 w;
+            w.x = Pack2<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
+            w.y = Pack2<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+            w.z = Pack2<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+            w.w = Pack2<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+            *reinterpret_cast<uint4*>(dst + 8 * c) = w;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<1>(tmem_base, kTmemCols);
+    }
+}
+
+// RoPE + cache append.  One thread handles one (token, head, pair index i < head_dim / 2): the rotate_half form
+//   out[i] = x[i] cos - x[i + d/2] sin,  out[i + d/2] = x[i + d/2] cos + x[i] sin,  angle = position * base^(-2 i / d)
+// (reference Model/model.py:188-198; cos / sin in fp32 instead of the reference's storage-dtype cos / sin).
+template <typename T>
+__global__ void __launch_bounds__(256) rope_kv_append_kernel(T* q, const T* __restrict__ k_new, const T* __restrict__ v_new,
+                                                            const long long* __restrict__ position_ids, T* cache_k, T* cache_v,
+                                                            int batch, int q_len, int heads, int kv_heads, int d, int max_len,
+                                                            int past_len, float log2_base) {
+    pdl_wait_prior_grid();
+    const int half = d >> 1;
+    const int per_tok = (heads + 2 * kv_heads) * half;
+    const long long total = static_cast<long long>(batch) * q_len * per_tok;
+    for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
+        const int i = static_cast<int>(idx % half);
+        const int hh = static_cast<int>((idx / half) % (heads + 2 * kv_heads));
+        const long long tok = idx / per_tok;                 // b * q_len + t
+        const int t = static_cast<int>(tok % q_len);
+        const int b = static_cast<int>(tok / q_len);
+        if (hh >= heads + kv_heads) {                        // value head: plain copy into the cache
+            const int h = hh - heads - kv_heads;
+            const T* src = v_new + (tok * kv_heads + h) * d;
+            T* dst = cache_v + ((static_cast<long long>(b) * kv_heads + h) * max_len + past_len + t) * d;
+            dst[i] = src[i];
+            dst[i + half] = src[i + half];
+            continue;
+        }
+        const float pos = static_cast<float>(position_ids[tok]);
+        const float inv_freq = exp2f(-log2_base * (2.0f * static_cast<float>(i) / static_cast<float>(d)));
+        float sn, cs;
+        sincosf(pos * inv_freq, &sn, &cs);
+        if (hh < heads) {
+            T* x = q + (tok * heads + hh) * d;
+            const float a = static_cast<float>(x[i]), c = static_cast<float>(x[i + half]);
+            x[i] = static_cast<T>(a * cs - c * sn);
+            x[i + half] = static_cast<T>(c * cs + a * sn);
+        } else {
+            const int h = hh - heads;
+            const T* x = k_new + (tok * kv_heads + h) * d;
+            T* dst = cache_k + ((static_cast<long long>(b) * kv_heads + h) * max_len + past_len + t) * d;
+            const float a = static_cast<float>(x[i]), c = static_cast<float>(x[i + half]);
+            dst[i] = static_cast<T>(a * cs - c * sn);
+            dst[i + half] = static_cast<T>(c * cs + a * sn);
+        }
+    }
+}
+
+template <int kD, typename T>
+int launch_attention(const AttnParams& p, cudaStream_t s) {
+    auto* kernel = gqa_attention_kernel<kD, T>;
+    constexpr size_t smem = kQTile * kD * 2 + 4 * kKvTile * kD * 2 + kQTile * kKvTile * 2 + 64;
+    static bool configured_dev[kMaxDevices] = {};
+    bool& configured = configured_dev[current_device_slot()];
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return static_cast<int>(e);
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>((p.q_len + kQTile - 1) / kQTile), static_cast<unsigned>(p.heads),
+                       static_cast<unsigned>(p.batch));
+    cfg.blockDim = dim3(kAttThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p);
+    if (e == cudaSuccess) count_launch();
+    return static_cast<int>(e);
+}
+
+}  // namespace
+
+int rope_kv_append(void* q, const void* k_new, const void* v_new, const long long* position_ids, void* cache_k, void* cache_v,
+                   int batch, int q_len, int heads, int kv_heads, int head_dim, int max_len, int past_len, float rope_base,
+                   int dtype, cudaStream_t s) {
+    const long long total = static_cast<long long>(batch) * q_len * (heads + 2 * kv_heads) * (head_dim / 2);
+    if (total == 0) return L32_OK;
+    long long blocks = (total + 255) / 256;
+    const long long cap = static_cast<long long>(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+    cfg.blockDim = dim3(256);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const float log2_base = log2f(rope_base);
+    cudaError_t e;
+    if (dtype == L32_BF16)
+        e = cudaLaunchKernelEx(&cfg, rope_kv_append_kernel<__nv_bfloat16>, static_cast<__nv_bfloat16*>(q),
+                               static_cast<const __nv_bfloat16*>(k_new), static_cast<const __nv_bfloat16*>(v_new), position_ids,
+                               static_cast<__nv_bfloat16*>(cache_k), static_cast<__nv_bfloat16*>(cache_v), batch, q_len, heads,
+                               kv_heads, head_dim, max_len, past_len, log2_base);
+    else
+        e = cudaLaunchKernelEx(&cfg, rope_kv_append_kernel<__half>, static_cast<__half*>(q), static_cast<const __half*>(k_new),
+                               static_cast<const __half*>(v_new), position_ids, static_cast<__half*>(cache_k),
+                               static_cast<__half*>(cache_v), batch, q_len, heads, kv_heads, head_dim, max_len, past_len, log2_base);
+    if (e == cudaSuccess) count_launch();
+    return static_cast<int>(e);
+}
+
+int gqa_attention(const void* q, const void* cache_k, const void* cache_v, const uint8_t* keep, void* out, int batch, int q_len,
+                  int heads, int kv_heads, int head_dim, int max_len, int kv_len, int past_len, int causal, int dtype,
+                  cudaStream_t s) {
+    if (head_dim != 64 && head_dim != 128) return L32_ERR_BAD_SHAPE;
+    if (batch <= 0 || q_len <= 0) return L32_OK;
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = out;
+    p.keep = keep;
+    p.batch = batch; p.q_len = q_len; p.heads = heads; p.kv_heads = kv_heads; p.max_len = max_len; p.kv_len = kv_len;
+    p.past_len = past_len; p.causal = causal;
+    p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
+    p.idesc_s = make_idesc_f16(dtype == L32_BF16, kQTile, kKvTile, false, false);
+    p.idesc_o = make_idesc_f16(dtype == L32_BF16, kQTile, static_cast<uint32_t>(head_dim), false, true);
+    int rc = make_tensor_map_2d(&p.map_q, q, static_cast<uint64_t>(batch) * q_len, static_cast<uint64_t>(heads) * head_dim,
+                                static_cast<uint64_t>(heads) * head_dim, kQTile, 64, dtype);
+    if (rc != L32_OK) return rc;
+    const uint64_t kv_rows = static_cast<uint64_t>(batch) * kv_heads * max_len;
+    rc = make_tensor_map_2d(&p.map_k, cache_k, kv_rows, head_dim, head_dim, kKvTile, 64, dtype);
+    if (rc != L32_OK) return rc;
+    rc = make_tensor_map_2d(&p.map_v, cache_v, kv_rows, head_dim, head_dim, kKvTile, 64, dtype);
+    if (rc != L32_OK) return rc;
+    if (dtype == L32_BF16) {
+        if (head_dim == 128) return launch_attention<128, __nv_bfloat16>(p, s);
+        return launch_attention<64, __nv_bfloat16>(p, s);
+    }
+    if (head_dim == 128) return launch_attention<128, __half>(p, s);
+    return launch_attention<64, __half>(p, s);
+}
+
+}  // namespace l32

@@ -24,7 +24,7 @@ from . import ops
 __all__ = [
     "RMSNormFunction", "LLAMARMSNorm", "SwiGLUFunction", "FusedSwiGLU", "LinearFunction", "Linear_LORA", "FFNFunction", "FFNLoRAFunction",
     "FusedFeedforward", "FusedFeedForward", "convert_feedforward_to_fused", "patch_reference", "convert_instances", "block_tail",
-    "BlockTailFunction", "LinearLoRAFunction", "chain_block_norms", "LMHeadCEFunction", "lm_head_loss", "shift_labels",
+    "BlockTailFunction", "LinearLoRAFunction", "chain_block_norms", "LMHeadCEFunction", "lm_head_loss", "shift_labels", "GroupQueryAttention", "KVCache",
 ]
 
 
@@ -480,6 +480,157 @@ def chain_block_norms(blocks, final_norm=None):
         object.__setattr__(blk, "_l32_next_norm", nxt if isinstance(nxt, LLAMARMSNorm) else None)
 
 
+# ------------------------------------------------------------------------------------------------ attention + KV cache
+class KVCache:
+    """Drop-in for reference Model/model.py:12-29 with PREALLOCATED storage: per layer one zero-initialised
+    [batch, kv_heads, capacity, head_dim] buffer for keys and one for values; appending is a store at the current length
+    (capacity doubles when it runs out) instead of the reference's torch.cat per layer per step.
+    Same surface (`key_cache`, `value_cache`, `num_items()`, `update()`); `update` returns views of the filled part, so code
+    written against the reference's cache keeps working."""
+
+    def __init__(self, capacity: int = 0):
+        self.key_cache: list = []        # per layer: the FILLED view [B, kv, len, d] (what the reference keeps)
+        self.value_cache: list = []
+        self._k: list = []               # per layer: preallocated storage
+        self._v: list = []
+        self._len: list = []
+        self._capacity = int(capacity)
+
+    def num_items(self) -> int:
+        return self._len[0] if self._len else 0
+
+    def length(self, layer_idx: int) -> int:
+        return self._len[layer_idx] if layer_idx < len(self._len) else 0
+
+    def reserve(self, layer_idx, batch, kv_heads, head_dim, need, dtype, device):
+        """Storage of layer `layer_idx` with room for `need` tokens; returns (cache_k, cache_v, current length)."""
+        while len(self._k) <= layer_idx:
+            self._k.append(None); self._v.append(None); self._len.append(0)
+            self.key_cache.append(None); self.value_cache.append(None)
+        k = self._k[layer_idx]
+        if k is None or k.shape[2] < need:
+            cap = max(need, self._capacity, 2 * (k.shape[2] if k is not None else 0), 64)
+            cap = -(-cap // 64) * 64
+            nk = torch.zeros(batch, kv_heads, cap, head_dim, dtype=dtype, device=device)
+            nv = torch.zeros_like(nk)
+            if k is not None and self._len[layer_idx] > 0:
+                n = self._len[layer_idx]
+                nk[:, :, :n].copy_(k[:, :, :n]); nv[:, :, :n].copy_(self._v[layer_idx][:, :, :n])
+            self._k[layer_idx], self._v[layer_idx] = nk, nv
+        return self._k[layer_idx], self._v[layer_idx], self._len[layer_idx]
+
+    def advance(self, layer_idx, n):
+        self._len[layer_idx] += n
+        ln = self._len[layer_idx]
+        self.key_cache[layer_idx] = self._k[layer_idx][:, :, :ln]
+        self.value_cache[layer_idx] = self._v[layer_idx][:, :, :ln]
+
+    def update(self, key_states, value_states, layer_idx: int):
+        """Reference-compatible append of [B, kv, t, d] keys / values (already rotated); returns the filled views."""
+        b, kvh, t, d = key_states.shape
+        ck, cv, ln = self.reserve(layer_idx, b, kvh, d, self.length(layer_idx) + t, key_states.dtype, key_states.device)
+        ck[:, :, ln:ln + t].copy_(key_states)
+        cv[:, :, ln:ln + t].copy_(value_states)
+        self.advance(layer_idx, t)
+        return self.key_cache[layer_idx], self.value_cache[layer_idx]
+
+
+def _rotate_half(x):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+class GroupQueryAttention(nn.Module):
+    """Drop-in for reference Model/model.py:220-254 (same ctor, submodule names and state_dict keys: W_query, W_key, W_value,
+    out_proj).  16-bit CUDA inference with head_dim 64 / 128: the three projections and out_proj run on the tcgen05 GEMM
+    (fused with their adapter when they are Linear_LORA), RoPE + cache append is one kernel writing straight into the
+    preallocated KVCache, and the attention itself is the flash-style tcgen05 kernel -- no [B, heads, S, S] scores, no
+    repeat_kv copies, no torch.cat.  `attention_mask` is interpreted as the mask the reference's Llama3Model builds
+    (Model/model.py:304-319: causal + key padding); None means no masking at all, as in the reference.  Anything else
+    (fp32, CPU, autograd, other head sizes, a foreign cache object) evaluates the reference's own expressions."""
+
+    def __init__(self, config, layer_idx=None, dtype=None):
+        super().__init__()
+        assert config.hidden_size % config.n_heads == 0
+        assert config.n_heads % config.n_kv_groups == 0
+        self.config = config
+        self.layer_idx = layer_idx
+        self.num_heads = config.n_heads
+        self.head_dim = config.hidden_size // config.n_heads
+        self.num_kv_groups = config.n_kv_groups
+        self.group_size = config.n_heads // config.n_kv_groups
+        self.W_query = nn.Linear(config.hidden_size, config.n_heads * self.head_dim, bias=False, dtype=dtype)
+        self.W_key = nn.Linear(config.hidden_size, config.n_kv_groups * self.head_dim, bias=False, dtype=dtype)
+        self.W_value = nn.Linear(config.hidden_size, config.n_kv_groups * self.head_dim, bias=False, dtype=dtype)
+        self.out_proj = nn.Linear(config.n_heads * self.head_dim, config.hidden_size, bias=False, dtype=dtype)
+        self.rope_base = float(getattr(config, "rope_base", 500000.0))
+        self.is_causal = True
+
+    # -- reference expressions (Model/model.py:176-198, 238-253)
+    def _cos_sin(self, x, position_ids):
+        inv_freq = 1.0 / (self.rope_base ** (torch.arange(0, self.head_dim, 2, dtype=torch.int64).float() / self.head_dim))
+        inv_freq = inv_freq.to(x.device)
+        freqs = (inv_freq[None, :, None].float().expand(position_ids.shape[0], -1, 1) @ position_ids[:, None, :].float()).transpose(1, 2)
+        emb = torch.cat((freqs, freqs), dim=-1)
+        return emb.cos().to(x.dtype), emb.sin().to(x.dtype)
+
+    def _reference_forward(self, hidden_states, attention_mask, position_ids, kv_cache):
+        b, t, _ = hidden_states.shape
+        q = self.W_query(hidden_states).view(b, t, self.num_heads, self.head_dim).transpose(1, 2)
+        k = self.W_key(hidden_states).view(b, t, self.num_kv_groups, self.head_dim).transpose(1, 2)
+        v = self.W_value(hidden_states).view(b, t, self.num_kv_groups, self.head_dim).transpose(1, 2)
+        cos, sin = self._cos_sin(v, position_ids)
+        cos, sin = cos.unsqueeze(1), sin.unsqueeze(1)
+        q, k = (q * cos) + (_rotate_half(q) * sin), (k * cos) + (_rotate_half(k) * sin)
+        if kv_cache is not None:
+            k, v = kv_cache.update(k, v, self.layer_idx)
+        g = self.group_size
+        if g > 1:
+            k = k[:, :, None].expand(b, self.num_kv_groups, g, k.shape[-2], self.head_dim).reshape(b, self.num_heads, k.shape[-2], self.head_dim)
+            v = v[:, :, None].expand(b, self.num_kv_groups, g, v.shape[-2], self.head_dim).reshape(b, self.num_heads, v.shape[-2], self.head_dim)
+        score = q @ k.transpose(2, 3)
+        if attention_mask is not None:
+            score = score + attention_mask[:, :, :, : k.shape[-2]]
+        w = torch.softmax(score / (k.shape[-1] ** 0.5), dim=-1)
+        ctx = (w @ v).transpose(1, 2).contiguous().reshape(b, t, -1)
+        return self.out_proj(ctx)
+
+    def _fast_ok(self, x, kv_cache):
+        ws = [m.linear.weight if _is_lora(m) else m.weight for m in (self.W_query, self.W_key, self.W_value, self.out_proj)]
+        return (ops.supported(x) and self.head_dim in (64, 128) and x.dim() == 3 and x.numel() > 0 and
+                all(w.is_cuda and w.dtype == x.dtype for w in ws) and (kv_cache is None or isinstance(kv_cache, KVCache)) and
+                not _wants_grad(x, *ws, *[p for m in (self.W_query, self.W_key, self.W_value, self.out_proj) for p in m.parameters()]))
+
+    @staticmethod
+    def _project(mod, x):
+        return mod(x) if _is_lora(mod) else _linear(x, mod.weight, mod.bias)
+
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, kv_cache=None):
+        if position_ids is None or not self._fast_ok(hidden_states, kv_cache):
+            return self._reference_forward(hidden_states, attention_mask, position_ids, kv_cache)
+        b, t, _ = hidden_states.shape
+        q = self._project(self.W_query, hidden_states)           # [b, t, heads * d]: the kernels read this layout as it is
+        k = self._project(self.W_key, hidden_states)
+        v = self._project(self.W_value, hidden_states)
+        cache = kv_cache if kv_cache is not None else KVCache()
+        layer = self.layer_idx if kv_cache is not None else 0
+        past = cache.length(layer)
+        ck, cv, _ = cache.reserve(layer, b, self.num_kv_groups, self.head_dim, past + t, q.dtype, q.device)
+        ops.rope_kv_append(q, k, v, position_ids.to(device=q.device, dtype=torch.int64), ck, cv, past, self.rope_base)
+        cache.advance(layer, t)
+        kv_len = past + t
+        causal, keep = False, None
+        if attention_mask is not None:
+            causal = True
+            if attention_mask.dim() == 4 and attention_mask.shape[-1] == kv_len and attention_mask.shape[-2] == t and t > 1:
+                # the last query row sees every key the causal part allows: what is still masked there is key padding
+                keep = attention_mask[:, 0, -1, :] > (torch.finfo(attention_mask.dtype).min / 2)
+                if keep.shape[0] != b:
+                    keep = keep.expand(b, -1)
+        ctx = ops.gqa_attention_forward(q, ck, cv, kv_len, past, causal=causal, key_keep=keep)
+        return self._project(self.out_proj, ctx)
+
+
 # ------------------------------------------------------------------------------------------------ lm_head + loss
 def shift_labels(labels, ignore_index=-100):
     """Row-aligned targets for `shift_logits = logits[..., :-1, :]` / `shift_labels = labels[..., 1:]` (reference
@@ -585,6 +736,8 @@ def patch_reference(model_module, swiglu_module=None, fuse_block_tail=True):
     model_module.FusedFeedforward = FusedFeedforward
     model_module.FusedSwiGLU = FusedSwiGLU
     model_module.Linear_LORA = Linear_LORA
+    model_module.GroupQueryAttention = GroupQueryAttention
+    model_module.KVCache = KVCache
     model_module.HAS_RMSNORM_EXT = True
     if fuse_block_tail and hasattr(model_module, "TransformerBlock"):
         model_module.TransformerBlock.forward = _transformer_block_forward
@@ -612,6 +765,10 @@ def convert_instances(root: nn.Module) -> nn.Module:
                 m.intermediate_size = m.swiglu.intermediate_size
         elif name == "Linear_LORA" and not isinstance(m, Linear_LORA):
             m.__class__ = Linear_LORA
+        elif name == "GroupQueryAttention" and not isinstance(m, GroupQueryAttention):
+            m.__class__ = GroupQueryAttention
+            if not hasattr(m, "rope_base"):
+                m.rope_base = float(getattr(getattr(m, "config", None), "rope_base", 500000.0))
     # chain every stack of decoder blocks into the norm that follows it (a `layers` ModuleList next to a `final_norm`)
     # (the reference's Llama3Model keeps them in `trf_blocks`, Model/model.py:296-299)
     for m in root.modules():

@@ -414,6 +414,46 @@ def ffn_lora_backward(grad_y, x, w_gate, w_up, w_down, lora_a, lora_bs, t, gate_
     return (dx.view(x.shape) if dx is not None else None), dwg, dwu, dla, dlb
 
 
+# --------------------------------------------------------------------------------------------- attention
+def rope_kv_append(q, k_new, v_new, position_ids, cache_k, cache_v, past_len, rope_base=500000.0):
+    """RoPE on q [b, t, heads*d] IN PLACE and on k_new while it is stored into cache_k [b, kv_heads, max_len, d] at
+    past_len; v_new stored next to it.  position_ids [b, t] int64."""
+    _check_cuda(q, k_new, v_new, position_ids, cache_k, cache_v)
+    b, t = q.shape[0], q.shape[1]
+    _, kvh, max_len, d = cache_k.shape
+    heads = q.shape[-1] // d
+    for ten in (q, k_new, v_new, cache_k, cache_v):
+        if not ten.is_contiguous():
+            raise L32Error("rope_kv_append: tensors must be contiguous")
+    pos = position_ids.contiguous()
+    if pos.dtype != torch.int64 or pos.numel() != b * t:
+        raise L32Error("rope_kv_append: position_ids must be int64 [batch, q_len]")
+    with torch.cuda.device(q.device):
+        check(lib().l32_rope_kv_append(_ptr(q), _ptr(k_new), _ptr(v_new), _ptr(pos), _ptr(cache_k), _ptr(cache_v), b, t, heads, kvh,
+                                       d, max_len, int(past_len), float(rope_base), _dtype_code(q), _stream(q)),
+              "l32_rope_kv_append")
+
+
+def gqa_attention_forward(q, cache_k, cache_v, kv_len, past_len, *, causal=True, key_keep=None):
+    """ctx [b, t, heads*d] = softmax(q k^T / sqrt(d) + mask) v over cache[:, :, :kv_len]; q [b, t, heads*d] (RoPE applied)."""
+    _check_cuda(q, cache_k, cache_v, key_keep)
+    b, t = q.shape[0], q.shape[1]
+    _, kvh, max_len, d = cache_k.shape
+    heads = q.shape[-1] // d
+    qc = q.contiguous()
+    keep = None
+    if key_keep is not None:
+        keep = key_keep.to(torch.uint8).contiguous()
+        if tuple(keep.shape) != (b, kv_len):
+            raise L32Error(f"key_keep must be [batch, kv_len] = {(b, kv_len)}, got {tuple(keep.shape)}")
+    ctx = torch.empty_like(qc)
+    with torch.cuda.device(q.device):
+        check(lib().l32_gqa_attention_forward(_ptr(qc), _ptr(cache_k), _ptr(cache_v), _ptr(keep), _ptr(ctx), b, t, heads, kvh, d,
+                                              max_len, int(kv_len), int(past_len), int(bool(causal)), _dtype_code(qc), _stream(qc)),
+              "l32_gqa_attention_forward")
+    return ctx
+
+
 # --------------------------------------------------------------------------------------------- lm_head + cross entropy
 def lm_head_ce_forward(hidden_states, weight, labels_shifted, ignore_index=-100):
     """logits = hidden_states weight^T and the mean cross entropy against `labels_shifted` (int64, one per token row, already

@@ -12,6 +12,8 @@ not a 16-bit CUDA tensor (which, for the FFN, is always: SURVEY.md section 0.1):
     block_hot_path<- TransformerBlock.forward lines norm2/ff   reference Model/model.py:270-273
     linear_lora   <- Linear_LORA.forward                       reference Model/model.py:120-121
     lm_head_shifted_ce <- MllamaForConditionalGeneration.forward tail   reference Model/model.py:429-438
+    gqa_attention (+ rope_cos_sin, rotate_half, causal_padding_mask) <- GroupQueryAttention.forward, LLAMARotaryEmbedding,
+                  KVCache.update, Llama3Model._prepare_attention_mask   reference Model/model.py:12-29, 176-198, 220-254, 304-319
 The arithmetic itself lives in the third-party dependency torch (reference setup.py:47 `torch>=2.0.0`;
 installed here: 2.11.0+cu128): F.linear, F.silu, rsqrt, mean.  Gradients: the reference's own backward
 functions cannot run on any path, so the gradient oracle is autograd over these
@@ -71,6 +73,53 @@ def block_hot_path(attn_out, hidden_states, norm2_weight, eps, w_gate, w_up, w_d
     normed = add_rmsnorm(attn_out, norm2_weight, eps, residual=hidden_states)
     ff_out = feedforward(normed, w_gate, w_up, w_down)
     return normed, ff_out, attn_out + ff_out
+
+
+def rope_cos_sin(position_ids, head_dim, rope_base=500000.0):
+    """reference Model/model.py:176-186 (LLAMARotaryEmbedding.forward): inv_freq = base^(-2i/d); emb = cat(freqs, freqs)."""
+    inv_freq = 1.0 / (rope_base ** (torch.arange(0, head_dim, 2, dtype=torch.int64).float() / head_dim))
+    freqs = (inv_freq[None, :, None].float().expand(position_ids.shape[0], -1, 1) @ position_ids[:, None, :].float()).transpose(1, 2)
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos(), emb.sin()
+
+
+def rotate_half(x):
+    """reference Model/model.py:189-192."""
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def causal_padding_mask(mask2d, seq_len, dtype=torch.float32):
+    """reference Model/model.py:304-319 (_prepare_attention_mask): triu(-inf, 1) + (1 - mask) * finfo.min, [B, 1, S, S]."""
+    bsz = mask2d.shape[0]
+    causal = torch.triu(torch.full((seq_len, seq_len), float("-inf"), dtype=dtype), diagonal=1)[None, None].expand(bsz, 1, seq_len, seq_len)
+    padding = ((1.0 - mask2d.to(dtype)) * torch.finfo(dtype).min)[:, None, None, :].expand(bsz, 1, seq_len, seq_len)
+    return causal + padding
+
+
+def gqa_attention(hidden_states, wq, wk, wv, wo, n_heads, n_kv, position_ids, attention_mask=None, past_k=None, past_v=None,
+                  rope_base=500000.0):
+    """reference Model/model.py:238-253 (GroupQueryAttention.forward) with KVCache.update (:21-29) as an explicit concat.
+    Returns (out, k_all, v_all) with k_all / v_all the cache contents [B, n_kv, len, d] after the call."""
+    b, t, _ = hidden_states.shape
+    d = wq.shape[0] // n_heads
+    q = F.linear(hidden_states, wq).view(b, t, n_heads, d).transpose(1, 2)
+    k = F.linear(hidden_states, wk).view(b, t, n_kv, d).transpose(1, 2)
+    v = F.linear(hidden_states, wv).view(b, t, n_kv, d).transpose(1, 2)
+    cos, sin = rope_cos_sin(position_ids, d, rope_base)
+    cos, sin = cos.unsqueeze(1), sin.unsqueeze(1)
+    q, k = (q * cos) + (rotate_half(q) * sin), (k * cos) + (rotate_half(k) * sin)
+    if past_k is not None:
+        k, v = torch.cat([past_k, k], dim=-2), torch.cat([past_v, v], dim=-2)
+    g = n_heads // n_kv
+    kr = k[:, :, None].expand(b, n_kv, g, k.shape[-2], d).reshape(b, n_heads, k.shape[-2], d)      # repeat_kv, model.py:124-132
+    vr = v[:, :, None].expand(b, n_kv, g, v.shape[-2], d).reshape(b, n_heads, v.shape[-2], d)
+    score = q @ kr.transpose(2, 3)
+    if attention_mask is not None:
+        score = score + attention_mask[:, :, :, : kr.shape[-2]]
+    w = torch.softmax(score / (d ** 0.5), dim=-1)
+    ctx = (w @ vr).transpose(1, 2).contiguous().reshape(b, t, -1)
+    return F.linear(ctx, wo), k, v
 
 
 def lm_head_shifted_ce(hidden_states, lm_head_weight, labels, ignore_index=-100):

@@ -204,7 +204,43 @@ def golden_lm_head_loss():
          source="reference Model/model.py:429-438 (lm_head + shifted CrossEntropyLoss), config-1 MLLAMA, labels with ignore_index")
 
 
+def golden_attention():
+    """The reference's own GroupQueryAttention + KVCache + LLAMARotaryEmbedding + Llama3Model._prepare_attention_mask
+    (Model/model.py:12-29, 176-198, 220-254, 304-319): a prefill with a padded batch, then one KV-cached decode step with
+    EXPLICIT position_ids.  Two head geometries the tcgen05 kernel supports: head_dim 64 and 128."""
+    for tag, hidden, heads, kv, t in (("d64", 256, 4, 2, 40), ("d128", 512, 4, 1, 150)):
+        torch.manual_seed(77)
+        cfg = M.LLAMA32Config(vocab_size=64, hidden_size=hidden, n_heads=heads, n_layers=1, hidden_dim=128, n_kv_groups=kv,
+                              dtype=torch.float32)
+        att = M.GroupQueryAttention(cfg, layer_idx=0, dtype=torch.float32).eval()
+        lm = M.Llama3Model(cfg)                                   # only for its own mask / position helpers
+        with torch.no_grad():
+            for p_ in att.parameters():
+                p_.copy_(rep(p_))
+        b = 2
+        x = rep(torch.randn(b, t, hidden))
+        mask2d = torch.ones(b, t)
+        mask2d[1, t - 7:] = 0                                     # right-padded second sequence
+        mask4d = lm._prepare_attention_mask(mask2d, x)
+        pos = lm._prepare_position_ids(None, x)
+        cache = M.KVCache()
+        with torch.no_grad():
+            y = att(x, attention_mask=mask4d, position_ids=pos, kv_cache=cache)
+            x1 = rep(torch.randn(b, 1, hidden))
+            mask1 = lm._prepare_attention_mask(None, x1)          # what the reference builds for a decode step: [B,1,1,1] zeros
+            pos1 = torch.full((b, 1), t, dtype=torch.long)        # explicit: the cache holds t tokens
+            y1 = att(x1, attention_mask=mask1, position_ids=pos1, kv_cache=cache)
+        sd = att.state_dict()
+        save(f"attention_{tag}.npz", x=x, mask2d=mask2d, position_ids=pos, y_prefill=y, x_decode=x1, position_ids_decode=pos1,
+             y_decode=y1, cache_k=cache.key_cache[0], cache_v=cache.value_cache[0],
+             wq_bits=bits(sd["W_query.weight"]), wk_bits=bits(sd["W_key.weight"]), wv_bits=bits(sd["W_value.weight"]),
+             wo_bits=bits(sd["out_proj.weight"]), n_heads=np.int32(heads), n_kv=np.int32(kv), rope_base=np.float32(cfg.rope_base),
+             state_dict_keys=np.array(sorted(sd.keys())),
+             source="reference Model/model.py:220-254 GroupQueryAttention with KVCache (:12-29), prefill + one decode step")
+
+
 if __name__ == "__main__":
+    golden_attention()
     golden_lm_head_loss()
     golden_rmsnorm()
     golden_ffn()

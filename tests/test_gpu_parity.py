@@ -781,3 +781,76 @@ def test_lm_head_ce_forward_backward_vs_oracle(batch, seq, hidden, vocab, frac_i
     assert abs(loss.item() - loss_r.item()) <= 5e-3 * abs(loss_r.item()), (loss.item(), loss_r.item())
     close(hs.grad, hr.grad, (2e-2, 2.0 ** -5), "d_hidden")
     close(head.weight.grad, wr.grad, (2e-2, 2.0 ** -5), "d_lm_head_weight")
+
+
+# ----------------------------------------------------------------------------------------------- f3: attention + KV cache
+class _Cfg:
+    def __init__(self, hidden, heads, kv, rope_base=500000.0):
+        self.hidden_size, self.n_heads, self.n_kv_groups, self.rope_base = hidden, heads, kv, rope_base
+
+
+def _gqa_module(hidden, heads, kv, wq, wk, wv, wo, rope_base=500000.0, layer_idx=0):
+    att = L.GroupQueryAttention(_Cfg(hidden, heads, kv, rope_base), layer_idx=layer_idx).to(DEV, torch.bfloat16).eval()
+    with torch.no_grad():
+        att.W_query.weight.copy_(dev(wq)); att.W_key.weight.copy_(dev(wk)); att.W_value.weight.copy_(dev(wv))
+        att.out_proj.weight.copy_(dev(wo))
+    return att
+
+
+@pytest.mark.parametrize("tag", ["d64", "d128"])
+def test_attention_vs_reference_outputs(tag):
+    """GroupQueryAttention drop-in (RoPE + preallocated KV cache + flash-style tcgen05 attention) against the reference's own
+    module outputs: padded prefill, then a KV-cached decode step with explicit position_ids; cache contents included."""
+    g = load_golden(f"attention_{tag}.npz")
+    heads, kv = int(g["n_heads"]), int(g["n_kv"])
+    b, t, hidden = g["x"].shape
+    att = _gqa_module(hidden, heads, kv, g["wq"], g["wk"], g["wv"], g["wo"], float(g["rope_base"]))
+    assert sorted(att.state_dict().keys()) == list(g["state_dict_keys"])
+    mask4d = O.causal_padding_mask(g["mask2d"], t).to(DEV, torch.bfloat16)
+    cache = L.KVCache()
+    with torch.no_grad():
+        y = att(dev(g["x"]), attention_mask=mask4d, position_ids=g["position_ids"].to(DEV), kv_cache=cache)
+        assert cache.num_items() == t
+        y1 = att(dev(g["x_decode"]), attention_mask=torch.zeros(b, 1, 1, 1, device=DEV, dtype=torch.bfloat16),
+                 position_ids=g["position_ids_decode"].to(DEV), kv_cache=cache)
+    close(y, g["y_prefill"], FWD, "prefill output")
+    close(y1, g["y_decode"], FWD, "decode output")
+    assert cache.num_items() == t + 1
+    close(cache.key_cache[0], g["cache_k"], FWD, "cache keys (rotated)")
+    close(cache.value_cache[0], g["cache_v"], FWD, "cache values")
+
+
+@pytest.mark.parametrize("b,t,hidden,heads,kv,steps", [(2, 300, 1024, 8, 2, 3), (1, 512, 4096, 32, 8, 2), (3, 129, 512, 8, 8, 1),
+                                                     (2, 64, 256, 4, 1, 2)])
+def test_attention_shapes_vs_oracle(b, t, hidden, heads, kv, steps):
+    """More geometries (the 11B one: 32 query / 8 KV heads of 128) against the oracle: causal prefill with left-over tiles,
+    a padded batch, several decode steps growing the preallocated cache, and the no-mask (non-causal) call."""
+    gen = torch.Generator().manual_seed(b * 1000 + t)
+    bf = O.bf16_representable
+    d = hidden // heads
+    mk = lambda o, i: bf((torch.rand(o, i, generator=gen) * 2 - 1) / i ** 0.5)
+    wq, wk, wv, wo = mk(heads * d, hidden), mk(kv * d, hidden), mk(kv * d, hidden), mk(hidden, heads * d)
+    att = _gqa_module(hidden, heads, kv, wq, wk, wv, wo)
+    x = bf(torch.randn(b, t, hidden, generator=gen))
+    mask2d = torch.ones(b, t)
+    if b > 1:
+        mask2d[-1, t - 5:] = 0
+    pos = torch.arange(t)[None].expand(b, -1).contiguous()
+    cache = L.KVCache(capacity=t + 1)                       # forces one re-allocation when steps > 1
+    with torch.no_grad():
+        y = att(dev(x), attention_mask=O.causal_padding_mask(mask2d, t).to(DEV, torch.bfloat16), position_ids=pos.to(DEV), kv_cache=cache)
+    yr, kr, vr = O.gqa_attention(x, wq, wk, wv, wo, heads, kv, pos, O.causal_padding_mask(mask2d, t))
+    close(y, yr, FWD, "prefill")
+    for sidx in range(steps):
+        x1 = bf(torch.randn(b, 1, hidden, generator=gen))
+        p1 = torch.full((b, 1), t + sidx, dtype=torch.long)
+        with torch.no_grad():
+            y1 = att(dev(x1), attention_mask=torch.zeros(b, 1, 1, 1, device=DEV, dtype=torch.bfloat16), position_ids=p1.to(DEV), kv_cache=cache)
+        y1r, kr, vr = O.gqa_attention(x1, wq, wk, wv, wo, heads, kv, p1, torch.zeros(b, 1, 1, 1), past_k=kr, past_v=vr)
+        close(y1, y1r, FWD, f"decode step {sidx}")
+    assert cache.num_items() == t + steps
+    # attention_mask=None: no masking at all (the reference adds nothing), no cache
+    with torch.no_grad():
+        yn = att(dev(x), attention_mask=None, position_ids=pos.to(DEV), kv_cache=None)
+    ynr, _, _ = O.gqa_attention(x, wq, wk, wv, wo, heads, kv, pos, None)
+    close(yn, ynr, FWD, "no mask")
