@@ -489,6 +489,52 @@ def extra_numbers(dev, peaks):
                                              "the softmax statistics (Model/model.py:429-438); eager = nn.Linear + F.cross_entropy in bf16"}
     del head, hs, labels
     torch.cuda.empty_cache()
+
+    # ---- attention at the 11B geometry: 32 query / 8 KV heads of 128, 4 x 2048 tokens, causal prefill;
+    #      then KV-cached decode steps at batch 64 with 2048 cached tokens.  Baselines on the same GPU: the reference's own
+    #      expressions (materialised scores + repeat_kv, Model/model.py:238-253) and torch's fused SDPA.
+    from llama32_b200 import ops as _ops
+    Bq, Tq, NH, NKV, D = 4, 2048, 32, 8, 128
+    q = rnd(Bq, Tq, NH * D)
+    ck, cv = torch.zeros(Bq, NKV, Tq, D, device=dev, dtype=dt), torch.zeros(Bq, NKV, Tq, D, device=dev, dtype=dt)
+    ck.copy_(rnd(Bq, NKV, Tq, D)); cv.copy_(rnd(Bq, NKV, Tq, D))
+    fl_att = 4.0 * Bq * NH * Tq * Tq * D / 2                          # causal: half of the score matrix
+    t_ours = _time_cuda(lambda: _ops.gqa_attention_forward(q, ck, cv, Tq, 0, causal=True), 10, warm=3)
+    q4 = q.view(Bq, Tq, NH, D).transpose(1, 2)
+
+    def sdpa():
+        with torch.no_grad():
+            torch.nn.functional.scaled_dot_product_attention(q4, ck, cv, is_causal=True, enable_gqa=True)
+
+    def eager_ref():
+        with torch.no_grad():
+            kk = ck[:, :, None].expand(Bq, NKV, NH // NKV, Tq, D).reshape(Bq, NH, Tq, D)
+            vv = cv[:, :, None].expand(Bq, NKV, NH // NKV, Tq, D).reshape(Bq, NH, Tq, D)
+            sc = q4 @ kk.transpose(2, 3) + causal_mask
+            (torch.softmax(sc / D ** 0.5, dim=-1) @ vv).transpose(1, 2).contiguous()
+    causal_mask = torch.triu(torch.full((Tq, Tq), float("-inf"), device=dev, dtype=dt), diagonal=1)[None, None]
+    try:
+        t_sdpa = _time_cuda(sdpa, 10, warm=3)
+    except Exception:   # noqa: BLE001 -- a baseline that this torch build cannot run is reported as absent
+        t_sdpa = None
+    t_eager = _time_cuda(eager_ref, 5, warm=2)
+    out["attention_prefill_11b_4x2048"] = {"ms": t_ours * 1e3, "TFLOPs": fl_att / t_ours / 1e12, "ms_reference_expressions": t_eager * 1e3,
+                                           "speedup_vs_reference_expressions": t_eager / t_ours,
+                                           "ms_torch_sdpa": (t_sdpa * 1e3 if t_sdpa else None),
+                                           "what": "causal GQA forward, 32/8 heads x 128, bf16: flash-style tcgen05 kernel vs the reference's "
+                                                   "materialised-score expressions (Model/model.py:244-252) and torch SDPA (library flash kernel)"}
+    del q, q4, ck, cv, causal_mask
+    Bd, Lk = 64, 2048
+    qd = rnd(Bd, 1, NH * D)
+    ck, cv = rnd(Bd, NKV, Lk + 64, D), rnd(Bd, NKV, Lk + 64, D)
+    kv_bytes = 2.0 * Bd * NKV * Lk * D * 2
+    t_dec = _time_cuda(lambda: _ops.gqa_attention_forward(qd, ck, cv, Lk, Lk - 1, causal=True), 50, warm=5)
+    out["attention_decode_11b_b64_kv2048"] = {"us": t_dec * 1e6, "GBps_kv_read": kv_bytes / t_dec / 1e9,
+                                              "frac_of_measured_hbm": kv_bytes / t_dec / 1e9 / hbm, "algorithmic_bytes": kv_bytes,
+                                              "what": "one decode step of attention for 64 sequences with 2048 cached tokens each "
+                                                      "(K and V of the 8 KV heads read once: HBM-bound)"}
+    del qd, ck, cv
+    torch.cuda.empty_cache()
     return out
 
 

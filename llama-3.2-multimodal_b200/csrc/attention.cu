@@ -148,16 +148,19 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
         if (ok && keep_row != nullptr) ok = keep_row[key] != 0;
         return ok;
     };
-    auto fold_pv = [&]() {                          // o += (P V of the previous tile), straight from TMEM
+    // o = o * alpha_prev + (P V of the previous tile), straight from TMEM.  alpha_prev rescales the old sum from the row
+    // maximum it was built with to the maximum the previous tile's probabilities used -- one FMA per element.
+    auto fold_pv = [&](float alpha_prev) {
 #pragma unroll
         for (int c = 0; c < kD / 32; ++c) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[c * 32 + j] += __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) o[c * 32 + j] = fmaf(o[c * 32 + j], alpha_prev, __uint_as_float(v[j]));
         }
     };
+    float alpha_prev = 1.f;
 
     for (int t = 0; t < ntiles; ++t) {
         const int s = t & 1;
@@ -184,6 +187,8 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
         }
         mbar_wait(bar_s, t & 1u);
         tc_fence_after();
+        // A tile every key of which this row may see needs no per-element predicates (all but the diagonal / last tiles)
+        const bool full = (j0 + kKvTile <= p.kv_len) && (!p.causal || j0 + kKvTile - 1 <= qpos) && keep_row == nullptr;
         // ---- pass 1 over this row's 64 scores: the tile maximum (scores stay in TMEM, they are read again in pass 2)
         float tmax = -INFINITY;
 #pragma unroll
@@ -191,10 +196,16 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_s + lane_off + hf * 32, v);
             tmem_ld_wait();
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (visible(j0 + hf * 32 + j)) tmax = fmaxf(tmax, __uint_as_float(v[j]) * p.scale_log2);
+                for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, __uint_as_float(v[j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (visible(j0 + hf * 32 + j)) tmax = fmaxf(tmax, __uint_as_float(v[j]));
+            }
         }
+        tmax *= p.scale_log2;                                         // the scale is positive: max commutes with it
         const float m_new = fmaxf(m, tmax);
         const bool dead = (m_new == -INFINITY);                       // nothing visible so far
         const float alpha = dead ? 1.f : fast_exp2(m - m_new);       // m = -inf: exp2(-inf) = 0 (o and l are 0 anyway)
@@ -202,13 +213,12 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
         if (t > 0) {
             mbar_wait(bar_o, (t - 1) & 1u);
             tc_fence_after();
-            fold_pv();
+            fold_pv(alpha_prev);
             if (tid == 0 && t + 1 < ntiles) load_v(t + 1);
         }
-#pragma unroll
-        for (int j = 0; j < kD; ++j) o[j] *= alpha;
-        // ---- pass 2: probabilities (rounded to the storage type: the row sum uses what the MMA will see) -> P in shared
-        // memory, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of 16 bytes per row
+        alpha_prev = alpha;
+        // ---- pass 2: probabilities -> P in shared memory, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of
+        // 16 bytes per row
         float psum = 0.f;
         uint8_t* prow = sp + tid * 128;
 #pragma unroll
@@ -217,14 +227,23 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
             tmem_ld_32x32b_x32(tmem_s + lane_off + hf * 32, v);
             tmem_ld_wait();
             uint32_t pk[16];
+            if (full) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int key = j0 + hf * 32 + 2 * j;
-                const float p0 = (!dead && visible(key)) ? fast_exp2(__uint_as_float(v[2 * j]) * p.scale_log2 - m_new) : 0.f;
-                const float p1 = (!dead && visible(key + 1)) ? fast_exp2(__uint_as_float(v[2 * j + 1]) * p.scale_log2 - m_new) : 0.f;
-                pk[j] = Pack2<T>::pack(p0, p1);
-                const float2 pr = Pack2<T>::unpack(pk[j]);
-                psum += pr.x + pr.y;
+                for (int j = 0; j < 16; ++j) {
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_new));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_new));
+                    pk[j] = Pack2<T>::pack(p0, p1);
+                    psum += p0 + p1;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int key = j0 + hf * 32 + 2 * j;
+                    const float p0 = (!dead && visible(key)) ? fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_new)) : 0.f;
+                    const float p1 = (!dead && visible(key + 1)) ? fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_new)) : 0.f;
+                    pk[j] = Pack2<T>::pack(p0, p1);
+                    psum += p0 + p1;
+                }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -252,7 +271,7 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
     if (ntiles > 0) {
         mbar_wait(bar_o, (ntiles - 1) & 1u);
         tc_fence_after();
-        fold_pv();
+        fold_pv(alpha_prev);
     }
     if (row_ok) {
         const float inv = l > 0.f ? 1.f / l : 0.f;     // a row without any visible key gives zeros
@@ -387,6 +406,14 @@ int gqa_attention(const void* q, const void* cache_k, const void* cache_v, const
                   cudaStream_t s) {
     if (head_dim != 64 && head_dim != 128) return L32_ERR_BAD_SHAPE;
     if (batch <= 0 || q_len <= 0) return L32_OK;
+    if (q_len == 1 && heads > kv_heads && keep == nullptr) {
+        // Decode: the query heads of one KV group become the ROWS of one tile (q is [batch, kv_heads, group, head_dim] in
+        // memory), so every K / V tile is read once per group instead of once per query head.  One query per sequence sees
+        // the whole cache: no causal predicate needed.
+        const int group = heads / kv_heads;
+        return gqa_attention(q, cache_k, cache_v, nullptr, out, batch * kv_heads, group, 1, 1, head_dim, max_len, kv_len, 0, 0,
+                             dtype, s);
+    }
     AttnParams p;
     memset(&p, 0, sizeof(p));
     p.out = out;

@@ -45,5 +45,22 @@ elif what == "train":
     for i in range(3):
         y, gc, uc = ops.ffn_forward(x, wg, wu, wd, want_cache=True)
         ops.ffn_backward(dy, x, wg, wu, wd, gc, uc)
+elif what == "attention":
+    B, T, NH, NKV, D = 4, 2048, 32, 8, 128
+    q = rnd(B, T, NH * D)
+    ck, cv = rnd(B, NKV, T, D), rnd(B, NKV, T, D)
+    for i in range(3):
+        ops.gqa_attention_forward(q, ck, cv, T, 0, causal=True)
+    qd = rnd(64, 1, NH * D)
+    ckd, cvd = rnd(64, NKV, 2112, D), rnd(64, NKV, 2112, D)
+    for i in range(3):
+        ops.gqa_attention_forward(qd, ckd, cvd, 2048, 2047, causal=True)
+elif what == "lmhead":
+    T, H, V = 8192, 4096, 128256
+    w = uni(V, H)
+    hs = rnd(T, H)
+    labels = torch.randint(0, V, (T,), device=dev)
+    for i in range(3):
+        ops.lm_head_ce_forward(hs, w, labels)
 torch.cuda.synchronize()
 print("done", what)
