@@ -62,8 +62,9 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
     uint64_t* bar_q = reinterpret_cast<uint64_t*>(sp + kPBytes);
     uint64_t* bar_k = bar_q + 1;                           // [2] K tile landed
     uint64_t* bar_v = bar_k + 2;                           // [2] V tile landed
-    uint64_t* bar_s = bar_v + 2;                           // S = Q K^T complete
-    uint64_t* bar_o = bar_s + 1;                           // P V complete (P and the V stage may be reused)
+    uint64_t* bar_s = bar_v + 2;                           // [2] S = Q K^T complete (two accumulators: S of tile t + 1 runs
+                                                           //     on the tensor cores while the softmax of tile t is computed)
+    uint64_t* bar_o = bar_s + 2;                           // P V complete (P and the V stage may be reused)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
 
     const int tid = threadIdx.x;
@@ -82,11 +83,12 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
             mbar_init(&bar_k[i], 1);
             mbar_init(&bar_v[i], 1);
         }
-        mbar_init(bar_s, 1);
+        mbar_init(&bar_s[0], 1);
+        mbar_init(&bar_s[1], 1);
         mbar_init(bar_o, 1);
         fence_mbar_init();
     }
-    constexpr uint32_t kTmemCols = (kKvTile + kD) <= 128 ? 128u : 256u;
+    constexpr uint32_t kTmemCols = 256u;                   // S[2] (2 x 64 columns) + P V (kD columns)
     if (warp == 1) {
         tmem_alloc<1>(tmem_slot, kTmemCols);
         tmem_relinquish<1>();
@@ -95,8 +97,7 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const uint32_t tmem_s = tmem_base;             // S: columns [0, 64)
-    const uint32_t tmem_o = tmem_base + kKvTile;   // P V: columns [64, 64 + kD)
+    const uint32_t tmem_o = tmem_base + 2 * kKvTile;   // S of even / odd tiles: columns [0, 64) / [64, 128); P V: [128, 128 + kD)
     pdl_launch_dependents();
     pdl_wait_prior_grid();
 
@@ -122,6 +123,21 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
         for (int a = 0; a < kDAtoms; ++a)
             tma_load_2d(sv + s * kKBytes + a * (kKvTile * 128), &p.map_v, &bar_v[s], a * 64, kv_row0 + t * kKvTile, kEvictNormal);
     };
+    // S[128, 64] = Q[128, kD] K[64, kD]^T of tile t into accumulator t & 1
+    auto issue_s = [&](int t) {
+        const int s = t & 1;
+        mbar_wait(&bar_k[s], (t >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sq), k_addr = smem_u32(sk + s * kKBytes);
+#pragma unroll
+        for (int kk = 0; kk < kD / kUmmaKAtt; ++kk) {
+            const uint32_t qoff = (kk / 4) * (kQTile * 128) + (kk % 4) * 32;      // column block, then 32 B per K step
+            const uint32_t koff = (kk / 4) * (kKvTile * 128) + (kk % 4) * 32;
+            umma_f16<1>(tmem_base + s * kKvTile, make_smem_desc_sw128(q_addr + qoff, 0, 1024),
+                        make_smem_desc_sw128(k_addr + koff, 0, 1024), p.idesc_s, kk > 0 ? 1u : 0u);
+        }
+        umma_commit<1>(&bar_s[s]);
+    };
     if (tid == 0) {
         mbar_arrive_expect_tx(bar_q, kQBytes);
 #pragma unroll
@@ -130,6 +146,12 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
         if (ntiles > 0) {
             load_k(0);
             load_v(0);
+            if (ntiles > 1) {
+                load_k(1);
+                load_v(1);
+            }
+            mbar_wait(bar_q, 0);
+            issue_s(0);
         }
     }
 
@@ -137,10 +159,12 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
     const int qi = q0 + tid;                       // query index inside the sequence
     const int qpos = p.past_len + qi;              // its absolute position
     const bool row_ok = qi < p.q_len;
-    float o[kD];
-#pragma unroll
-    for (int j = 0; j < kD; ++j) o[j] = 0.f;
-    float m = -INFINITY, l = 0.f;
+    // Online softmax with a LAZY reference: the output accumulator stays in TMEM across the key tiles (P V accumulates
+    // there) and is rescaled -- a TMEM read-modify-write of this thread's row -- only when the row maximum outgrows the
+    // reference by more than 2^kLazyLog2 (probabilities then stay <= 2^kLazyLog2: exact in fp32, harmless in the 16-bit P).
+    // TMEM reads are the scarce resource here (64 B / clock / SM): S is read once per tile, O once at the end.
+    constexpr float kLazyLog2 = 8.0f;
+    float m_ref = -INFINITY, l = 0.f;
     const uint32_t lane_off = (warp * 32u) << 16;
     const uint8_t* keep_row = p.keep != nullptr ? p.keep + static_cast<size_t>(b) * p.kv_len : nullptr;
     auto visible = [&](int key) {
@@ -148,48 +172,23 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
         if (ok && keep_row != nullptr) ok = keep_row[key] != 0;
         return ok;
     };
-    // o = o * alpha_prev + (P V of the previous tile), straight from TMEM.  alpha_prev rescales the old sum from the row
-    // maximum it was built with to the maximum the previous tile's probabilities used -- one FMA per element.
-    auto fold_pv = [&](float alpha_prev) {
-#pragma unroll
-        for (int c = 0; c < kD / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[c * 32 + j] = fmaf(o[c * 32 + j], alpha_prev, __uint_as_float(v[j]));
-        }
-    };
-    float alpha_prev = 1.f;
 
     for (int t = 0; t < ntiles; ++t) {
         const int s = t & 1;
         const int j0 = t * kKvTile;
-        if (tid == 0) {
-            // K stage (t + 1) & 1 was last read by S of tile t - 1, complete long ago; V needs P V of tile t - 1 (below)
-            if (t + 1 < ntiles) {
-                load_k(t + 1);
-                if (t == 0) load_v(1);
-            }
-            if (t == 0) mbar_wait(bar_q, 0);
-            mbar_wait(&bar_k[s], (t >> 1) & 1u);
-            tc_fence_after();
-            // S[128, 64] = Q[128, kD] K[64, kD]^T
-            const uint32_t q_addr = smem_u32(sq), k_addr = smem_u32(sk + s * kKBytes);
-#pragma unroll
-            for (int kk = 0; kk < kD / kUmmaKAtt; ++kk) {
-                const uint32_t qoff = (kk / 4) * (kQTile * 128) + (kk % 4) * 32;      // column block, then 32 B per K step
-                const uint32_t koff = (kk / 4) * (kKvTile * 128) + (kk % 4) * 32;
-                umma_f16<1>(tmem_s, make_smem_desc_sw128(q_addr + qoff, 0, 1024), make_smem_desc_sw128(k_addr + koff, 0, 1024),
-                            p.idesc_s, kk > 0 ? 1u : 0u);
-            }
-            umma_commit<1>(bar_s);
-        }
-        mbar_wait(bar_s, t & 1u);
+        const uint32_t tmem_s = tmem_base + s * kKvTile;
+        mbar_wait(&bar_s[s], (t >> 1) & 1u);
         tc_fence_after();
-        // A tile every key of which this row may see needs no per-element predicates (all but the diagonal / last tiles)
+        if (tid == 0 && t + 1 < ntiles) {
+            // S of tile t is complete: its K stage is free for tile t + 2, and tile t + 1's S can run while this tile's
+            // softmax is computed (its accumulator was drained by every thread before the barrier that ended tile t - 1)
+            if (t + 2 < ntiles) load_k(t + 2);
+            issue_s(t + 1);
+        }
+        // ---- this row's 64 scores, scaled to the log2 domain; keys the row may not see become -inf.
+        // A tile every key of which is visible needs no per-element predicates (all but the diagonal / last tiles).
         const bool full = (j0 + kKvTile <= p.kv_len) && (!p.causal || j0 + kKvTile - 1 <= qpos) && keep_row == nullptr;
-        // ---- pass 1 over this row's 64 scores: the tile maximum (scores stay in TMEM, they are read again in pass 2)
+        float sc[kKvTile];
         float tmax = -INFINITY;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -198,92 +197,109 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
             tmem_ld_wait();
             if (full) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, __uint_as_float(v[j]));
+                for (int j = 0; j < 32; ++j) {
+                    sc[hf * 32 + j] = __uint_as_float(v[j]) * p.scale_log2;
+                    tmax = fmaxf(tmax, sc[hf * 32 + j]);
+                }
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (visible(j0 + hf * 32 + j)) tmax = fmaxf(tmax, __uint_as_float(v[j]));
+                for (int j = 0; j < 32; ++j) {
+                    sc[hf * 32 + j] = visible(j0 + hf * 32 + j) ? __uint_as_float(v[j]) * p.scale_log2 : -INFINITY;
+                    tmax = fmaxf(tmax, sc[hf * 32 + j]);
+                }
             }
         }
-        tmax *= p.scale_log2;                                         // the scale is positive: max commutes with it
-        const float m_new = fmaxf(m, tmax);
-        const bool dead = (m_new == -INFINITY);                       // nothing visible so far
-        const float alpha = dead ? 1.f : fast_exp2(m - m_new);       // m = -inf: exp2(-inf) = 0 (o and l are 0 anyway)
-        // ---- the previous tile's P V: wait, fold into the running output, free the V stage
+        // ---- the previous tile's P V must be complete before P is overwritten and before the accumulator is touched
         if (t > 0) {
             mbar_wait(bar_o, (t - 1) & 1u);
             tc_fence_after();
-            fold_pv(alpha_prev);
-            if (tid == 0 && t + 1 < ntiles) load_v(t + 1);
+            if (tid == 0 && t + 1 < ntiles) load_v(t + 1);      // V stage (t + 1) & 1 was read by P V of tile t - 1
         }
-        alpha_prev = alpha;
-        // ---- pass 2: probabilities -> P in shared memory, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of
-        // 16 bytes per row
+        // tcgen05.ld / .st are warp-collective: the branch is taken by the whole warp as soon as one of its rows needs a new
+        // reference; the other rows rescale by exactly 1
+        const bool want = tmax > m_ref + kLazyLog2;                   // also true for the first visible key (m_ref = -inf)
+        if (__any_sync(0xffffffffu, want)) {
+            const float alpha = want ? fast_exp2(m_ref - tmax) : 1.f;   // m_ref = -inf: 0
+            l *= alpha;
+            if (t > 0) {                                             // tile 0 overwrites the accumulator (no rescale needed)
+#pragma unroll
+                for (int c = 0; c < kD / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+                    tmem_st_32x32b_x32(tmem_o + lane_off + c * 32, v);
+                }
+                tmem_st_wait();
+            }
+            if (want) m_ref = tmax;
+        }
+        // ---- probabilities -> P in shared memory, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of 16 bytes
         float psum = 0.f;
         uint8_t* prow = sp + tid * 128;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_s + lane_off + hf * 32, v);
-            tmem_ld_wait();
-            uint32_t pk[16];
-            if (full) {
+        for (int c = 0; c < 8; ++c) {
+            uint32_t pk[4];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_new));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_new));
-                    pk[j] = Pack2<T>::pack(p0, p1);
-                    psum += p0 + p1;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int key = j0 + hf * 32 + 2 * j;
-                    const float p0 = (!dead && visible(key)) ? fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, -m_new)) : 0.f;
-                    const float p1 = (!dead && visible(key + 1)) ? fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, -m_new)) : 0.f;
-                    pk[j] = Pack2<T>::pack(p0, p1);
-                    psum += p0 + p1;
-                }
+            for (int j = 0; j < 4; ++j) {
+                // -inf - m_ref = -inf -> 0 (m_ref is finite whenever any key of the row has been visible; a dead row has
+                // m_ref = -inf and sc = -inf: -inf - -inf = nan, hence the guard)
+                const float a0 = sc[c * 8 + 2 * j], a1 = sc[c * 8 + 2 * j + 1];
+                const float p0 = (a0 == -INFINITY) ? 0.f : fast_exp2(a0 - m_ref);
+                const float p1 = (a1 == -INFINITY) ? 0.f : fast_exp2(a1 - m_ref);
+                pk[j] = Pack2<T>::pack(p0, p1);
+                psum += p0 + p1;
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4*>(prow + (((hf * 4 + c) ^ (tid & 7)) << 4)) =
-                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        l = l * alpha + psum;
-        m = m_new;
+        l += psum;
         fence_proxy_async_smem();
         tc_fence_before();
-        __syncthreads();                                // every row of P is in place; every thread is done with S and with P V
+        __syncthreads();                                // every row of P is in place; every thread is done with S and with O
         if (tid == 0) {
             tc_fence_after();
             mbar_wait(&bar_v[s], (t >> 1) & 1u);
             tc_fence_after();
-            // O_tile[128, kD] = P[128, 64] V[64, kD]   (V consumed MN-major: [64 keys][kD])
+            // O[128, kD] (+)= P[128, 64] V[64, kD]   (V consumed MN-major: [64 keys][kD]); tile 0 overwrites
             const uint32_t p_addr = smem_u32(sp), v_addr = smem_u32(sv + s * kKBytes);
 #pragma unroll
             for (int kk = 0; kk < kKvTile / kUmmaKAtt; ++kk)
                 umma_f16<1>(tmem_o, make_smem_desc_sw128(p_addr + kk * 32, 0, 1024),
-                            make_smem_desc_sw128(v_addr + kk * (kUmmaKAtt * 128), kKvTile * 128, 1024), p.idesc_o, kk > 0 ? 1u : 0u);
+                            make_smem_desc_sw128(v_addr + kk * (kUmmaKAtt * 128), kKvTile * 128, 1024), p.idesc_o,
+                            (t > 0 || kk > 0) ? 1u : 0u);
             umma_commit<1>(bar_o);
         }
     }
     if (ntiles > 0) {
         mbar_wait(bar_o, (ntiles - 1) & 1u);
         tc_fence_after();
-        fold_pv(alpha_prev);
     }
-    if (row_ok) {
-        const float inv = l > 0.f ? 1.f / l : 0.f;     // a row without any visible key gives zeros
-        T* dst = static_cast<T*>(p.out) + (static_cast<size_t>(b) * p.q_len + qi) * (static_cast<size_t>(p.heads) * kD) + head * kD;
+    {
+        const float inv = (ntiles > 0 && l > 0.f) ? 1.f / l : 0.f;     // a row without any visible key gives zeros
+        T* dst = static_cast<T*>(p.out) + (static_cast<size_t>(b) * p.q_len + (row_ok ? qi : 0)) * (static_cast<size_t>(p.heads) * kD) +
+                 head * kD;
 #pragma unroll
-        for (int c = 0; c < kD / 8; ++c) {
-            uint4 w;
-            w.x = Pack2<T>::pack(o[8 * c] * inv, o[8 * c + 1] * inv);
-            w.y = Pack2<T>::pack(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
-            w.z = Pack2<T>::pack(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
-            w.w = Pack2<T>::pack(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
-            *reinterpret_cast<uint4*>(dst + 8 * c) = w;
+        for (int c = 0; c < kD / 32; ++c) {
+            uint32_t v[32];
+            if (ntiles > 0) {                          // CTA-uniform; the loads are warp-collective (every lane takes part)
+                tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            if (row_ok) {
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    uint4 w;
+                    w.x = Pack2<T>::pack(__uint_as_float(v[8 * j4]) * inv, __uint_as_float(v[8 * j4 + 1]) * inv);
+                    w.y = Pack2<T>::pack(__uint_as_float(v[8 * j4 + 2]) * inv, __uint_as_float(v[8 * j4 + 3]) * inv);
+                    w.z = Pack2<T>::pack(__uint_as_float(v[8 * j4 + 4]) * inv, __uint_as_float(v[8 * j4 + 5]) * inv);
+                    w.w = Pack2<T>::pack(__uint_as_float(v[8 * j4 + 6]) * inv, __uint_as_float(v[8 * j4 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c * 32 + 8 * j4) = w;
+                }
+            }
         }
     }
     tc_fence_before();
