@@ -23,9 +23,9 @@
 namespace l32 {
 namespace {
 
-constexpr int kQTile = 128;      // query rows per CTA = TMEM lanes = threads
+constexpr int kQTile = 128;      // query rows per CTA = TMEM lanes = softmax threads
 constexpr int kKvTile = 64;      // keys per iteration (one 128-byte swizzle atom of P)
-constexpr int kAttThreads = 128;
+constexpr int kAttThreads = 160;   // warps 0-3: softmax (one query row per thread); warp 4: TMA producer + MMA issuer
 constexpr int kUmmaKAtt = 16;
 
 struct AttnParams {
@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
     uint64_t* bar_s = bar_v + 2;                           // [2] S = Q K^T complete (two accumulators: S of tile t + 1 runs
                                                            //     on the tensor cores while the softmax of tile t is computed)
     uint64_t* bar_o = bar_s + 2;                           // P V complete (P and the V stage may be reused)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
+    uint64_t* bar_p = bar_o + 1;                           // P of the tile is in shared memory, S and O are drained (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_p + 1);
 
     const int tid = threadIdx.x;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -82,14 +83,14 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_k[i], 1);
             mbar_init(&bar_v[i], 1);
+            mbar_init(&bar_s[i], 1);
         }
-        mbar_init(&bar_s[0], 1);
-        mbar_init(&bar_s[1], 1);
         mbar_init(bar_o, 1);
+        mbar_init(bar_p, kQTile);
         fence_mbar_init();
     }
     constexpr uint32_t kTmemCols = 256u;                   // S[2] (2 x 64 columns) + P V (kD columns)
-    if (warp == 1) {
+    if (warp == 4) {
         tmem_alloc<1>(tmem_slot, kTmemCols);
         tmem_relinquish<1>();
     }
@@ -108,42 +109,47 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
     const int ntiles = (hi + kKvTile - 1) / kKvTile;
     const int kv_row0 = (b * p.kv_heads + kvh) * p.max_len;
 
-    // K tile, K-major: [64 keys][64 dims] per column block;  V tile: the same boxes, consumed as an MN-major B operand
-    auto load_k = [&](int t) {
-        const int s = t & 1;
-        mbar_arrive_expect_tx(&bar_k[s], kKBytes);
+    if (warp == 4) {
+        // ------------------------------------------------------------------ TMA producer + MMA issuer (one thread)
+        // The softmax warps never issue anything: the serial descriptor / tcgen05.mma stream of this thread is off their
+        // critical path (measured: with the issuer inside softmax warp 0 the other warps spent a third of the kernel at the
+        // CTA barrier waiting for it).
+        if (lane_id() == 0 && ntiles > 0) {
+            // K tile, K-major: [64 keys][64 dims] per column block;  V tile: the same boxes, consumed as an MN-major B operand
+            auto load_k = [&](int t) {
+                const int s = t & 1;
+                mbar_arrive_expect_tx(&bar_k[s], kKBytes);
 #pragma unroll
-        for (int a = 0; a < kDAtoms; ++a)
-            tma_load_2d(sk + s * kKBytes + a * (kKvTile * 128), &p.map_k, &bar_k[s], a * 64, kv_row0 + t * kKvTile, kEvictNormal);
-    };
-    auto load_v = [&](int t) {
-        const int s = t & 1;
-        mbar_arrive_expect_tx(&bar_v[s], kKBytes);
+                for (int a = 0; a < kDAtoms; ++a)
+                    tma_load_2d(sk + s * kKBytes + a * (kKvTile * 128), &p.map_k, &bar_k[s], a * 64, kv_row0 + t * kKvTile, kEvictNormal);
+            };
+            auto load_v = [&](int t) {
+                const int s = t & 1;
+                mbar_arrive_expect_tx(&bar_v[s], kKBytes);
 #pragma unroll
-        for (int a = 0; a < kDAtoms; ++a)
-            tma_load_2d(sv + s * kKBytes + a * (kKvTile * 128), &p.map_v, &bar_v[s], a * 64, kv_row0 + t * kKvTile, kEvictNormal);
-    };
-    // S[128, 64] = Q[128, kD] K[64, kD]^T of tile t into accumulator t & 1
-    auto issue_s = [&](int t) {
-        const int s = t & 1;
-        mbar_wait(&bar_k[s], (t >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(sq), k_addr = smem_u32(sk + s * kKBytes);
+                for (int a = 0; a < kDAtoms; ++a)
+                    tma_load_2d(sv + s * kKBytes + a * (kKvTile * 128), &p.map_v, &bar_v[s], a * 64, kv_row0 + t * kKvTile, kEvictNormal);
+            };
+            // S[128, 64] = Q[128, kD] K[64, kD]^T of tile t into accumulator t & 1
+            const uint32_t q_addr = smem_u32(sq), p_addr = smem_u32(sp);
+            auto issue_s = [&](int t) {
+                const int s = t & 1;
+                mbar_wait(&bar_k[s], (t >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sk + s * kKBytes);
 #pragma unroll
-        for (int kk = 0; kk < kD / kUmmaKAtt; ++kk) {
-            const uint32_t qoff = (kk / 4) * (kQTile * 128) + (kk % 4) * 32;      // column block, then 32 B per K step
-            const uint32_t koff = (kk / 4) * (kKvTile * 128) + (kk % 4) * 32;
-            umma_f16<1>(tmem_base + s * kKvTile, make_smem_desc_sw128(q_addr + qoff, 0, 1024),
-                        make_smem_desc_sw128(k_addr + koff, 0, 1024), p.idesc_s, kk > 0 ? 1u : 0u);
-        }
-        umma_commit<1>(&bar_s[s]);
-    };
-    if (tid == 0) {
-        mbar_arrive_expect_tx(bar_q, kQBytes);
+                for (int kk = 0; kk < kD / kUmmaKAtt; ++kk) {
+                    const uint32_t qoff = (kk / 4) * (kQTile * 128) + (kk % 4) * 32;      // column block, then 32 B per K step
+                    const uint32_t koff = (kk / 4) * (kKvTile * 128) + (kk % 4) * 32;
+                    umma_f16<1>(tmem_base + s * kKvTile, make_smem_desc_sw128(q_addr + qoff, 0, 1024),
+                                make_smem_desc_sw128(k_addr + koff, 0, 1024), p.idesc_s, kk > 0 ? 1u : 0u);
+                }
+                umma_commit<1>(&bar_s[s]);
+            };
+            mbar_arrive_expect_tx(bar_q, kQBytes);
 #pragma unroll
-        for (int a = 0; a < kDAtoms; ++a)
-            tma_load_2d(sq + a * (kQTile * 128), &p.map_q, bar_q, head * kD + a * 64, b * p.q_len + q0, kEvictNormal);
-        if (ntiles > 0) {
+            for (int a = 0; a < kDAtoms; ++a)
+                tma_load_2d(sq + a * (kQTile * 128), &p.map_q, bar_q, head * kD + a * 64, b * p.q_len + q0, kEvictNormal);
             load_k(0);
             load_v(0);
             if (ntiles > 1) {
@@ -152,130 +158,132 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
             }
             mbar_wait(bar_q, 0);
             issue_s(0);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t & 1;
+                // S of tile t + 1 first (its accumulator was drained when bar_p of tile t - 1 completed, waited below in the
+                // previous turn), so the tensor cores have work while the softmax of tile t runs
+                if (t + 1 < ntiles) issue_s(t + 1);
+                if (t + 2 < ntiles) {                     // K stage t & 1 is free once S of tile t is complete
+                    mbar_wait(&bar_s[s], (t >> 1) & 1u);
+                    load_k(t + 2);
+                }
+                // O[128, kD] (+)= P[128, 64] V[64, kD]   (V consumed MN-major: [64 keys][kD]); tile 0 overwrites
+                mbar_wait(bar_p, t & 1u);
+                mbar_wait(&bar_v[s], (t >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(sv + s * kKBytes);
+#pragma unroll
+                for (int kk = 0; kk < kKvTile / kUmmaKAtt; ++kk)
+                    umma_f16<1>(tmem_o, make_smem_desc_sw128(p_addr + kk * 32, 0, 1024),
+                                make_smem_desc_sw128(v_addr + kk * (kUmmaKAtt * 128), kKvTile * 128, 1024), p.idesc_o,
+                                (t > 0 || kk > 0) ? 1u : 0u);
+                umma_commit<1>(bar_o);
+                if (t + 2 < ntiles) {                     // V stage t & 1 is free once P V of tile t is complete
+                    mbar_wait(bar_o, t & 1u);
+                    load_v(t + 2);
+                }
+            }
         }
-    }
+    } else {
+        // ------------------------------------------------------------------ softmax warps: one query row per thread = one TMEM lane
+        const int qi = q0 + tid;                       // query index inside the sequence
+        const int qpos = p.past_len + qi;              // its absolute position
+        const bool row_ok = qi < p.q_len;
+        // Online softmax with a LAZY reference: the output accumulator stays in TMEM across the key tiles (P V accumulates
+        // there) and is rescaled -- a TMEM read-modify-write of this thread's row -- only when the row maximum outgrows the
+        // reference by more than 2^kLazyLog2 (probabilities then stay <= 2^kLazyLog2: exact in fp32, harmless in the 16-bit
+        // P).  TMEM reads are the scarce resource here (64 B / clock / SM): S is read once per tile, O once at the end.
+        constexpr float kLazyLog2 = 8.0f;
+        float m_ref = -INFINITY, l = 0.f;
+        const uint32_t lane_off = (warp * 32u) << 16;
+        const uint8_t* keep_row = p.keep != nullptr ? p.keep + static_cast<size_t>(b) * p.kv_len : nullptr;
+        auto visible = [&](int key) {
+            bool ok = key < p.kv_len && (!p.causal || key <= qpos);
+            if (ok && keep_row != nullptr) ok = keep_row[key] != 0;
+            return ok;
+        };
 
-    // one query row per thread = one TMEM lane
-    const int qi = q0 + tid;                       // query index inside the sequence
-    const int qpos = p.past_len + qi;              // its absolute position
-    const bool row_ok = qi < p.q_len;
-    // Online softmax with a LAZY reference: the output accumulator stays in TMEM across the key tiles (P V accumulates
-    // there) and is rescaled -- a TMEM read-modify-write of this thread's row -- only when the row maximum outgrows the
-    // reference by more than 2^kLazyLog2 (probabilities then stay <= 2^kLazyLog2: exact in fp32, harmless in the 16-bit P).
-    // TMEM reads are the scarce resource here (64 B / clock / SM): S is read once per tile, O once at the end.
-    constexpr float kLazyLog2 = 8.0f;
-    float m_ref = -INFINITY, l = 0.f;
-    const uint32_t lane_off = (warp * 32u) << 16;
-    const uint8_t* keep_row = p.keep != nullptr ? p.keep + static_cast<size_t>(b) * p.kv_len : nullptr;
-    auto visible = [&](int key) {
-        bool ok = key < p.kv_len && (!p.causal || key <= qpos);
-        if (ok && keep_row != nullptr) ok = keep_row[key] != 0;
-        return ok;
-    };
-
-    for (int t = 0; t < ntiles; ++t) {
-        const int s = t & 1;
-        const int j0 = t * kKvTile;
-        const uint32_t tmem_s = tmem_base + s * kKvTile;
-        mbar_wait(&bar_s[s], (t >> 1) & 1u);
-        tc_fence_after();
-        if (tid == 0 && t + 1 < ntiles) {
-            // S of tile t is complete: its K stage is free for tile t + 2, and tile t + 1's S can run while this tile's
-            // softmax is computed (its accumulator was drained by every thread before the barrier that ended tile t - 1)
-            if (t + 2 < ntiles) load_k(t + 2);
-            issue_s(t + 1);
-        }
-        // ---- this row's 64 scores, scaled to the log2 domain; keys the row may not see become -inf.
-        // A tile every key of which is visible needs no per-element predicates (all but the diagonal / last tiles).
-        const bool full = (j0 + kKvTile <= p.kv_len) && (!p.causal || j0 + kKvTile - 1 <= qpos) && keep_row == nullptr;
-        float sc[kKvTile];
-        float tmax = -INFINITY;
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t & 1;
+            const int j0 = t * kKvTile;
+            const uint32_t tmem_s = tmem_base + s * kKvTile;
+            mbar_wait(&bar_s[s], (t >> 1) & 1u);
+            tc_fence_after();
+            // ---- this row's 64 scores, scaled to the log2 domain; keys the row may not see become -inf.
+            // A tile every key of which is visible needs no per-element predicates (all but the diagonal / last tiles).
+            const bool full = (j0 + kKvTile <= p.kv_len) && (!p.causal || j0 + kKvTile - 1 <= qpos) && keep_row == nullptr;
+            float sc[kKvTile];
+            float tmax = -INFINITY;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_s + lane_off + hf * 32, v);
-            tmem_ld_wait();
-            if (full) {
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_s + lane_off + hf * 32, v);
+                tmem_ld_wait();
+                if (full) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    sc[hf * 32 + j] = __uint_as_float(v[j]) * p.scale_log2;
-                    tmax = fmaxf(tmax, sc[hf * 32 + j]);
-                }
-            } else {
+                    for (int j = 0; j < 32; ++j) {
+                        sc[hf * 32 + j] = __uint_as_float(v[j]) * p.scale_log2;
+                        tmax = fmaxf(tmax, sc[hf * 32 + j]);
+                    }
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    sc[hf * 32 + j] = visible(j0 + hf * 32 + j) ? __uint_as_float(v[j]) * p.scale_log2 : -INFINITY;
-                    tmax = fmaxf(tmax, sc[hf * 32 + j]);
+                    for (int j = 0; j < 32; ++j) {
+                        sc[hf * 32 + j] = visible(j0 + hf * 32 + j) ? __uint_as_float(v[j]) * p.scale_log2 : -INFINITY;
+                        tmax = fmaxf(tmax, sc[hf * 32 + j]);
+                    }
                 }
             }
-        }
-        // ---- the previous tile's P V must be complete before P is overwritten and before the accumulator is touched
-        if (t > 0) {
-            mbar_wait(bar_o, (t - 1) & 1u);
-            tc_fence_after();
-            if (tid == 0 && t + 1 < ntiles) load_v(t + 1);      // V stage (t + 1) & 1 was read by P V of tile t - 1
-        }
-        // tcgen05.ld / .st are warp-collective: the branch is taken by the whole warp as soon as one of its rows needs a new
-        // reference; the other rows rescale by exactly 1
-        const bool want = tmax > m_ref + kLazyLog2;                   // also true for the first visible key (m_ref = -inf)
-        if (__any_sync(0xffffffffu, want)) {
-            const float alpha = want ? fast_exp2(m_ref - tmax) : 1.f;   // m_ref = -inf: 0
-            l *= alpha;
-            if (t > 0) {                                             // tile 0 overwrites the accumulator (no rescale needed)
+            // ---- the previous tile's P V must be complete before P is overwritten and before the accumulator is touched
+            if (t > 0) {
+                mbar_wait(bar_o, (t - 1) & 1u);
+                tc_fence_after();
+            }
+            // tcgen05.ld / .st are warp-collective: the branch is taken by the whole warp as soon as one of its rows needs a
+            // new reference; the other rows rescale by exactly 1
+            const bool want = tmax > m_ref + kLazyLog2;                   // also true for the first visible key (m_ref = -inf)
+            if (__any_sync(0xffffffffu, want)) {
+                const float alpha = want ? fast_exp2(m_ref - tmax) : 1.f;   // m_ref = -inf: 0
+                l *= alpha;
+                if (t > 0) {                                             // tile 0 overwrites the accumulator (no rescale needed)
 #pragma unroll
-                for (int c = 0; c < kD / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, v);
-                    tmem_ld_wait();
+                    for (int c = 0; c < kD / 32; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, v);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-                    tmem_st_32x32b_x32(tmem_o + lane_off + c * 32, v);
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+                        tmem_st_32x32b_x32(tmem_o + lane_off + c * 32, v);
+                    }
+                    tmem_st_wait();
                 }
-                tmem_st_wait();
+                if (want) m_ref = tmax;
             }
-            if (want) m_ref = tmax;
-        }
-        // ---- probabilities -> P in shared memory, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of 16 bytes
-        float psum = 0.f;
-        uint8_t* prow = sp + tid * 128;
+            // ---- probabilities -> P in shared memory, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of 16 B
+            float psum = 0.f;
+            uint8_t* prow = sp + tid * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint32_t pk[4];
+            for (int c = 0; c < 8; ++c) {
+                uint32_t pk[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                // -inf - m_ref = -inf -> 0 (m_ref is finite whenever any key of the row has been visible; a dead row has
-                // m_ref = -inf and sc = -inf: -inf - -inf = nan, hence the guard)
-                const float a0 = sc[c * 8 + 2 * j], a1 = sc[c * 8 + 2 * j + 1];
-                const float p0 = (a0 == -INFINITY) ? 0.f : fast_exp2(a0 - m_ref);
-                const float p1 = (a1 == -INFINITY) ? 0.f : fast_exp2(a1 - m_ref);
-                pk[j] = Pack2<T>::pack(p0, p1);
-                psum += p0 + p1;
+                for (int j = 0; j < 4; ++j) {
+                    // a dead row has m_ref = -inf and sc = -inf: -inf - -inf = nan, hence the guard
+                    const float a0 = sc[c * 8 + 2 * j], a1 = sc[c * 8 + 2 * j + 1];
+                    const float p0 = (a0 == -INFINITY) ? 0.f : fast_exp2(a0 - m_ref);
+                    const float p1 = (a1 == -INFINITY) ? 0.f : fast_exp2(a1 - m_ref);
+                    pk[j] = Pack2<T>::pack(p0, p1);
+                    psum += p0 + p1;
+                }
+                *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-            *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            l += psum;
+            fence_proxy_async_smem();      // generic-proxy st.shared -> async-proxy (tensor core) reads
+            tc_fence_before();             // this thread's tcgen05.ld / .st are ordered before the issuer's next tcgen05.mma
+            mbar_arrive(bar_p);
         }
-        l += psum;
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncthreads();                                // every row of P is in place; every thread is done with S and with O
-        if (tid == 0) {
+        if (ntiles > 0) {
+            mbar_wait(bar_o, (ntiles - 1) & 1u);
             tc_fence_after();
-            mbar_wait(&bar_v[s], (t >> 1) & 1u);
-            tc_fence_after();
-            // O[128, kD] (+)= P[128, 64] V[64, kD]   (V consumed MN-major: [64 keys][kD]); tile 0 overwrites
-            const uint32_t p_addr = smem_u32(sp), v_addr = smem_u32(sv + s * kKBytes);
-#pragma unroll
-            for (int kk = 0; kk < kKvTile / kUmmaKAtt; ++kk)
-                umma_f16<1>(tmem_o, make_smem_desc_sw128(p_addr + kk * 32, 0, 1024),
-                            make_smem_desc_sw128(v_addr + kk * (kUmmaKAtt * 128), kKvTile * 128, 1024), p.idesc_o,
-                            (t > 0 || kk > 0) ? 1u : 0u);
-            umma_commit<1>(bar_o);
         }
-    }
-    if (ntiles > 0) {
-        mbar_wait(bar_o, (ntiles - 1) & 1u);
-        tc_fence_after();
-    }
-    {
         const float inv = (ntiles > 0 && l > 0.f) ? 1.f / l : 0.f;     // a row without any visible key gives zeros
         T* dst = static_cast<T*>(p.out) + (static_cast<size_t>(b) * p.q_len + (row_ok ? qi : 0)) * (static_cast<size_t>(p.heads) * kD) +
                  head * kD;
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 4) {
         tc_fence_after();
         tmem_dealloc<1>(tmem_base, kTmemCols);
     }
