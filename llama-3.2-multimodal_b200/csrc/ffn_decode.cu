@@ -120,55 +120,75 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
     if (warp == 0) {
         if (lane == 0) {
             // ---------------------------------------------------------------- TMA producer
-            auto load_w = [&](int kb) {
-                const int s = kb % stages;
+            // (running stage / k-block counters: no integer divisions in the per-stage instruction stream)
+            const int row0 = row_block * (kEpi == DEC_SWIGLU ? 64 : kRowsA);
+            auto load_w = [&](int s, int kr) {
                 uint8_t* sa = smem + s * stage_bytes;
                 mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-                int kr = kb + rot;
-                if (kr >= cnt) kr -= cnt;
                 const int kcol = (kb0 + kr) * kBlockK;
                 if constexpr (kEpi == DEC_SWIGLU) {
-                    tma_load_2d(sa, &p.map_w[0], &full_bar[s], kcol, row_block * 64, kEvictFirst);
-                    tma_load_2d(sa + kABytes / 2, &p.map_w[1], &full_bar[s], kcol, row_block * 64, kEvictFirst);
+                    tma_load_2d(sa, &p.map_w[0], &full_bar[s], kcol, row0, kEvictFirst);
+                    tma_load_2d(sa + kABytes / 2, &p.map_w[1], &full_bar[s], kcol, row0, kEvictFirst);
                 } else {
-                    tma_load_2d(sa, &p.map_w[0], &full_bar[s], kcol, row_block * kRowsA, kEvictFirst);
+                    tma_load_2d(sa, &p.map_w[0], &full_bar[s], kcol, row0, kEvictFirst);
                 }
             };
-            auto load_x = [&](int kb) {
-                const int s = kb % stages;
-                int kr = kb + rot;
-                if (kr >= cnt) kr -= cnt;
+            auto load_x = [&](int s, int kr) {
                 tma_load_2d(smem + s * stage_bytes + kABytes, &p.map_x, &full_bar[s], (kb0 + kr) * kBlockK, 0, kEvictLast);
             };
             const int pre = min(stages, cnt);
-            for (int kb = 0; kb < pre; ++kb) load_w(kb);        // weights do not depend on the previous kernel
+            {
+                int kr = rot;
+                for (int kb = 0; kb < pre; ++kb) {            // weights do not depend on the previous kernel
+                    load_w(kb, kr);
+                    if (++kr == cnt) kr = 0;
+                }
+            }
             pdl_wait_prior_grid();                              // activations do
+            int s = 0, kr = rot;
+            uint32_t phase = 0;
             for (int kb = 0; kb < cnt; ++kb) {
                 if (kb >= pre) {
-                    mbar_wait(&empty_bar[kb % stages], ((kb / stages) & 1u) ^ 1u);
-                    load_w(kb);
+                    mbar_wait(&empty_bar[s], phase ^ 1u);
+                    load_w(s, kr);
                 }
-                load_x(kb);
+                load_x(s, kr);
+                if (++kr == cnt) kr = 0;
+                if (++s == stages) { s = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ---------------------------------------------------------------- MMA issuer
+            // This one thread's instruction stream (wait, 4 x tcgen05.mma, commit per 16 KB of weights) paces the stage: the
+            // shared-memory descriptors are built ONCE and advanced by adding to their 14-bit address field (>> 4 units;
+            // shared-memory addresses are < 256 KB, so the field never carries into the next one).
+            const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem), 0, 1024);
+            const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem) + kABytes, 0, 1024);
+            const uint32_t stage_step = stage_bytes >> 4;
             uint32_t accumulate = 0;
+            int s = 0;
+            uint32_t phase = 0;
+            uint64_t a_desc = a_desc0, b_desc = b_desc0;
             for (int kb = 0; kb < cnt; ++kb) {
-                const int s = kb % stages;
-                mbar_wait(&full_bar[s], (kb / stages) & 1u);
+                mbar_wait(&full_bar[s], phase);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-                const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
                 for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                    const uint64_t adesc = make_smem_desc_sw128(a_addr + k * kUmmaK * 2, 0, 1024);
-                    const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * kUmmaK * 2, 0, 1024);
-                    umma_f16<1>(tmem_base, adesc, bdesc, p.idesc, accumulate);
+                    umma_f16<1>(tmem_base, a_desc + static_cast<uint64_t>(k * (kUmmaK * 2 / 16)),
+                                b_desc + static_cast<uint64_t>(k * (kUmmaK * 2 / 16)), p.idesc, accumulate);
                     accumulate = 1;
                 }
                 umma_commit<1>(&empty_bar[s]);
+                if (++s == stages) {
+                    s = 0;
+                    phase ^= 1u;
+                    a_desc = a_desc0;
+                    b_desc = b_desc0;
+                } else {
+                    a_desc += stage_step;
+                    b_desc += stage_step;
+                }
             }
             umma_commit<1>(tfull_bar);
         }
