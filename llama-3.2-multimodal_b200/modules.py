@@ -28,6 +28,12 @@ __all__ = [
 ]
 
 
+def _dims8(*dims) -> bool:
+    """The tcgen05 / TMA kernels want every matrix dimension to be a multiple of 8 elements (16-byte rows).  Shapes that are
+    not take the reference's own F.linear expressions, which accept anything (the reference's live path does too)."""
+    return all(int(d) % 8 == 0 and int(d) > 0 for d in dims)
+
+
 def _wants_grad(*tensors) -> bool:
     """True when autograd will record this call.  Function.forward always runs with grad mode off and
     ctx.needs_input_grad ignores an enclosing torch.no_grad(), so the decision is taken in `apply`."""
@@ -105,7 +111,8 @@ class SwiGLUFunction(torch.autograd.Function):
     def _cuda_path(x, w_gate, w_up):
         # sm_100a kernels only when activations AND weights share a 16-bit CUDA dtype; anything else (fp32 master weights
         # under bf16 activations, CPU, fp32) evaluates the reference's F.linear expressions (FusedSwiglu.py:17-20)
-        return ops.supported(x) and w_gate.dtype == x.dtype and w_up.dtype == x.dtype and w_gate.is_cuda and w_up.is_cuda
+        return (ops.supported(x) and w_gate.dtype == x.dtype and w_up.dtype == x.dtype and w_gate.is_cuda and w_up.is_cuda and
+                _dims8(*w_gate.shape))
 
     @classmethod
     def apply(cls, x, w_gate, w_up, b_gate=None, b_up=None):
@@ -210,7 +217,7 @@ class LinearFunction(torch.autograd.Function):
 
 
 def _linear(x, weight, bias=None):
-    if ops.supported(x) and weight.dtype == x.dtype:
+    if ops.supported(x) and weight.dtype == x.dtype and weight.is_cuda and _dims8(*weight.shape):
         return LinearFunction.apply(x, weight, bias)
     return F.linear(x, weight, bias)
 
@@ -376,7 +383,7 @@ class FusedFeedforward(nn.Module):
 
     def forward(self, x):
         sw, wd = self.swiglu, self.w_down
-        if ops.supported(x) and sw.w_gate.dtype == x.dtype:
+        if ops.supported(x) and sw.w_gate.dtype == x.dtype and _dims8(*sw.w_gate.shape):
             if isinstance(wd, nn.Linear) and wd.weight.dtype == x.dtype:
                 return FFNFunction.apply(x, sw.w_gate, sw.w_up, wd.weight, sw.b_gate, sw.b_up, wd.bias)
             if _is_lora(wd) and wd.linear.weight.dtype == x.dtype:
@@ -443,6 +450,7 @@ def block_tail(norm2, ff, attn_out, residual, next_norm=None):
     LoRA / biases) the modules are composed exactly as the reference does."""
     sw, wd = ff.swiglu, ff.w_down
     fusable = (ops.supported(attn_out) and isinstance(wd, nn.Linear) and wd.bias is None and sw.b_gate is None and
+               _dims8(*sw.w_gate.shape) and
                sw.w_gate.dtype == attn_out.dtype and wd.weight.dtype == attn_out.dtype and
                (residual is None or (residual.shape == attn_out.shape and residual.dtype == attn_out.dtype)) and
                attn_out.numel() > 0)

@@ -854,3 +854,16 @@ def test_attention_shapes_vs_oracle(b, t, hidden, heads, kv, steps):
         yn = att(dev(x), attention_mask=None, position_ids=pos.to(DEV), kv_cache=None)
     ynr, _, _ = O.gqa_attention(x, wq, wk, wv, wo, heads, kv, pos, None)
     close(yn, ynr, FWD, "no mask")
+
+
+def test_odd_feature_sizes_take_the_reference_expressions():
+    """hidden / inter that are not multiples of 8 (no 16-byte rows for TMA): the reference's live path accepts anything, so the
+    drop-in modules evaluate the reference's F.linear expressions there instead of raising (smaller #14)."""
+    torch.manual_seed(0)
+    ff = L.FusedFeedforward(60, 100).to(DEV, torch.bfloat16)
+    x = torch.randn(3, 7, 60, device=DEV).bfloat16().requires_grad_(True)
+    y = ff(x)
+    y.sum().backward()
+    ref = torch.nn.functional.linear(torch.nn.functional.silu(torch.nn.functional.linear(x, ff.swiglu.w_gate)) *
+                                     torch.nn.functional.linear(x, ff.swiglu.w_up), ff.w_down.weight)
+    assert torch.equal(y, ref) and x.grad is not None and ff.swiglu.w_gate.grad is not None
