@@ -267,10 +267,16 @@ L32_API int l32_rope_kv_append(void* q, const void* k_new, const void* v_new, co
 /* ctx = softmax(q k^T / sqrt(head_dim) + mask) v over keys [0, kv_len) of the cache, flash-style on tcgen05 (scores never
  * leave the SM).  Query i of the call sits at position past_len + i.  causal != 0: key j is visible iff j <= past_len + i
  * (the reference's triu(-inf, 1) mask, Model/model.py:314-317); key_keep: optional [batch, kv_len] bytes, 0 = padded key
- * (the reference's padding term, :318).  A row without any visible key yields zeros.  head_dim 64 or 128. */
+ * (the reference's padding term, :318).  A row without any visible key yields zeros.  head_dim 64 or 128.
+ * workspace (optional): l32_gqa_attention_workspace_bytes(...) bytes.  With it a decode step (q_len == 1) splits the cached
+ * keys over several CTAs per KV head (fp32 partials + a merge kernel, fixed order: deterministic), which is what keeps small
+ * batches with long contexts from running on a handful of SMs; without it (or when the function returns 0) one CTA per KV head
+ * walks the whole cache. */
+L32_API size_t l32_gqa_attention_workspace_bytes(int batch, int q_len, int heads, int kv_heads, int head_dim, int kv_len);
 L32_API int l32_gqa_attention_forward(const void* q, const void* cache_k, const void* cache_v, const uint8_t* key_keep,
-                                      void* ctx, int batch, int q_len, int heads, int kv_heads, int head_dim, int max_len,
-                                      int kv_len, int past_len, int causal, int dtype, void* stream);
+                                      void* ctx, void* workspace, size_t workspace_bytes, int batch, int q_len, int heads,
+                                      int kv_heads, int head_dim, int max_len, int kv_len, int past_len, int causal, int dtype,
+                                      void* stream);
 
 /* General tiled GEMM used by the entry points above (exposed for tests, tuning and the tensor-parallel
  * host code):  D[m,n] = A[m,k] B[n,k]^T  (+ A1 B1^T when a1 != NULL).

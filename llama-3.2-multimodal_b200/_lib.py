@@ -47,7 +47,8 @@ SIGNATURES = {
     "l32_lm_head_ce_backward": (c_int, [c_void_p] * 3 + [ctypes.c_longlong, c_void_p, c_void_p] + [c_void_p] * 5 +
                                 [c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_rope_kv_append": (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_float, c_int, c_void_p]),
-    "l32_gqa_attention_forward": (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p]),
+    "l32_gqa_attention_workspace_bytes": (c_size_t, [c_int] * 6),
+    "l32_gqa_attention_forward": (c_int, [c_void_p] * 6 + [c_size_t] + [c_int] * 10 + [c_void_p]),
     "l32_ffn_backward_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "l32_ffn_backward": (c_int, [c_void_p] * 12 + [c_size_t, c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_ffn_lora_forward": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),

@@ -674,9 +674,14 @@ int l32_rope_kv_append(void* q, const void* k_new, const void* v_new, const int6
                           kv_heads, head_dim, max_len, past_len, rope_base, dtype, as_stream(stream));
 }
 
-int l32_gqa_attention_forward(const void* q, const void* cache_k, const void* cache_v, const uint8_t* key_keep, void* ctx, int batch,
-                              int q_len, int heads, int kv_heads, int head_dim, int max_len, int kv_len, int past_len, int causal,
-                              int dtype, void* stream) {
+size_t l32_gqa_attention_workspace_bytes(int batch, int q_len, int heads, int kv_heads, int head_dim, int kv_len) {
+    if (batch <= 0 || q_len <= 0 || heads <= 0 || kv_heads <= 0 || (heads % kv_heads) != 0 || kv_len <= 0) return 0;
+    return gqa_attention_workspace_bytes(batch, q_len, heads, kv_heads, head_dim, kv_len);
+}
+
+int l32_gqa_attention_forward(const void* q, const void* cache_k, const void* cache_v, const uint8_t* key_keep, void* ctx,
+                              void* workspace, size_t workspace_bytes, int batch, int q_len, int heads, int kv_heads, int head_dim,
+                              int max_len, int kv_len, int past_len, int causal, int dtype, void* stream) {
     if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
     if (batch < 0 || q_len < 0 || heads <= 0 || kv_heads <= 0 || (heads % kv_heads) != 0 || (head_dim != 64 && head_dim != 128) ||
         max_len <= 0 || kv_len < 0 || kv_len > max_len || past_len < 0)
@@ -684,8 +689,9 @@ int l32_gqa_attention_forward(const void* q, const void* cache_k, const void* ca
     if (batch == 0 || q_len == 0) return L32_OK;
     if (q == nullptr || cache_k == nullptr || cache_v == nullptr || ctx == nullptr) return L32_ERR_NULL;
     if (!is_aligned16(q) || !is_aligned16(cache_k) || !is_aligned16(cache_v) || !is_aligned16(ctx)) return L32_ERR_BAD_ALIGN;
+    if (workspace != nullptr && !is_aligned16(workspace)) return L32_ERR_WORKSPACE;
     return gqa_attention(q, cache_k, cache_v, key_keep, ctx, batch, q_len, heads, kv_heads, head_dim, max_len, kv_len, past_len,
-                         causal, dtype, as_stream(stream));
+                         causal, workspace, workspace_bytes, dtype, as_stream(stream));
 }
 
 int l32_gemm(const void* a, int64_t lda, int a_mn_major, const void* b, int64_t ldb, int b_mn_major, const void* a1,

@@ -37,6 +37,11 @@ struct AttnParams {
     int batch, q_len, heads, kv_heads, max_len, kv_len, past_len, causal;
     float scale_log2;    // log2(e) / sqrt(head_dim)
     uint32_t idesc_s, idesc_o;
+    // split-KV (decode): gridDim.x = splits CTAs per (batch, head), each over `tiles_per_split` key tiles; unnormalised partial
+    // outputs and (reference, sum) pairs go to the workspace, attention_combine_kernel merges them.  splits == 1: off.
+    int splits, tiles_per_split;
+    float* part_o;       // [batch][heads][splits][q_len][head_dim] fp32
+    float2* part_ml;     // [batch][heads][splits][q_len] (m_ref in the log2 domain, l)
 };
 
 L32_DEVICE float fast_exp2(float x) {
@@ -70,7 +75,8 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
 
     const int tid = threadIdx.x;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int q0 = blockIdx.x * kQTile;
+    const int split = p.splits > 1 ? static_cast<int>(blockIdx.x) : 0;
+    const int q0 = p.splits > 1 ? 0 : blockIdx.x * kQTile;
     const int head = blockIdx.y;
     const int b = blockIdx.z;
     const int kvh = head / (p.heads / p.kv_heads);
@@ -106,8 +112,10 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
     const int q_last = min(q0 + kQTile, p.q_len) - 1;
     int hi = p.kv_len;
     if (p.causal) hi = min(hi, p.past_len + q_last + 1);
-    const int ntiles = (hi + kKvTile - 1) / kKvTile;
-    const int kv_row0 = (b * p.kv_heads + kvh) * p.max_len;
+    const int total_tiles = (hi + kKvTile - 1) / kKvTile;
+    const int tile0 = split * p.tiles_per_split;                          // first key tile of this CTA (0 without split-KV)
+    const int ntiles = p.splits > 1 ? max(0, min(p.tiles_per_split, total_tiles - tile0)) : total_tiles;
+    const int kv_row0 = (b * p.kv_heads + kvh) * p.max_len + tile0 * kKvTile;
 
     if (warp == 4) {
         // ------------------------------------------------------------------ TMA producer + MMA issuer (one thread)
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
 
         for (int t = 0; t < ntiles; ++t) {
             const int s = t & 1;
-            const int j0 = t * kKvTile;
+            const int j0 = (tile0 + t) * kKvTile;
             const uint32_t tmem_s = tmem_base + s * kKvTile;
             mbar_wait(&bar_s[s], (t >> 1) & 1u);
             tc_fence_after();
@@ -284,6 +292,28 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
             mbar_wait(bar_o, (ntiles - 1) & 1u);
             tc_fence_after();
         }
+        if (p.splits > 1) {
+            // split-KV: the unnormalised accumulator row and its (reference, sum) leave for the combine kernel
+            const size_t slot = ((static_cast<size_t>(b) * p.heads + head) * p.splits + split) * p.q_len + (row_ok ? qi : 0);
+            if (row_ok) p.part_ml[slot] = make_float2(ntiles > 0 ? m_ref : -INFINITY, ntiles > 0 ? l : 0.f);
+            float* dstf = p.part_o + slot * kD;
+#pragma unroll
+            for (int c = 0; c < kD / 32; ++c) {
+                uint32_t v[32];
+                if (ntiles > 0) {
+                    tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4)
+                        *reinterpret_cast<uint4*>(dstf + c * 32 + 4 * j4) = make_uint4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                }
+            }
+        } else {
         const float inv = (ntiles > 0 && l > 0.f) ? 1.f / l : 0.f;     // a row without any visible key gives zeros
         T* dst = static_cast<T*>(p.out) + (static_cast<size_t>(b) * p.q_len + (row_ok ? qi : 0)) * (static_cast<size_t>(p.heads) * kD) +
                  head * kD;
@@ -309,12 +339,49 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
                 }
             }
         }
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
         tmem_dealloc<1>(tmem_base, kTmemCols);
+    }
+}
+
+// Split-KV combine: out[row] = sum_s O_s 2^(m_s - M) / sum_s l_s 2^(m_s - M), M = max_s m_s.  One warp per (batch, head, row).
+template <typename T>
+__global__ void __launch_bounds__(128) attention_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
+                                                               T* __restrict__ out, int batch, int heads, int q_len, int splits,
+                                                               int d) {
+    pdl_wait_prior_grid();
+    const long long w = blockIdx.x * 4ll + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const long long total = static_cast<long long>(batch) * heads * q_len;
+    if (w >= total) return;
+    const int qi = static_cast<int>(w % q_len);
+    const long long bh = w / q_len;                       // b * heads + head
+    float mx = -INFINITY;
+    for (int s = 0; s < splits; ++s) mx = fmaxf(mx, part_ml[(bh * splits + s) * q_len + qi].x);
+    float lsum = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};                  // d <= 128: 4 columns per lane
+    for (int s = 0; s < splits; ++s) {
+        const size_t slot = (bh * splits + s) * q_len + qi;
+        const float2 ml = part_ml[slot];
+        if (ml.x == -INFINITY) continue;
+        const float sc = exp2f(ml.x - mx);
+        lsum += ml.y * sc;
+        for (int c = 0; c < 4; ++c) {
+            const int col = lane + 32 * c;
+            if (col < d) acc[c] = fmaf(part_o[slot * d + col], sc, acc[c]);
+        }
+    }
+    const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+    const int b = static_cast<int>(bh / heads), head = static_cast<int>(bh % heads);
+    T* dst = out + (static_cast<size_t>(b) * q_len + qi) * (static_cast<size_t>(heads) * d) + static_cast<size_t>(head) * d;
+    for (int c = 0; c < 4; ++c) {
+        const int col = lane + 32 * c;
+        if (col < d) dst[col] = static_cast<T>(acc[c] * inv);
     }
 }
 
@@ -376,8 +443,8 @@ int launch_attention(const AttnParams& p, cudaStream_t s) {
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>((p.q_len + kQTile - 1) / kQTile), static_cast<unsigned>(p.heads),
-                       static_cast<unsigned>(p.batch));
+    cfg.gridDim = dim3(static_cast<unsigned>(p.splits > 1 ? p.splits : (p.q_len + kQTile - 1) / kQTile),
+                       static_cast<unsigned>(p.heads), static_cast<unsigned>(p.batch));
     cfg.blockDim = dim3(kAttThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
@@ -392,6 +459,12 @@ int launch_attention(const AttnParams& p, cudaStream_t s) {
 }
 
 }  // namespace
+
+int gqa_attention_packed(const void* q, const void* cache_k, const void* cache_v, void* out, int batch2, int group, int head_dim,
+                         int max_len, int kv_len, int splits, void* workspace, int dtype, cudaStream_t s);
+int gqa_attention_launch(const void* q, const void* cache_k, const void* cache_v, const uint8_t* keep, void* out, int batch, int q_len,
+                         int heads, int kv_heads, int head_dim, int max_len, int kv_len, int past_len, int causal, int splits,
+                         void* workspace, int dtype, cudaStream_t s);
 
 int rope_kv_append(void* q, const void* k_new, const void* v_new, const long long* position_ids, void* cache_k, void* cache_v,
                    int batch, int q_len, int heads, int kv_heads, int head_dim, int max_len, int past_len, float rope_base,
@@ -425,9 +498,19 @@ int rope_kv_append(void* q, const void* k_new, const void* v_new, const long lon
     return static_cast<int>(e);
 }
 
+size_t gqa_attention_workspace_bytes(int batch, int q_len, int heads, int kv_heads, int head_dim, int kv_len) {
+    if (q_len != 1 || batch <= 0) return 0;               // split-KV serves decode (one query per sequence) only
+    const int tiles = (kv_len + kKvTile - 1) / kKvTile;
+    const int ctas = batch * kv_heads;                    // decode packs the heads of a KV group into one CTA
+    int splits = (2 * num_sms() + ctas - 1) / ctas;       // aim at two CTAs per SM
+    if (splits > tiles / 2) splits = tiles / 2;           // at least two key tiles (128 keys) per split
+    if (splits < 2) return 0;
+    return static_cast<size_t>(batch) * heads * splits * (static_cast<size_t>(head_dim) + 2) * sizeof(float) + 256;
+}
+
 int gqa_attention(const void* q, const void* cache_k, const void* cache_v, const uint8_t* keep, void* out, int batch, int q_len,
-                  int heads, int kv_heads, int head_dim, int max_len, int kv_len, int past_len, int causal, int dtype,
-                  cudaStream_t s) {
+                  int heads, int kv_heads, int head_dim, int max_len, int kv_len, int past_len, int causal, void* workspace,
+                  size_t workspace_bytes, int dtype, cudaStream_t s) {
     if (head_dim != 64 && head_dim != 128) return L32_ERR_BAD_SHAPE;
     if (batch <= 0 || q_len <= 0) return L32_OK;
     if (q_len == 1 && heads > kv_heads && keep == nullptr) {
@@ -435,9 +518,30 @@ int gqa_attention(const void* q, const void* cache_k, const void* cache_v, const
         // memory), so every K / V tile is read once per group instead of once per query head.  One query per sequence sees
         // the whole cache: no causal predicate needed.
         const int group = heads / kv_heads;
-        return gqa_attention(q, cache_k, cache_v, nullptr, out, batch * kv_heads, group, 1, 1, head_dim, max_len, kv_len, 0, 0,
-                             dtype, s);
+        int splits = 1;
+        if (workspace != nullptr && workspace_bytes >= gqa_attention_workspace_bytes(batch, 1, heads, kv_heads, head_dim, kv_len) &&
+            gqa_attention_workspace_bytes(batch, 1, heads, kv_heads, head_dim, kv_len) > 0) {
+            const int tiles = (kv_len + kKvTile - 1) / kKvTile;
+            splits = (2 * num_sms() + batch * kv_heads - 1) / (batch * kv_heads);
+            if (splits > tiles / 2) splits = tiles / 2;
+        }
+        return gqa_attention_packed(q, cache_k, cache_v, out, batch * kv_heads, group, head_dim, max_len, kv_len, splits, workspace,
+                                    dtype, s);
     }
+    return gqa_attention_launch(q, cache_k, cache_v, keep, out, batch, q_len, heads, kv_heads, head_dim, max_len, kv_len, past_len,
+                                causal, 1, nullptr, dtype, s);
+}
+
+// Decode layout: batch' = batch * kv_heads sequences of `group` query rows, one head.
+int gqa_attention_packed(const void* q, const void* cache_k, const void* cache_v, void* out, int batch2, int group, int head_dim,
+                         int max_len, int kv_len, int splits, void* workspace, int dtype, cudaStream_t s) {
+    return gqa_attention_launch(q, cache_k, cache_v, nullptr, out, batch2, group, 1, 1, head_dim, max_len, kv_len, 0, 0, splits,
+                                workspace, dtype, s);
+}
+
+int gqa_attention_launch(const void* q, const void* cache_k, const void* cache_v, const uint8_t* keep, void* out, int batch, int q_len,
+                         int heads, int kv_heads, int head_dim, int max_len, int kv_len, int past_len, int causal, int splits,
+                         void* workspace, int dtype, cudaStream_t s) {
     AttnParams p;
     memset(&p, 0, sizeof(p));
     p.out = out;
@@ -455,12 +559,42 @@ int gqa_attention(const void* q, const void* cache_k, const void* cache_v, const
     if (rc != L32_OK) return rc;
     rc = make_tensor_map_2d(&p.map_v, cache_v, kv_rows, head_dim, head_dim, kKvTile, 64, dtype);
     if (rc != L32_OK) return rc;
-    if (dtype == L32_BF16) {
-        if (head_dim == 128) return launch_attention<128, __nv_bfloat16>(p, s);
-        return launch_attention<64, __nv_bfloat16>(p, s);
+    p.splits = splits > 1 ? splits : 1;
+    if (p.splits > 1) {
+        const int tiles = (kv_len + kKvTile - 1) / kKvTile;
+        p.tiles_per_split = (tiles + p.splits - 1) / p.splits;
+        const size_t rows = static_cast<size_t>(batch) * heads * p.splits * q_len;
+        p.part_o = static_cast<float*>(workspace);
+        p.part_ml = reinterpret_cast<float2*>(static_cast<uint8_t*>(workspace) + ((rows * head_dim * sizeof(float) + 255) & ~static_cast<size_t>(255)));
     }
-    if (head_dim == 128) return launch_attention<128, __half>(p, s);
-    return launch_attention<64, __half>(p, s);
+    if (dtype == L32_BF16) {
+        rc = head_dim == 128 ? launch_attention<128, __nv_bfloat16>(p, s) : launch_attention<64, __nv_bfloat16>(p, s);
+    } else {
+        rc = head_dim == 128 ? launch_attention<128, __half>(p, s) : launch_attention<64, __half>(p, s);
+    }
+    if (rc != L32_OK || p.splits == 1) return rc;
+    // merge the split-KV partials
+    const long long rows = static_cast<long long>(batch) * heads * q_len;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>((rows + 3) / 4));
+    cfg.blockDim = dim3(128);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const float* po = p.part_o;
+    const float2* pml = p.part_ml;
+    cudaError_t e;
+    if (dtype == L32_BF16)
+        e = cudaLaunchKernelEx(&cfg, attention_combine_kernel<__nv_bfloat16>, po, pml, static_cast<__nv_bfloat16*>(out), batch, heads,
+                               q_len, p.splits, head_dim);
+    else
+        e = cudaLaunchKernelEx(&cfg, attention_combine_kernel<__half>, po, pml, static_cast<__half*>(out), batch, heads, q_len,
+                               p.splits, head_dim);
+    if (e == cudaSuccess) count_launch();
+    return static_cast<int>(e);
 }
 
 }  // namespace l32

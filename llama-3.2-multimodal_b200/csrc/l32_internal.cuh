@@ -139,9 +139,10 @@ cudaError_t ce_backward_logits(const void* logits, const float* lse, const long 
 int rope_kv_append(void* q, const void* k_new, const void* v_new, const long long* position_ids, void* cache_k, void* cache_v,
                    int batch, int q_len, int heads, int kv_heads, int head_dim, int max_len, int past_len, float rope_base,
                    int dtype, cudaStream_t s);
+size_t gqa_attention_workspace_bytes(int batch, int q_len, int heads, int kv_heads, int head_dim, int kv_len);
 int gqa_attention(const void* q, const void* cache_k, const void* cache_v, const uint8_t* keep, void* out, int batch, int q_len,
-                  int heads, int kv_heads, int head_dim, int max_len, int kv_len, int past_len, int causal, int dtype,
-                  cudaStream_t s);
+                  int heads, int kv_heads, int head_dim, int max_len, int kv_len, int past_len, int causal, void* workspace,
+                  size_t workspace_bytes, int dtype, cudaStream_t s);
 
 // ---- tp.cu : tensor-parallel glue (cross-GPU flags, reduction of the partial slots)
 cudaError_t tp_signal(void* const* peer_flags, int world, int index, uint32_t value, uint32_t* zero8, cudaStream_t s);

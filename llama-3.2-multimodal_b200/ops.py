@@ -447,10 +447,13 @@ def gqa_attention_forward(q, cache_k, cache_v, kv_len, past_len, *, causal=True,
         if tuple(keep.shape) != (b, kv_len):
             raise L32Error(f"key_keep must be [batch, kv_len] = {(b, kv_len)}, got {tuple(keep.shape)}")
     ctx = torch.empty_like(qc)
+    L = lib()
+    ws_bytes = L.l32_gqa_attention_workspace_bytes(b, t, heads, kvh, d, int(kv_len)) if keep is None else 0
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device) if ws_bytes else None
     with torch.cuda.device(q.device):
-        check(lib().l32_gqa_attention_forward(_ptr(qc), _ptr(cache_k), _ptr(cache_v), _ptr(keep), _ptr(ctx), b, t, heads, kvh, d,
-                                              max_len, int(kv_len), int(past_len), int(bool(causal)), _dtype_code(qc), _stream(qc)),
-              "l32_gqa_attention_forward")
+        check(L.l32_gqa_attention_forward(_ptr(qc), _ptr(cache_k), _ptr(cache_v), _ptr(keep), _ptr(ctx), _ptr(ws), ws_bytes, b, t,
+                                          heads, kvh, d, max_len, int(kv_len), int(past_len), int(bool(causal)), _dtype_code(qc),
+                                          _stream(qc)), "l32_gqa_attention_forward")
     return ctx
 
 

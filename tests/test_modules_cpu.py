@@ -122,3 +122,46 @@ def test_mixed_dtype_weight_is_rejected_by_cuda_ops_but_module_gates():
     n = L.LLAMARMSNorm(16)
     y = n(torch.randn(2, 16, dtype=torch.bfloat16))
     assert y.dtype == torch.float32   # promotion, as the reference fallback does
+
+
+def test_kv_cache_preallocated_semantics():
+    """KVCache (drop-in for reference Model/model.py:12-29): update() returns what the reference's torch.cat version would,
+    capacity grows by doubling without losing content, num_items() follows layer 0."""
+    import llama32_b200 as L
+    torch.manual_seed(0)
+    cache = L.KVCache(capacity=4)
+    ks, vs = [], []
+    for step, t in enumerate((3, 1, 1, 70, 1)):
+        for layer in range(2):
+            k, v = torch.randn(2, 2, t, 8), torch.randn(2, 2, t, 8)
+            if layer == 0:
+                ks.append(k); vs.append(v)
+            kk, vv = cache.update(k, v, layer)
+            if layer == 0:
+                assert torch.equal(kk, torch.cat(ks, dim=-2)) and torch.equal(vv, torch.cat(vs, dim=-2))
+        assert cache.num_items() == sum(x.shape[-2] for x in ks)
+    assert cache._k[0].shape[2] >= 76 and cache._k[0].shape[2] % 64 == 0
+    assert torch.equal(cache.key_cache[0], torch.cat(ks, dim=-2))
+
+
+@pytest.mark.parametrize("tag", ["d64", "d128"])
+def test_gqa_module_cpu_path_matches_the_reference_fixture(tag, golden):
+    """GroupQueryAttention on CPU fp32 evaluates the reference's expressions: bit-for-bit the reference's own outputs
+    (prefill with a padded batch + a KV-cached decode step), with OUR preallocated KVCache underneath."""
+    import llama32_b200 as L
+    from oracle import ffn_oracle as O
+    g = golden(f"attention_{tag}.npz")
+    heads, kv = int(g["n_heads"]), int(g["n_kv"])
+    b, t, hidden = g["x"].shape
+
+    class Cfg:
+        hidden_size, n_heads, n_kv_groups, rope_base = hidden, heads, kv, float(g["rope_base"])
+    att = L.GroupQueryAttention(Cfg, layer_idx=0).eval()
+    with torch.no_grad():
+        att.W_query.weight.copy_(g["wq"]); att.W_key.weight.copy_(g["wk"]); att.W_value.weight.copy_(g["wv"]); att.out_proj.weight.copy_(g["wo"])
+    cache = L.KVCache()
+    with torch.no_grad():
+        y = att(g["x"], attention_mask=O.causal_padding_mask(g["mask2d"], t), position_ids=g["position_ids"], kv_cache=cache)
+        y1 = att(g["x_decode"], attention_mask=torch.zeros(b, 1, 1, 1), position_ids=g["position_ids_decode"], kv_cache=cache)
+    assert torch.allclose(y, g["y_prefill"], rtol=0, atol=2e-6) and torch.allclose(y1, g["y_decode"], rtol=0, atol=2e-6)
+    assert torch.allclose(cache.key_cache[0], g["cache_k"], rtol=0, atol=2e-6) and torch.equal(cache.value_cache[0], g["cache_v"])
