@@ -19,6 +19,9 @@ full() {   # name, kernel regex, skip, count, target args...
     timeout 900 $NCU --set full --import-source on -k regex:$regex --launch-skip $skip -c $count -f -o $OUT/${TAG}_full_$name \
       python scripts/profile_targets.py "$@" > $OUT/${TAG}_ncu_$name.log 2>&1
     echo "$name: ncu rc=$?" >> $OUT/${TAG}_digest.txt
+    # summarise on the box (gpurun_out/ may carry at most 64 MiB back) and drop the raw report unless asked to keep it
+    python scripts/ncu_summary.py $OUT/${TAG}_full_$name.ncu-rep "lib_sha256_16=$DIGEST; ncu --set full --clock-control none --import-source on; python scripts/profile_targets.py $*; $(date -u +%F)" > $OUT/${TAG}_ncu_full_$name.txt 2>/dev/null
+    if [ "${KEEP_REP:-0}" = 0 ]; then rm -f $OUT/${TAG}_full_$name.ncu-rep; fi
   else
     echo "$name: plain run FAILED, not profiled" >> $OUT/${TAG}_digest.txt
   fi
