@@ -535,6 +535,86 @@ def extra_numbers(dev, peaks):
                                                       "(K and V of the 8 KV heads read once: HBM-bound)"}
     del qd, ck, cv
     torch.cuda.empty_cache()
+
+    # ---- one WHOLE decoder layer at the 11B geometry (norm1 -> GQA attention with RoPE + KV cache -> norm2 -> SwiGLU FFN ->
+    #      residual; reference Model/model.py:257-273) from the drop-in modules, against the same layer evaluated with the
+    #      reference's own expressions on the same GPU (what the reference executes when its extensions are unusable)
+    class _C:
+        hidden_size, n_heads, n_kv_groups, rope_base = H, NH, NKV, 500000.0
+
+    class _Layer(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.att = L.GroupQueryAttention(_C, layer_idx=0)
+            self.norm1, self.norm2 = L.LLAMARMSNorm(H, EPS), L.LLAMARMSNorm(H, EPS)
+            self.ff = L.FusedFeedforward(H, I)
+
+        def forward(self, hs, mask, pos, cache):
+            a = self.att(self.norm1(hs), attention_mask=mask, position_ids=pos, kv_cache=cache)
+            return L.block_tail(self.norm2, self.ff, a, hs)
+
+        def reference(self, hs, mask, pos, cache):           # the reference's expressions, op for op
+            n1 = torch_rms(hs, None, self.norm1.weight)
+            a = self.att._reference_forward(n1, mask, pos, cache)
+            n2 = torch_rms(a, hs, self.norm2.weight)
+            F = torch.nn.functional
+            return a + F.linear(F.silu(F.linear(n2, self.ff.swiglu.w_gate)) * F.linear(n2, self.ff.swiglu.w_up), self.ff.w_down.weight)
+
+    def torch_rms(x_, r_, w_):
+        h_ = x_ if r_ is None else x_ + r_
+        return h_ * torch.rsqrt(h_.pow(2).mean(-1, keepdim=True) + EPS) * w_
+
+    layer = _Layer().to(dev, dt).eval()
+    Bp, Tp = 4, 2048
+    hs = rnd(Bp, Tp, H)
+    pos = torch.arange(Tp, device=dev)[None].expand(Bp, -1).contiguous()
+    mask = torch.triu(torch.full((Tp, Tp), float("-inf"), device=dev, dtype=dt), diagonal=1)[None, None].expand(Bp, 1, Tp, Tp)
+
+    def ours_prefill():
+        with torch.no_grad():
+            layer(hs, mask, pos, L.KVCache(capacity=Tp))
+
+    def ref_prefill():
+        with torch.no_grad():
+            layer.reference(hs, mask, pos, None)
+    t_o = _time_cuda(ours_prefill, 10, warm=3)
+    t_r = _time_cuda(ref_prefill, 5, warm=2)
+    res = {"prefill_4x2048_ms": t_o * 1e3, "prefill_tokens_per_s": Bp * Tp / t_o, "prefill_ms_reference_expressions": t_r * 1e3,
+           "prefill_speedup": t_r / t_o}
+    # decode: batch 64, 2048 cached tokens, one step replayed from a CUDA graph (preallocated cache: stable addresses)
+    Bd, Lk = 64, 2048
+    cache = L.KVCache(capacity=Lk + 64)
+    with torch.no_grad():
+        for i in range(0, Lk, 512):                          # fill the cache with 2048 positions
+            chunk = rnd(Bd, 512, H)
+            cpos = torch.arange(i, i + 512, device=dev)[None].expand(Bd, -1).contiguous()
+            layer.att(layer.norm1(chunk), attention_mask=None, position_ids=cpos, kv_cache=cache)
+    x1 = rnd(Bd, 1, H)
+    p1 = torch.full((Bd, 1), Lk, device=dev, dtype=torch.long)
+    zmask = torch.zeros(Bd, 1, 1, 1, device=dev, dtype=dt)
+
+    def dec_step():
+        with torch.no_grad():
+            cache._len[0] = Lk
+            cache.advance(0, 0)
+            return layer(x1, zmask, p1, cache)
+    for _ in range(3):
+        dec_step()
+    torch.cuda.synchronize()
+    t_eager = _time_cuda(dec_step, 30, warm=3)
+    gph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gph):
+        dec_step()
+    t_graph = _time_cuda(gph.replay, 50, warm=5)
+    res.update({"decode_b64_kv2048_us_graph": t_graph * 1e6, "decode_b64_kv2048_us_eager_launch": t_eager * 1e6,
+                "decode_tokens_per_s_graph": Bd / t_graph,
+                "what": "one decoder layer (32/8 heads x 128, hidden 4096, FFN 14336), bf16: drop-in modules (tcgen05 GEMMs, flash-style "
+                        "attention, preallocated KV cache, fused block tail) vs the same layer through the reference's own expressions "
+                        "(materialised scores, repeat_kv, eager norm / SwiGLU) on the same GPU; decode = 64 sequences x 2048 cached "
+                        "tokens, the step replayed from a CUDA graph and launched eagerly from Python"})
+    out["decoder_layer_11b"] = res
+    del layer, hs, mask, cache
+    torch.cuda.empty_cache()
     return out
 
 
