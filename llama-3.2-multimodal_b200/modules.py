@@ -516,6 +516,11 @@ class KVCache:
             self._k.append(None); self._v.append(None); self._len.append(0)
             self.key_cache.append(None); self.value_cache.append(None)
         k = self._k[layer_idx]
+        if k is not None and (k.shape[0] != batch or k.shape[1] != kv_heads or k.shape[3] != head_dim or k.dtype != dtype or
+                              k.device != torch.device(device)):
+            k = None                                  # a different batch / geometry starts a fresh cache for this layer
+            self._k[layer_idx] = self._v[layer_idx] = None
+            self._len[layer_idx] = 0
         if k is None or k.shape[2] < need:
             cap = max(need, self._capacity, 2 * (k.shape[2] if k is not None else 0), 64)
             cap = -(-cap // 64) * 64
@@ -614,9 +619,14 @@ class GroupQueryAttention(nn.Module):
         return mod(x) if _is_lora(mod) else _linear(x, mod.weight, mod.bias)
 
     def forward(self, hidden_states, attention_mask=None, position_ids=None, kv_cache=None):
-        if position_ids is None or not self._fast_ok(hidden_states, kv_cache):
+        if (position_ids is None or not self._fast_ok(hidden_states, kv_cache) or
+                (attention_mask is not None and not attention_mask.is_floating_point())):
             return self._reference_forward(hidden_states, attention_mask, position_ids, kv_cache)
         b, t, _ = hidden_states.shape
+        if position_ids.dim() == 1:
+            position_ids = position_ids[None]
+        if position_ids.shape[0] != b:
+            position_ids = position_ids.expand(b, -1)
         q = self._project(self.W_query, hidden_states)           # [b, t, heads * d]: the kernels read this layout as it is
         k = self._project(self.W_key, hidden_states)
         v = self._project(self.W_value, hidden_states)

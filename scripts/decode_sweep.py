@@ -3,7 +3,7 @@ import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 if len(sys.argv) == 1:
-    settings = [{}, {"L32_DECODE_SPLITS_LINEAR": "4"}, {"L32_DECODE_SPLITS_LINEAR": "2"}, {"L32_DECODE_SPLITS_SWIGLU": "2"}]
+    settings = [{}, {"L32_DECODE_CTAS_PER_SM": "3"}, {"L32_DECODE_CTAS_PER_SM": "4"}, {"L32_DECODE_CTAS_PER_SM": "1"}]
     for st in settings:
         subprocess.run([sys.executable, __file__, "run", repr(st)], env={**os.environ, **st})
     sys.exit(0)
@@ -30,8 +30,11 @@ for B in (1, 16, 32, 48, 64, 128):
     def nxt():
         i[0] += 1
         return ws[i[0] % 3]
+    gamma = torch.ones(H, device=dev, dtype=torch.bfloat16)
+    r = torch.randn(B, H, device=dev, generator=g).bfloat16()
+    t_blk = timeit(lambda: ops.ffn_forward(ops.add_rmsnorm_forward(x, gamma, r, 1e-5, want_rms=False)[0], *nxt()))
     t_ffn = timeit(lambda: ops.ffn_forward(x, *nxt()))
     t_gu = timeit(lambda: ops.swiglu_forward(x, *nxt()[:2]))
     t_dn = timeit(lambda: ops.linear_forward(act, nxt()[2]))
-    out.append(f"B={B}: ffn {t_ffn:.1f} gu {t_gu:.1f} ({2*H*I*2/t_gu/1e3:.0f} GB/s) dn {t_dn:.1f} ({H*I*2/t_dn/1e3:.0f} GB/s)")
+    out.append(f"B={B}: norm+ffn {t_blk:.1f} ffn {t_ffn:.1f} gu {t_gu:.1f} ({2*H*I*2/t_gu/1e3:.0f} GB/s) dn {t_dn:.1f} ({H*I*2/t_dn/1e3:.0f} GB/s)")
 print(sys.argv[2], " | ".join(out), flush=True)
