@@ -12,8 +12,11 @@
 //     reduces its fp32 partials through distributed shared memory (no atomics, no workspace, deterministic);
 //   * the host sizes the grid so that ALL CTAs are co-resident (2-4 per SM): equal work per CTA and a fair
 //     share of HBM bandwidth means no wave-quantisation tail although 224 or 256 units never divide by 148 SMs;
-//   * warp 0 streams weight tiles (TMA, evict-first) and activation tiles (TMA, evict-last) through a deep
-//     shared-memory ring, warp 1 issues tcgen05.mma, all four warps run the epilogue;
+//   * warp 0 streams weight tiles (TMA, evict-first) through a deep shared-memory ring, warp 2 the activation tiles (TMA,
+//     evict-last) through a SEPARATE shallow ring: the weights come from HBM and need many bytes in flight, the token
+//     tiles come from L2 and need little lookahead, so they do not take ring depth away from the weights (at 64 tokens a
+//     joint ring had 4 stages of 24 KB, the split rings hold 6 x 16 KB of weights + 2 x 8 KB of tokens in the same space);
+//     warp 1 issues tcgen05.mma, all four warps run the epilogue;
 //   * gate and up rows of the same 64 act columns sit in one 128-row A tile (two 64-row TMA boxes), so
 //     SiLU(g)*u is applied on chip and gate / up never exist in HBM;
 //   * programmatic dependent launch: the kernel prefetches its first weight stages BEFORE waiting for the
@@ -30,10 +33,12 @@ namespace {
 constexpr int kBlockK = 64;                 // one 128-byte swizzle atom of 16-bit elements
 constexpr int kUmmaK = 16;
 constexpr int kRowsA = 128;                 // UMMA M: weight rows per CTA
-constexpr int kThreads = 128;
+constexpr int kMaxThreads = 512;             // 4 x kParts warps; launched with 128 * parts threads (a one-warp-per-scheduler
+                                             // epilogue ran at low IPC and is a pure tail: no HBM traffic while it runs)
 constexpr int kABytes = kRowsA * kBlockK * 2;   // 16 KiB weight tile per stage
-constexpr int kMaxStages = 12;
-constexpr int kBarrierBytes = (2 * kMaxStages + 1) * 8 + 16;
+constexpr int kMaxStages = 12;               // weight ring
+constexpr int kMaxXStages = 8;               // token-tile ring
+constexpr int kBarrierBytes = (2 * kMaxStages + 2 * kMaxXStages + 1) * 8 + 16;
 
 enum : int { DEC_LINEAR = 0, DEC_SWIGLU = 1 };
 
@@ -48,7 +53,10 @@ struct DecodeParams {
     int rows_out;           // inter (SwiGLU) or out_features (linear)
     int k;                  // reduction length
     int splits;             // K splits = cluster size
-    int stages;             // shared-memory ring depth
+    int stages;             // depth of the weight ring (16 KB per stage)
+    int xstages;            // depth of the token-tile ring (n_pad * 128 bytes per stage)
+    int dbg_nox;            // experiments only (L32_DECODE_DEBUG_NOX=1, wrong results): token tiles are loaded for the first
+                            // `xstages` k-blocks only -- what the step costs without the token tiles' L2 traffic
     int rotate;             // 1: every row block starts its K loop at a different k-block (spreads the L2 reads of
                             // the shared activation tiles over time instead of all CTAs hitting the same lines)
     long long ldo;          // row pitch of out, elements
@@ -71,16 +79,18 @@ L32_DEVICE float ld_dsmem_f32(uint32_t local_addr, uint32_t cta_rank) {
 }
 
 template <int kEpi, typename T>
-__global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_constant__ DecodeParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int stages = p.stages;
+__global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_constant__ DecodeParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];   // no static shared memory in this kernel: the window starts 1024-aligned
+    const int stages = p.stages, xstages = p.xstages;
     const uint32_t b_bytes = static_cast<uint32_t>(p.n_pad) * 128u;
-    const uint32_t stage_bytes = kABytes + b_bytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+    uint8_t* smem_x = smem + stages * kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_x + xstages * b_bytes);
     uint64_t* empty_bar = full_bar + kMaxStages;
-    uint64_t* tfull_bar = empty_bar + kMaxStages;
+    uint64_t* xfull_bar = empty_bar + kMaxStages;
+    uint64_t* xempty_bar = xfull_bar + kMaxXStages;
+    uint64_t* tfull_bar = xempty_bar + kMaxXStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();       // the 128-byte swizzle needs 1024-aligned tiles
 
     const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const uint32_t lane = lane_id();
@@ -102,6 +112,10 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
+        for (int i = 0; i < xstages; ++i) {
+            mbar_init(&xfull_bar[i], 1);
+            mbar_init(&xempty_bar[i], 1);
+        }
         mbar_init(tfull_bar, 1);
         fence_mbar_init();
     }
@@ -119,12 +133,15 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            // ---------------------------------------------------------------- TMA producer
+            // ---------------------------------------------------------------- TMA producer: weights
             // (running stage / k-block counters: no integer divisions in the per-stage instruction stream)
             const int row0 = row_block * (kEpi == DEC_SWIGLU ? 64 : kRowsA);
-            auto load_w = [&](int s, int kr) {
-                uint8_t* sa = smem + s * stage_bytes;
-                mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+            int s = 0, kr = rot;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < cnt; ++kb) {                  // weights do not depend on the previous kernel: no PDL wait here
+                if (kb >= stages) mbar_wait(&empty_bar[s], phase ^ 1u);
+                uint8_t* sa = smem + s * kABytes;
+                mbar_arrive_expect_tx(&full_bar[s], kABytes);
                 const int kcol = (kb0 + kr) * kBlockK;
                 if constexpr (kEpi == DEC_SWIGLU) {
                     tma_load_2d(sa, &p.map_w[0], &full_bar[s], kcol, row0, kEvictFirst);
@@ -132,45 +149,40 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
                 } else {
                     tma_load_2d(sa, &p.map_w[0], &full_bar[s], kcol, row0, kEvictFirst);
                 }
-            };
-            auto load_x = [&](int s, int kr) {
-                tma_load_2d(smem + s * stage_bytes + kABytes, &p.map_x, &full_bar[s], (kb0 + kr) * kBlockK, 0, kEvictLast);
-            };
-            const int pre = min(stages, cnt);
-            {
-                int kr = rot;
-                for (int kb = 0; kb < pre; ++kb) {            // weights do not depend on the previous kernel
-                    load_w(kb, kr);
-                    if (++kr == cnt) kr = 0;
-                }
+                if (++kr == cnt) kr = 0;
+                if (++s == stages) { s = 0; phase ^= 1u; }
             }
-            pdl_wait_prior_grid();                              // activations do
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // ---------------------------------------------------------------- TMA producer: token tiles (L2-resident)
+            pdl_wait_prior_grid();                              // the activations are the previous kernel's output
             int s = 0, kr = rot;
             uint32_t phase = 0;
             for (int kb = 0; kb < cnt; ++kb) {
-                if (kb >= pre) {
-                    mbar_wait(&empty_bar[s], phase ^ 1u);
-                    load_w(s, kr);
-                }
-                load_x(s, kr);
+                if (p.dbg_nox && kb >= xstages) break;
+                if (kb >= xstages) mbar_wait(&xempty_bar[s], phase ^ 1u);
+                mbar_arrive_expect_tx(&xfull_bar[s], b_bytes);
+                tma_load_2d(smem_x + s * b_bytes, &p.map_x, &xfull_bar[s], (kb0 + kr) * kBlockK, 0, kEvictLast);
                 if (++kr == cnt) kr = 0;
-                if (++s == stages) { s = 0; phase ^= 1u; }
+                if (++s == xstages) { s = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ---------------------------------------------------------------- MMA issuer
-            // This one thread's instruction stream (wait, 4 x tcgen05.mma, commit per 16 KB of weights) paces the stage: the
+            // This one thread's instruction stream (waits, 4 x tcgen05.mma, commits per 16 KB of weights) paces the stage: the
             // shared-memory descriptors are built ONCE and advanced by adding to their 14-bit address field (>> 4 units;
             // shared-memory addresses are < 256 KB, so the field never carries into the next one).
             const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(smem), 0, 1024);
-            const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem) + kABytes, 0, 1024);
-            const uint32_t stage_step = stage_bytes >> 4;
+            const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(smem_x), 0, 1024);
+            const uint32_t a_step = kABytes >> 4, b_step = b_bytes >> 4;
             uint32_t accumulate = 0;
-            int s = 0;
-            uint32_t phase = 0;
+            int s = 0, sx = 0;
+            uint32_t phase = 0, xphase = 0;
             uint64_t a_desc = a_desc0, b_desc = b_desc0;
             for (int kb = 0; kb < cnt; ++kb) {
+                if (!(p.dbg_nox && kb >= xstages)) mbar_wait(&xfull_bar[sx], xphase);
                 mbar_wait(&full_bar[s], phase);
                 tc_fence_after();
 #pragma unroll
@@ -180,14 +192,20 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
                     accumulate = 1;
                 }
                 umma_commit<1>(&empty_bar[s]);
+                umma_commit<1>(&xempty_bar[sx]);
                 if (++s == stages) {
                     s = 0;
                     phase ^= 1u;
                     a_desc = a_desc0;
+                } else {
+                    a_desc += a_step;
+                }
+                if (++sx == xstages) {
+                    sx = 0;
+                    xphase ^= 1u;
                     b_desc = b_desc0;
                 } else {
-                    a_desc += stage_step;
-                    b_desc += stage_step;
+                    b_desc += b_step;
                 }
             }
             umma_commit<1>(tfull_bar);
@@ -201,10 +219,15 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
     pdl_wait_prior_grid();   // `out` may still be read by the previous kernel of the stream
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
+    // Warp w reads TMEM lanes 32 * (w % 4) .. + 31 (hardware rule); the `nparts` warps of a lane quarter split the tokens in
+    // units of 8 (one tcgen05.ld.x8 each).
     float* part = reinterpret_cast<float*>(smem);
-    const int row = static_cast<int>(warp * 32 + lane);
-    const uint32_t taddr = tmem_base + ((warp * 32u) << 16);
-    const int nchunks = (p.tokens + 15) >> 4;
+    const uint32_t quarter = warp & 3u;
+    const int pt = static_cast<int>(warp >> 2);
+    const int nparts = static_cast<int>(blockDim.x >> 7);
+    const int row = static_cast<int>(quarter * 32 + lane);
+    const uint32_t taddr = tmem_base + ((quarter * 32u) << 16);
+    const int units = p.n_pad >> 3;            // even: n_pad is a multiple of 16
     T* out = static_cast<T*>(p.out);
 
     if (p.splits == 1) {
@@ -212,8 +235,9 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
         if constexpr (kEpi == DEC_SWIGLU) {
             // lanes 0-63 hold gate rows, lanes 64-127 the up rows of the same 64 act columns.  Token chunks of 16
             // alternate between the two halves: the gate warps finish the even chunks (up values through shared
-            // memory), the up warps the odd ones (gate values through shared memory).
-            const bool is_gate = warp < 2;
+            // memory), the up warps the odd ones (gate values through shared memory); chunk pairs alternate between the
+            // two warps of a lane quarter.
+            const bool is_gate = quarter < 2;
             const int r = row & 63;
             const int col = row_block * 64 + r;
             const bool col_ok = col < p.rows_out;
@@ -222,33 +246,35 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
                 if (p.bias[0] != nullptr) bg = static_cast<float>(static_cast<const T*>(p.bias[0])[col]);
                 if (p.bias[1] != nullptr) bu = static_cast<float>(static_cast<const T*>(p.bias[1])[col]);
             }
-            for (int c = is_gate ? 1 : 0; c < nchunks; c += 2) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(taddr + c * 16, v);
+            for (int uu = pt; uu < (units >> 1); uu += nparts) {          // units the OTHER kind finishes: export
+                const int u = 2 * uu + (is_gate ? 1 : 0);
+                uint32_t v[8];
+                tmem_ld_32x32b_x8(taddr + u * 8, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) part[(c * 16 + j) * 64 + r] = __uint_as_float(v[j]);
+                for (int j = 0; j < 8; ++j) part[(u * 8 + j) * 64 + r] = __uint_as_float(v[j]);
             }
             __syncthreads();
-            for (int c = is_gate ? 0 : 1; c < nchunks; c += 2) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(taddr + c * 16, v);
-                float o[16];
+            for (int uu = pt; uu < (units >> 1); uu += nparts) {
+                const int u = 2 * uu + (is_gate ? 0 : 1);
+                uint32_t v[8];
+                tmem_ld_32x32b_x8(taddr + u * 8, v);
+                float o[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = part[(c * 16 + j) * 64 + r];
+                for (int j = 0; j < 8; ++j) o[j] = part[(u * 8 + j) * 64 + r];
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     const float mine = __uint_as_float(v[j]);
                     const float g = (is_gate ? mine : o[j]) + bg;
-                    const float u = (is_gate ? o[j] : mine) + bu;
-                    const int n = c * 16 + j;
+                    const float uu_ = (is_gate ? o[j] : mine) + bu;
+                    const int n = u * 8 + j;
                     if (col_ok && n < p.tokens) {
                         const size_t o_idx = static_cast<size_t>(n) * p.ldo + col;
-                        out[o_idx] = static_cast<T>(silu_f32(g) * u);
+                        out[o_idx] = static_cast<T>(silu_f32(g) * uu_);
                         if (p.cache[0] != nullptr) {
                             static_cast<T*>(p.cache[0])[o_idx] = static_cast<T>(g);
-                            static_cast<T*>(p.cache[1])[o_idx] = static_cast<T>(u);
+                            static_cast<T*>(p.cache[1])[o_idx] = static_cast<T>(uu_);
                         }
                     }
                 }
@@ -258,13 +284,13 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
             const bool col_ok = col < p.rows_out;
             float b = 0.f;
             if (col_ok && p.bias[0] != nullptr) b = static_cast<float>(static_cast<const T*>(p.bias[0])[col]);
-            for (int c = 0; c < nchunks; ++c) {
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(taddr + c * 16, v);
+            for (int u = pt; u < units; u += nparts) {
+                uint32_t v[8];
+                tmem_ld_32x32b_x8(taddr + u * 8, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = c * 16 + j;
+                for (int j = 0; j < 8; ++j) {
+                    const int n = u * 8 + j;
                     if (col_ok && n < p.tokens) {
                         const size_t o_idx = static_cast<size_t>(n) * p.ldo + col;
                         float r = __uint_as_float(v[j]) + b;
@@ -285,15 +311,15 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
 
     // ---- split-K path: park the fp32 partial as part[token][row], reduce across the cluster through DSMEM
     if (cnt > 0) {
-        for (int c = 0; c < nchunks; ++c) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(taddr + c * 16, v);
+        for (int u = pt; u < units; u += nparts) {
+            uint32_t v[8];
+            tmem_ld_32x32b_x8(taddr + u * 8, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) part[(c * 16 + j) * kRowsA + row] = __uint_as_float(v[j]);
+            for (int j = 0; j < 8; ++j) part[(u * 8 + j) * kRowsA + row] = __uint_as_float(v[j]);
         }
     } else {
-        for (int n = 0; n < nchunks * 16; ++n) part[n * kRowsA + row] = 0.f;
+        for (int n = pt; n < p.n_pad; n += nparts) part[n * kRowsA + row] = 0.f;
     }
     tc_fence_before();
     __syncwarp();
@@ -319,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
             if (p.bias[0] != nullptr) bg = static_cast<float>(static_cast<const T*>(p.bias[0])[col]);
             if (p.bias[1] != nullptr) bu = static_cast<float>(static_cast<const T*>(p.bias[1])[col]);
         }
-        for (int n = n_lo + (row >> 6); n < n_hi; n += 2) {
+        for (int n = n_lo + (row >> 6) + 2 * pt; n < n_hi; n += 2 * nparts) {
             const float g = sum_splits(part_addr + (n * kRowsA + r) * 4) + bg;
             const float u = sum_splits(part_addr + (n * kRowsA + 64 + r) * 4) + bu;
             if (col_ok) {
@@ -341,13 +367,13 @@ __global__ void __launch_bounds__(kThreads) ffn_decode_kernel(const __grid_const
             if (p.addend != nullptr) r = static_cast<float>(static_cast<T>(r)) + static_cast<float>(static_cast<const T*>(p.addend)[o_idx]);
             out[o_idx] = static_cast<T>(r);
         };
-        int n = n_lo;
-        for (; n + 2 <= n_hi; n += 2) {
+        int n = n_lo + pt;
+        for (; n + nparts < n_hi; n += 2 * nparts) {          // two tokens of this warp's strided sequence at a time
             const float a0 = sum_splits(part_addr + (n * kRowsA + row) * 4);
-            const float a1 = sum_splits(part_addr + ((n + 1) * kRowsA + row) * 4);
+            const float a1 = sum_splits(part_addr + ((n + nparts) * kRowsA + row) * 4);
             if (col_ok) {
                 store_out(n, a0 + b);
-                store_out(n + 1, a1 + b);
+                store_out(n + nparts, a1 + b);
             }
         }
         if (n < n_hi) {
@@ -370,7 +396,7 @@ int env_int(const char* name, int dflt) {
 }
 
 template <int kEpi, typename T>
-int launch_decode(const DecodeParams& p, int grid, size_t smem_bytes, cudaStream_t s) {
+int launch_decode(const DecodeParams& p, int grid, int threads, size_t smem_bytes, cudaStream_t s) {
     auto* kernel = ffn_decode_kernel<kEpi, T>;
     static size_t configured_dev[kMaxDevices] = {};   // per instantiation and device: dynamic smem opted into so far
     size_t& configured = configured_dev[current_device_slot()];
@@ -381,7 +407,7 @@ int launch_decode(const DecodeParams& p, int grid, size_t smem_bytes, cudaStream
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(static_cast<unsigned>(threads));
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[2];
@@ -435,25 +461,39 @@ int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0
     if (splits < 1 || splits > 8 || (splits & (splits - 1)) != 0 || splits > nkb) return L32_ERR_BAD_SHAPE;
     p.splits = splits;
     p.rotate = env_int("L32_DECODE_ROTATE", 1);
+    p.dbg_nox = env_int("L32_DECODE_DEBUG_NOX", 0);
     const int grid = row_blocks * splits;
 
-    // Ring depth: all CTAs co-resident (up to 4 per SM), shared memory split evenly between them.
+    // Ring depths: all CTAs co-resident (up to 4 per SM), shared memory split evenly between them.  The token ring is
+    // shallow (its tiles come from L2; 3 stages = two k-blocks of lookahead, 2 when the tile is 8 KB or more), the weight
+    // ring takes everything else.
     int per_sm = (grid + sms - 1) / sms;
     if (per_sm > 4) per_sm = 4;
     if (const int v = env_int("L32_DECODE_CTAS_PER_SM", 0)) per_sm = v;
-    const int stage_bytes = kABytes + p.n_pad * 128;
-    const int budget = (228 * 1024) / per_sm - 1024 /* driver-reserved */ - 1024 /* alignment slack */ - kBarrierBytes;
-    int stages = budget / stage_bytes;
+    const int b_bytes = p.n_pad * 128;
+    const int budget = (228 * 1024) / per_sm - 1024 /* driver-reserved */ - kBarrierBytes;
     const int kb_per_cta = (nkb + splits - 1) / splits;
+    int xstages = b_bytes >= 8192 ? 2 : 3;
+    if (const int v = env_int("L32_DECODE_XSTAGES", 0)) xstages = v;
+    if (xstages > kb_per_cta) xstages = kb_per_cta;
+    if (xstages > kMaxXStages) xstages = kMaxXStages;
+    if (xstages < 1) xstages = 1;
+    int stages = (budget - xstages * b_bytes) / kABytes;
     if (stages > kb_per_cta) stages = kb_per_cta;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) stages = 2;
     if (const int v = env_int("L32_DECODE_STAGES", 0)) stages = v < kMaxStages ? v : kMaxStages;
-    // the fp32 partial [n_pad][128] of the epilogue reuses the ring
-    while (stages * stage_bytes < p.n_pad * kRowsA * 4) ++stages;
+    if (env_int("L32_DECODE_XSTAGES", 0) == 0) {   // what the weight ring leaves over deepens the token ring
+        const int spare = (budget - stages * kABytes) / b_bytes;
+        if (spare > xstages) xstages = spare < kMaxXStages ? spare : kMaxXStages;
+        if (xstages > kb_per_cta) xstages = kb_per_cta;
+    }
+    // the fp32 partial [n_pad][128] of the epilogue reuses the rings (contiguous: weights first, then tokens)
+    while (stages * kABytes + xstages * b_bytes < p.n_pad * kRowsA * 4) ++stages;
     if (stages < 1 || stages > kMaxStages) return L32_ERR_BAD_SHAPE;
     p.stages = stages;
-    const size_t smem_bytes = static_cast<size_t>(stages) * stage_bytes + kBarrierBytes + 1024;
+    p.xstages = xstages;
+    const size_t smem_bytes = static_cast<size_t>(stages) * kABytes + static_cast<size_t>(xstages) * b_bytes + kBarrierBytes;
     if (smem_bytes > 227 * 1024) return L32_ERR_BAD_SHAPE;
 
     int rc = make_tensor_map_2d(&p.map_x, x, static_cast<uint64_t>(tokens), static_cast<uint64_t>(k), static_cast<uint64_t>(k),
@@ -467,8 +507,12 @@ int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0
                                 static_cast<uint64_t>(k), rows_per_block, kBlockK, dtype);
         if (rc != L32_OK) return rc;
     }
-    if (dtype == L32_BF16) return launch_decode<kEpi, __nv_bfloat16>(p, grid, smem_bytes, s);
-    return launch_decode<kEpi, __half>(p, grid, smem_bytes, s);
+    // epilogue parallelism: 8 warps above 16 tokens (measured: 4 -> 8 warps takes 2 us off a 64-token step, 16 add nothing)
+    int threads = p.n_pad > 16 ? 256 : 128;
+    if (const int v = env_int("L32_DECODE_THREADS", 0)) threads = v;
+    if (threads < 128 || threads > kMaxThreads || (threads % 128) != 0) return L32_ERR_BAD_SHAPE;
+    if (dtype == L32_BF16) return launch_decode<kEpi, __nv_bfloat16>(p, grid, threads, smem_bytes, s);
+    return launch_decode<kEpi, __half>(p, grid, threads, smem_bytes, s);
 }
 
 }  // namespace

@@ -58,9 +58,10 @@ struct TileCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 4 * kEpiStageBytes + kNumBarriers * 8 + 16;
 };
 
+constexpr int kMaxGroup = 3;
 struct GemmKernelParams {
-    CUtensorMap map_a[2];
-    CUtensorMap map_b[2];
+    CUtensorMap map_a[kMaxGroup];   // per accumulation phase -- or, for a grouped launch (nprob > 1), per problem
+    CUtensorMap map_b[kMaxGroup];
     int m, n;
     int k[2];
     int num_phases;
@@ -83,6 +84,12 @@ struct GemmKernelParams {
     int ffn_prefix;         // gate/up-only tiles at the head of every mixed round
     uint32_t idesc_dn;
     uint32_t* act_done;
+    // Grouped launch (EPI_STORE, one phase): nprob independent problems with the same K and operand majors share ONE
+    // persistent tile loop -- e.g. the three weight-gradient GEMMs of a training step: 3 x 896 tiles = 36.3 waves instead of
+    // 3 x (12.1 run as 13).  Problem i: D_i = d[i] [gm x gn, pitch gldd], tiles [gstart[i], gstart[i + 1]).
+    int nprob;
+    int gm[kMaxGroup], gn[kMaxGroup], gtm[kMaxGroup], gtn[kMaxGroup], gstart[kMaxGroup + 1];
+    long long gldd[kMaxGroup];
     const long long* ce_labels;   // EPI_CE: target column of every row (int64; anything outside [0, n) never matches)
     float2* ce_partials;          // EPI_CE: [m][tiles_n] (max, sum of exp(v - max)) of the tile's columns of that row
     float* ce_target;             // EPI_CE: [m] logit of the target column (written by the tile that holds it)
@@ -290,19 +297,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
     const uint32_t rank = (kCtaGroup == 2) ? cluster_ctarank() : 0u;
     const int cluster_id = blockIdx.x / kCtaGroup;
     const int num_clusters = gridDim.x / kCtaGroup;
-    const int num_tiles = p.tiles_m * (p.tiles_n + (kTp ? p.tiles_n_dn : 0));
+    const bool grouped = (kEpi == EPI_STORE) && p.nprob > 1;
+    const int num_tiles = grouped ? p.gstart[p.nprob] : p.tiles_m * (p.tiles_n + (kTp ? p.tiles_n_dn : 0));
     const TileOrder order = {p.tiles_m, p.tiles_n, p.raster_group, p.m_rotate, p.m_il_world, p.m_il_tpc, p.rs.rank};
     const FfnOrder forder = {p.tiles_m, p.tiles_n, p.tiles_n_dn, p.raster_group, p.m_rotate, p.ffn_prefix};
     auto get_tile = [&](int t) -> TileCoord {
-        if constexpr (kTp) return ffn_tile_coord(t, forder);
-        else return tile_coord(t, order);
+        if constexpr (kTp) {
+            return ffn_tile_coord(t, forder);
+        } else {
+            if (grouped) {
+                int pr = 0;
+                while (pr + 1 < p.nprob && t >= p.gstart[pr + 1]) ++pr;
+                const TileOrder go = {p.gtm[pr], p.gtn[pr], p.raster_group, 0, 0, 0, 0};
+                TileCoord c = tile_coord(t - p.gstart[pr], go);
+                c.prob = pr;                                   // here: index of the problem of the group
+                return c;
+            }
+            return tile_coord(t, order);
+        }
     };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.map_a[0]);
         tma_prefetch_desc(&p.map_b[0]);
-        if (p.num_phases == 2) tma_prefetch_desc(&p.map_a[1]);
-        if (p.num_phases == 2 || kEpi == EPI_SWIGLU || kTp) tma_prefetch_desc(&p.map_b[1]);
+        if (p.num_phases == 2 || p.nprob > 1) tma_prefetch_desc(&p.map_a[1]);
+        if (p.nprob > 2) {
+            tma_prefetch_desc(&p.map_a[2]);
+            tma_prefetch_desc(&p.map_b[2]);
+        }
+        if (p.num_phases == 2 || p.nprob > 1 || kEpi == EPI_SWIGLU || kTp) tma_prefetch_desc(&p.map_b[1]);
         if constexpr (kEpi == EPI_SWIGLU_BWD) {
             tma_prefetch_desc(&p.map_out[0]);
             tma_prefetch_desc(&p.map_out[1]);
@@ -369,8 +392,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                 }
                 for (int ph = 0; ph < p.num_phases; ++ph) {
                     const int num_kb = ((dn ? p.k_dn : p.k[ph]) + kBlockK - 1) / kBlockK;
-                    const CUtensorMap* map_a = dn ? &p.map_a_dn : &p.map_a[ph];
-                    const CUtensorMap* map_b = dn ? &p.map_b_dn : &p.map_b[ph];
+                    const CUtensorMap* map_a = dn ? &p.map_a_dn : &p.map_a[grouped ? tc.prob : ph];
+                    const CUtensorMap* map_b = dn ? &p.map_b_dn : &p.map_b[grouped ? tc.prob : ph];
                     for (int kb = 0; kb < num_kb; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
                         uint8_t* sa = smem_a + stage * Cfg::kABytes;
@@ -452,11 +475,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
             const bool dn = kTp && tc.prob == 1;
             const bool store_tile = (kEpi == EPI_STORE) || (kEpi == EPI_CE) || dn;
             const bool swiglu_tile = (kEpi == EPI_SWIGLU) || (kTp && !dn);
-            const int tile_n = dn ? p.n_dn : p.n;                              // valid output columns of this problem
-            const size_t tile_ldd = static_cast<size_t>(dn ? p.n_dn : p.ldd);  // and its row pitch
+            const int tile_n = dn ? p.n_dn : (grouped ? p.gn[tc.prob] : p.n);   // valid output columns of this problem
+            const size_t tile_ldd = static_cast<size_t>(dn ? p.n_dn : (grouped ? p.gldd[tc.prob] : p.ldd));  // and its row pitch
             const int row = tc.m_blk * (kBlockM * kCtaGroup) + static_cast<int>(rank) * kBlockM + q * 32 + lane;
             const int n0 = tc.n_blk * (dn ? kAccCols : kTileNOut);
-            const bool row_ok = row < p.m;
+            const bool row_ok = row < (grouped ? p.gm[tc.prob] : p.m);
             const size_t row_off = static_cast<size_t>(row_ok ? row : 0) * tile_ldd;
             // EPI_SWIGLU_BWD: the gate / up cache rows of step c + 2 (this warp's next step) are requested before step c is
             // computed, the first ones before the accumulator is even complete (they do not depend on it)
@@ -506,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
                         d_row = static_cast<uint8_t*>(p.rs.peer_dst[owner]) +
                                 static_cast<size_t>(row - owner * p.rs.rows_per_rank) * tile_ldd * esz;
                     } else {
-                        d_row = static_cast<uint8_t*>(p.d[0]) + row_off * esz;
+                        d_row = static_cast<uint8_t*>(p.d[grouped ? tc.prob : 0]) + row_off * esz;
                     }
                 }
                 const uint8_t* add_row = (!kTp && p.e[0] != nullptr) ? static_cast<const uint8_t*>(p.e[0]) + row_off * esz : nullptr;
@@ -1003,6 +1026,37 @@ int gemm_sm100(const GemmProblem& g, cudaStream_t s) {
             int rc = make_tensor_map_2d(&kp.map_b[i], g.b[i].ptr, g.n, g.k[0], g.b[i].ld, n_act, kBlockK, g.dtype);
             if (rc != L32_OK) return rc;
         }
+    }
+    if (g.group_count > 1) {
+        // a grouped launch: every problem shares K, the operand majors and the dtype; no bias / addend / collectives
+        if (g.group_count > kMaxGroup || g.epilogue != EPI_STORE || g.num_phases != 1 || g.e[0] != nullptr || g.bias[0] != nullptr ||
+            g.rs.world > 0 || g.ag.world > 0 || cta_group != 2 || g.k[0] <= 0)
+            return L32_ERR_BAD_SHAPE;
+        kp.nprob = g.group_count;
+        int start = 0;
+        for (int i = 0; i < g.group_count; ++i) {
+            const GroupMember& q = g.group[i];
+            if (q.m <= 0 || q.n <= 0 || (q.n % 8) != 0 || (q.ldd % 8) != 0 || q.d == nullptr || !is_aligned16(q.d)) return L32_ERR_BAD_SHAPE;
+            kp.gm[i] = q.m; kp.gn[i] = q.n; kp.gldd[i] = q.ldd;
+            kp.gtm[i] = (q.m + tile_m - 1) / tile_m;
+            kp.gtn[i] = (q.n + kAccCols - 1) / kAccCols;
+            kp.gstart[i] = start;
+            start += kp.gtm[i] * kp.gtn[i];
+            kp.d[i] = q.d;
+            int rc;
+            if (!g.a[0].mn_major) rc = make_tensor_map_2d(&kp.map_a[i], q.a, q.m, g.k[0], q.lda, kBlockM, kBlockK, g.dtype);
+            else rc = make_tensor_map_2d(&kp.map_a[i], q.a, g.k[0], q.m, q.lda, kBlockK, 64, g.dtype);
+            if (rc != L32_OK) return rc;
+            if (!g.b[0].mn_major) rc = make_tensor_map_2d(&kp.map_b[i], q.b, q.n, g.k[0], q.ldb, kAccCols / cta_group, kBlockK, g.dtype);
+            else rc = make_tensor_map_2d(&kp.map_b[i], q.b, g.k[0], q.n, q.ldb, kBlockK, 64, g.dtype);
+            if (rc != L32_OK) return rc;
+        }
+        kp.gstart[g.group_count] = start;
+        kp.k[0] = g.k[0];
+        kp.m_il_world = 0;
+        kp.m_rotate = 0;
+        if (g.dtype == L32_BF16) return launch_epi<2, __nv_bfloat16>(kp, EPI_STORE, start, g.max_ctas, s);
+        return launch_epi<2, __half>(kp, EPI_STORE, start, g.max_ctas, s);
     }
     if (g.epilogue == EPI_CE) {
         if (g.ce.labels == nullptr || g.ce.partials == nullptr || g.ce.target == nullptr) return L32_ERR_NULL;

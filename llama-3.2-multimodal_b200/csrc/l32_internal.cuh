@@ -91,6 +91,15 @@ struct CeOutputs {
     float* target;
 };
 
+// One problem of a grouped launch: D[m, n] = A B^T with the group's common K, majors and dtype (GemmProblem::group).
+struct GroupMember {
+    const void* a;   // K-major: [m, k] (pitch lda);  MN-major: [k, m]
+    const void* b;   // K-major: [n, k] (pitch ldb);  MN-major: [k, n]
+    void* d;         // [m, n], pitch ldd
+    int64_t lda, ldb, ldd;
+    int m, n;
+};
+
 struct GemmProblem {
     int m, n;               // D is [m, n]; for EPI_SWIGLU n = intermediate size (act columns)
     int num_phases;         // 1, or 2 for D = A0*B0^T + A1*B1^T (EPI_SWIGLU: must be 1)
@@ -111,6 +120,8 @@ struct GemmProblem {
     TpReduceScatter rs;     // rs.world == 0: off (EPI_STORE and the down half of EPI_FFN_TP)
     TpFfnDown dn;           // EPI_FFN_TP only
     CeOutputs ce;           // EPI_CE only
+    int group_count;        // > 1: grouped launch (EPI_STORE, cta_group 2): `group` replaces m / n / a[].ptr / b[].ptr / d
+    GroupMember group[3];   //      (k[0], a[0].mn_major, b[0].mn_major and dtype are shared)
 };
 int gemm_sm100(const GemmProblem& p, cudaStream_t s);   // returns L32_* / cudaError_t
 void debug_tile_order(int t, int tiles_m, int tiles_n, int group, int m_rotate, int il_world, int il_tpc, int il_rank, int* out3);
