@@ -18,6 +18,8 @@
 // triu(-inf, 1), model.py:314-317), key padding (model.py:318, as a per-key keep byte) and the cache length.
 #include "l32_internal.cuh"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace l32 {
@@ -44,14 +46,20 @@ struct AttnParams {
     float2* part_ml;     // [batch][heads][splits][q_len] (m_ref in the log2 domain, l)
 };
 
+// L32_ATT_NOEXP / L32_ATT_NOPV / L32_ATT_NOLD: experiment builds only (wrong results) -- what the kernel costs without the
+// exponentials, without the P V MMAs, without the S reads from TMEM.
 L32_DEVICE float fast_exp2(float x) {
+#ifdef L32_ATT_NOEXP
+    return x * 0.001f;
+#else
     float y;
     asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 
 template <int kD, typename T>
-__global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ AttnParams p) {
     constexpr int kDAtoms = kD / 64;                       // 64-element (128-byte) column blocks of a head
     constexpr int kQBytes = kQTile * kD * 2;
     constexpr int kKBytes = kKvTile * kD * 2;              // also the V tile
@@ -70,15 +78,19 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
     uint64_t* bar_s = bar_v + 2;                           // [2] S = Q K^T complete (two accumulators: S of tile t + 1 runs
                                                            //     on the tensor cores while the softmax of tile t is computed)
     uint64_t* bar_o = bar_s + 2;                           // P V complete (P and the V stage may be reused)
-    uint64_t* bar_p = bar_o + 1;                           // P of the tile is in shared memory, S and O are drained (128 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_p + 1);
+    uint64_t* bar_p = bar_o + 1;                           // P of the tile is in shared memory, O is drained (128 arrivals)
+    uint64_t* bar_sd = bar_p + 1;                          // [2] the S accumulator has been read into registers (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_sd + 2);
 
     const int tid = threadIdx.x;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    // grid: split-KV (decode) = (splits, heads, batch); otherwise (heads, batch, query tiles) with the LAST query tile first:
+    // under a causal mask the late tiles see the most keys, so the long CTAs start first and the short ones fill the tail,
+    // and the CTAs running at the same time are the query heads of the same KV groups (their K / V tiles meet in L2)
     const int split = p.splits > 1 ? static_cast<int>(blockIdx.x) : 0;
-    const int q0 = p.splits > 1 ? 0 : blockIdx.x * kQTile;
-    const int head = blockIdx.y;
-    const int b = blockIdx.z;
+    const int q0 = p.splits > 1 ? 0 : static_cast<int>(gridDim.z - 1 - blockIdx.z) * kQTile;
+    const int head = p.splits > 1 ? blockIdx.y : blockIdx.x;
+    const int b = p.splits > 1 ? blockIdx.z : blockIdx.y;
     const int kvh = head / (p.heads / p.kv_heads);
 
     if (tid == 0) {
@@ -93,6 +105,8 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
         }
         mbar_init(bar_o, 1);
         mbar_init(bar_p, kQTile);
+        mbar_init(&bar_sd[0], kQTile);
+        mbar_init(&bar_sd[1], kQTile);
         fence_mbar_init();
     }
     constexpr uint32_t kTmemCols = 256u;                   // S[2] (2 x 64 columns) + P V (kD columns)
@@ -122,7 +136,8 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
         // The softmax warps never issue anything: the serial descriptor / tcgen05.mma stream of this thread is off their
         // critical path (measured: with the issuer inside softmax warp 0 the other warps spent a third of the kernel at the
         // CTA barrier waiting for it).
-        if (lane_id() == 0 && ntiles > 0) {
+        if (ntiles > 0 && elect_one()) {   // elect.sync: ptxas knows the branch is single-lane (a lane == 0 test makes it wrap every
+                                              // tcgen05.mma / TMA instruction in an ELECT ... BRA.U.ANY loop: ~140 clocks per MMA)
             // K tile, K-major: [64 keys][64 dims] per column block;  V tile: the same boxes, consumed as an MN-major B operand
             auto load_k = [&](int t) {
                 const int s = t & 1;
@@ -159,33 +174,50 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
             for (int a = 0; a < kDAtoms; ++a)
                 tma_load_2d(sq + a * (kQTile * 128), &p.map_q, bar_q, head * kD + a * 64, b * p.q_len + q0, kEvictNormal);
             load_k(0);
+            if (ntiles > 1) load_k(1);
             load_v(0);
-            if (ntiles > 1) {
-                load_k(1);
-                load_v(1);
-            }
+            if (ntiles > 1) load_v(1);
+            // S runs TWO tiles ahead of the softmax: the softmax warps read S of tile t + 1 into registers while they work on
+            // tile t (bar_sd fires right after P of tile t), so S of tile t + 3 is issued behind P V of tile t and S of tile
+            // t + 2 -- which the softmax asks for a few hundred clocks after P of tile t -- has been complete for a whole tile.
             mbar_wait(bar_q, 0);
             issue_s(0);
+            if (ntiles > 1) issue_s(1);
+            if (ntiles > 2) {                             // K stage 0 is free once S of tile 0 is complete
+                mbar_wait(&bar_s[0], 0);
+                load_k(2);
+            }
+            if (ntiles > 3) {
+                mbar_wait(&bar_s[1], 0);
+                load_k(3);
+            }
+            if (ntiles > 2) {                             // tile 0 is in registers before the softmax loop starts
+                mbar_wait(&bar_sd[0], 0);
+                issue_s(2);
+            }
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t & 1;
-                // S of tile t + 1 first (its accumulator was drained when bar_p of tile t - 1 completed, waited below in the
-                // previous turn), so the tensor cores have work while the softmax of tile t runs
-                if (t + 1 < ntiles) issue_s(t + 1);
-                if (t + 2 < ntiles) {                     // K stage t & 1 is free once S of tile t is complete
-                    mbar_wait(&bar_s[s], (t >> 1) & 1u);
-                    load_k(t + 2);
-                }
                 // O[128, kD] (+)= P[128, 64] V[64, kD]   (V consumed MN-major: [64 keys][kD]); tile 0 overwrites
                 mbar_wait(bar_p, t & 1u);
                 mbar_wait(&bar_v[s], (t >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(sv + s * kKBytes);
+#ifndef L32_ATT_NOPV
 #pragma unroll
                 for (int kk = 0; kk < kKvTile / kUmmaKAtt; ++kk)
                     umma_f16<1>(tmem_o, make_smem_desc_sw128(p_addr + kk * 32, 0, 1024),
                                 make_smem_desc_sw128(v_addr + kk * (kUmmaKAtt * 128), kKvTile * 128, 1024), p.idesc_o,
                                 (t > 0 || kk > 0) ? 1u : 0u);
+#endif
                 umma_commit<1>(bar_o);
+                if (t + 3 < ntiles) {                     // S of tile t + 3 into the accumulator tile t + 1 was read from
+                    mbar_wait(&bar_sd[s ^ 1], ((t + 1) >> 1) & 1u);
+                    issue_s(t + 3);
+                }
+                if (t + 4 < ntiles) {                     // K stage t & 1 is free once S of tile t + 2 is complete
+                    mbar_wait(&bar_s[s], ((t + 2) >> 1) & 1u);
+                    load_k(t + 4);
+                }
                 if (t + 2 < ntiles) {                     // V stage t & 1 is free once P V of tile t is complete
                     mbar_wait(bar_o, t & 1u);
                     load_v(t + 2);
@@ -205,88 +237,156 @@ __global__ void __launch_bounds__(kAttThreads) gqa_attention_kernel(const __grid
         float m_ref = -INFINITY, l = 0.f;
         const uint32_t lane_off = (warp * 32u) << 16;
         const uint8_t* keep_row = p.keep != nullptr ? p.keep + static_cast<size_t>(b) * p.kv_len : nullptr;
-        auto visible = [&](int key) {
-            bool ok = key < p.kv_len && (!p.causal || key <= qpos);
-            if (ok && keep_row != nullptr) ok = keep_row[key] != 0;
-            return ok;
-        };
 
-        for (int t = 0; t < ntiles; ++t) {
-            const int s = t & 1;
+        // One tile: `cur` holds the raw scores of tile t (read from TMEM during the previous tile); the scores of tile t + 1
+        // are requested into `nxt` before the exponentials of tile t are computed, so the TMEM read (64 B / clock / SM) and
+        // the wait for S hide behind the MUFU work.  The exponentials go to registers first: the previous tile's P V only has
+        // to be complete when P is stored and when the accumulator is rescaled.
+        auto process = [&](int t, uint32_t (&cur)[kKvTile], uint32_t (&nxt)[kKvTile]) {
             const int j0 = (tile0 + t) * kKvTile;
-            const uint32_t tmem_s = tmem_base + s * kKvTile;
-            mbar_wait(&bar_s[s], (t >> 1) & 1u);
-            tc_fence_after();
-            // ---- this row's 64 scores, scaled to the log2 domain; keys the row may not see become -inf.
             // A tile every key of which is visible needs no per-element predicates (all but the diagonal / last tiles).
             const bool full = (j0 + kKvTile <= p.kv_len) && (!p.causal || j0 + kKvTile - 1 <= qpos) && keep_row == nullptr;
-            float sc[kKvTile];
-            float tmax = -INFINITY;
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(tmem_s + lane_off + hf * 32, v);
-                tmem_ld_wait();
-                if (full) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        sc[hf * 32 + j] = __uint_as_float(v[j]) * p.scale_log2;
-                        tmax = fmaxf(tmax, sc[hf * 32 + j]);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        sc[hf * 32 + j] = visible(j0 + hf * 32 + j) ? __uint_as_float(v[j]) * p.scale_log2 : -INFINITY;
-                        tmax = fmaxf(tmax, sc[hf * 32 + j]);
+            if (!full) {
+                // keys [0, lim) of the tile pass the length / causal tests; the padding bytes are folded into a bit mask by a
+                // rolled loop (rare path, keeps the unrolled code small)
+                const int lim = min(p.kv_len, p.causal ? qpos + 1 : p.kv_len) - j0;
+                uint32_t vis_lo = lim >= 32 ? 0xffffffffu : (lim > 0 ? (1u << lim) - 1u : 0u);
+                uint32_t vis_hi = lim >= 64 ? 0xffffffffu : (lim > 32 ? (1u << (lim - 32)) - 1u : 0u);
+                if (keep_row != nullptr) {
+#pragma unroll 1
+                    for (int j = 0; j < kKvTile && j < lim; ++j) {
+                        if (keep_row[j0 + j] == 0) {
+                            if (j < 32) vis_lo &= ~(1u << j);
+                            else vis_hi &= ~(1u << (j - 32));
+                        }
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (!(vis_lo & (1u << j))) cur[j] = 0xff800000u;      // -inf
+                    if (!(vis_hi & (1u << j))) cur[32 + j] = 0xff800000u;
+                }
+            }
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int j = 0; j < kKvTile; j += 4) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) mx[q4] = fmaxf(mx[q4], __uint_as_float(cur[j + q4]));
+            }
+            const float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;   // scale > 0: max commutes with it
+            // tcgen05.ld / .st are warp-collective: the rescale is taken by the whole warp as soon as one of its rows needs a
+            // new reference; the other rows rescale by exactly 1
+            const bool want = tmax > m_ref + kLazyLog2;                   // also true for the first visible key (m_ref = -inf)
+            const bool any = __any_sync(0xffffffffu, want);
+            float alpha = 1.f;
+            if (any) {
+                alpha = want ? fast_exp2(m_ref - tmax) : 1.f;             // m_ref = -inf: 0
+                l *= alpha;
+                if (want) m_ref = tmax;
+            }
+            // next tile's scores: the first half is requested now, the second half once this tile's scores are dead (register
+            // pressure: 10 warps per SM on 4 schedulers = 3 warps on one 16 K register file, 168 registers per thread); both
+            // are awaited below
+            const uint32_t tmem_s_next = tmem_base + ((t + 1) & 1) * kKvTile + lane_off;
+            if (t + 1 < ntiles) {
+                mbar_wait(&bar_s[(t + 1) & 1], ((t + 1) >> 1) & 1u);
+                tc_fence_after();
+                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[0]);
+#ifndef L32_ATT_NOLD
+                tmem_ld_32x32b_x32(tmem_s_next, lo);
+#else
+#pragma unroll
+                for (int j = 0; j < 32; ++j) lo[j] = cur[j] + t;
+#endif
+            } else {                                  // (defined on every path: the old contents are dead for the compiler too)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) nxt[j] = 0u;
+            }
+            // ---- probabilities (registers).  A masked score is -inf: 2^(-inf * scale - m) = 0 as long as m is finite.  A row
+            // that has not seen a visible key yet has m_ref = -inf (and only -inf scores): its exponent reference is taken
+            // as 0 so that no nan appears.
+            float ps[4] = {0.f, 0.f, 0.f, 0.f};
+            const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+            uint8_t* prow = sp + tid * 128;         // P row, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of 16 B
+            uint32_t pk[kKvTile / 4];               // first half of the row: computed while the previous P V may still run
+#pragma unroll
+            for (int j = 0; j < kKvTile / 4; ++j) {
+                const float p0 = fast_exp2(fmaf(__uint_as_float(cur[2 * j]), p.scale_log2, neg_m));
+                const float p1 = fast_exp2(fmaf(__uint_as_float(cur[2 * j + 1]), p.scale_log2, neg_m));
+                pk[j] = Pack2<T>::pack(p0, p1);
+                ps[(2 * j) & 3] += p0;
+                ps[(2 * j + 1) & 3] += p1;
             }
             // ---- the previous tile's P V must be complete before P is overwritten and before the accumulator is touched
             if (t > 0) {
                 mbar_wait(bar_o, (t - 1) & 1u);
                 tc_fence_after();
-            }
-            // tcgen05.ld / .st are warp-collective: the branch is taken by the whole warp as soon as one of its rows needs a
-            // new reference; the other rows rescale by exactly 1
-            const bool want = tmax > m_ref + kLazyLog2;                   // also true for the first visible key (m_ref = -inf)
-            if (__any_sync(0xffffffffu, want)) {
-                const float alpha = want ? fast_exp2(m_ref - tmax) : 1.f;   // m_ref = -inf: 0
-                l *= alpha;
-                if (t > 0) {                                             // tile 0 overwrites the accumulator (no rescale needed)
+                if (any) {                                               // tile 0 overwrites the accumulator (no rescale needed)
 #pragma unroll
-                    for (int c = 0; c < kD / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(tmem_o + lane_off + c * 32, v);
+                    for (int c = 0; c < kD / 8; ++c) {                // rare path: small chunks keep its register need low
+                        uint32_t v[8];
+                        tmem_ld_32x32b_x8(tmem_o + lane_off + c * 8, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-                        tmem_st_32x32b_x32(tmem_o + lane_off + c * 32, v);
+                        for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+                        tmem_st_32x32b_x8(tmem_o + lane_off + c * 8, v);
                     }
                     tmem_st_wait();
                 }
-                if (want) m_ref = tmax;
             }
-            // ---- probabilities -> P in shared memory, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of 16 B
-            float psum = 0.f;
-            uint8_t* prow = sp + tid * 128;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint32_t pk[4];
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+#pragma unroll
+            for (int c = 4; c < 8; ++c) {
+                uint32_t q[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    // a dead row has m_ref = -inf and sc = -inf: -inf - -inf = nan, hence the guard
-                    const float a0 = sc[c * 8 + 2 * j], a1 = sc[c * 8 + 2 * j + 1];
-                    const float p0 = (a0 == -INFINITY) ? 0.f : fast_exp2(a0 - m_ref);
-                    const float p1 = (a1 == -INFINITY) ? 0.f : fast_exp2(a1 - m_ref);
-                    pk[j] = Pack2<T>::pack(p0, p1);
-                    psum += p0 + p1;
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(cur[c * 8 + 2 * j]), p.scale_log2, neg_m));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(cur[c * 8 + 2 * j + 1]), p.scale_log2, neg_m));
+                    q[j] = Pack2<T>::pack(p0, p1);
+                    ps[(2 * j) & 3] += p0;
+                    ps[(2 * j + 1) & 3] += p1;
                 }
-                *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(q[0], q[1], q[2], q[3]);
             }
-            l += psum;
+            l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+            if (t + 1 < ntiles) {
+                uint32_t (&hi32)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[32]);
+#ifndef L32_ATT_NOLD
+                tmem_ld_32x32b_x32(tmem_s_next + 32, hi32);
+#else
+#pragma unroll
+                for (int j = 0; j < 32; ++j) hi32[j] = cur[32 + j] + t;
+#endif
+            } else {
+#pragma unroll
+                for (int j = 32; j < kKvTile; ++j) nxt[j] = 0u;
+            }
             fence_proxy_async_smem();      // generic-proxy st.shared -> async-proxy (tensor core) reads
             tc_fence_before();             // this thread's tcgen05.ld / .st are ordered before the issuer's next tcgen05.mma
             mbar_arrive(bar_p);
+            if (t + 1 < ntiles) {
+                tmem_ld_wait();            // the next tile's scores are in registers: its accumulator may be overwritten
+                tc_fence_before();
+                mbar_arrive(&bar_sd[(t + 1) & 1]);
+            }
+        };
+        uint32_t sc_a[kKvTile], sc_b[kKvTile];
+        if (ntiles > 0) {
+            mbar_wait(&bar_s[0], 0);
+            tc_fence_after();
+            uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sc_a[0]);
+            uint32_t (&hi32)[32] = *reinterpret_cast<uint32_t (*)[32]>(&sc_a[32]);
+            tmem_ld_32x32b_x32(tmem_base + lane_off, lo);
+            tmem_ld_32x32b_x32(tmem_base + lane_off + 32, hi32);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bar_sd[0]);
+        }
+        for (int t = 0; t < ntiles; t += 2) {
+            process(t, sc_a, sc_b);
+            if (t + 1 < ntiles) process(t + 1, sc_b, sc_a);
         }
         if (ntiles > 0) {
             mbar_wait(bar_o, (ntiles - 1) & 1u);
@@ -434,17 +534,31 @@ __global__ void __launch_bounds__(256) rope_kv_append_kernel(T* q, const T* __re
 template <int kD, typename T>
 int launch_attention(const AttnParams& p, cudaStream_t s) {
     auto* kernel = gqa_attention_kernel<kD, T>;
-    constexpr size_t smem = kQTile * kD * 2 + 4 * kKvTile * kD * 2 + kQTile * kKvTile * 2 + 64;
+    size_t smem = kQTile * kD * 2 + 4 * kKvTile * kD * 2 + kQTile * kKvTile * 2 + 64;
+    if (const char* v = getenv("L32_ATT_ONE_CTA_PER_SM")) {   // experiments only: pad so that only one CTA fits per SM
+        if (*v == '1') smem = 160 * 1024;
+    }
     static bool configured_dev[kMaxDevices] = {};
     bool& configured = configured_dev[current_device_slot()];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return static_cast<int>(e);
         configured = true;
+        if (getenv("L32_ATT_DEBUG") != nullptr) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kAttThreads, smem);
+            cudaFuncAttributes fa;
+            cudaFuncGetAttributes(&fa, kernel);
+            fprintf(stderr, "[l32] gqa_attention_kernel<%d>: %d CTAs / SM, %d registers, %zu B local, %zu B dynamic smem\n", kD, nb,
+                    fa.numRegs, fa.localSizeBytes, smem);
+        }
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(p.splits > 1 ? p.splits : (p.q_len + kQTile - 1) / kQTile),
-                       static_cast<unsigned>(p.heads), static_cast<unsigned>(p.batch));
+    if (p.splits > 1)
+        cfg.gridDim = dim3(static_cast<unsigned>(p.splits), static_cast<unsigned>(p.heads), static_cast<unsigned>(p.batch));
+    else
+        cfg.gridDim = dim3(static_cast<unsigned>(p.heads), static_cast<unsigned>(p.batch),
+                           static_cast<unsigned>((p.q_len + kQTile - 1) / kQTile));
     cfg.blockDim = dim3(kAttThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
