@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_co
     pdl_launch_dependents();
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: single-lane branch the compiler can see (no ELECT / BRA.U.ANY loop per TMA / MMA)
             // ---------------------------------------------------------------- TMA producer: weights
             // (running stage / k-block counters: no integer divisions in the per-stage instruction stream)
             const int row0 = row_block * (kEpi == DEC_SWIGLU ? 64 : kRowsA);
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_co
             }
         }
     } else if (warp == 2) {
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: single-lane branch the compiler can see (no ELECT / BRA.U.ANY loop per TMA / MMA)
             // ---------------------------------------------------------------- TMA producer: token tiles (L2-resident)
             pdl_wait_prior_grid();                              // the activations are the previous kernel's output
             int s = 0, kr = rot;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_co
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {   // elect.sync: single-lane branch the compiler can see (no ELECT / BRA.U.ANY loop per TMA / MMA)
             // ---------------------------------------------------------------- MMA issuer
             // This one thread's instruction stream (waits, 4 x tcgen05.mma, commits per 16 KB of weights) paces the stage: the
             // shared-memory descriptors are built ONCE and advanced by adding to their 14-bit address field (>> 4 units;

@@ -364,7 +364,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // (elect.sync, not lane == 0: ptxas then knows the branch is single-lane and emits the TMA / tcgen05 instructions
+        //  back to back; behind a lane test it wraps each of them in an ELECT ... BRA.U.ANY loop, ~100 clocks apiece)
+        if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             for (int t = cluster_id; t < num_tiles; t += num_clusters) {
                 const TileCoord tc = get_tile(t);
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const __grid_constant
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (rank == 0 && lane == 0) {
+        if (rank == 0 && elect_one()) {
             const uint32_t a_kstep = p.a_mn_major ? (kUmmaK * 128) : (kUmmaK * 2);   // bytes per UMMA K step
             const uint32_t b_kstep = p.b_mn_major ? (kUmmaK * 128) : (kUmmaK * 2);
             const uint32_t a_lbo = p.a_mn_major ? kAtomBytes : 0;
