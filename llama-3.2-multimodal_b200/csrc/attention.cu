@@ -284,38 +284,41 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
                 l *= alpha;
                 if (want) m_ref = tmax;
             }
-            // next tile's scores: the first half is requested now, the second half once this tile's scores are dead (register
-            // pressure: 10 warps per SM on 4 schedulers = 3 warps on one 16 K register file, 168 registers per thread); both
-            // are awaited below
-            const uint32_t tmem_s_next = tmem_base + ((t + 1) & 1) * kKvTile + lane_off;
-            if (t + 1 < ntiles) {
-                mbar_wait(&bar_s[(t + 1) & 1], ((t + 1) >> 1) & 1u);
-                tc_fence_after();
-                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[0]);
-#ifndef L32_ATT_NOLD
-                tmem_ld_32x32b_x32(tmem_s_next, lo);
-#else
-#pragma unroll
-                for (int j = 0; j < 32; ++j) lo[j] = cur[j] + t;
-#endif
-            } else {                                  // (defined on every path: the old contents are dead for the compiler too)
-#pragma unroll
-                for (int j = 0; j < 32; ++j) nxt[j] = 0u;
-            }
-            // ---- probabilities (registers).  A masked score is -inf: 2^(-inf * scale - m) = 0 as long as m is finite.  A row
-            // that has not seen a visible key yet has m_ref = -inf (and only -inf scores): its exponent reference is taken
-            // as 0 so that no nan appears.
+            // ---- probabilities (registers): ALL the MUFU work of the tile comes before anything that depends on the previous
+            // tile's P V.  A masked score is -inf: 2^(-inf * scale - m) = 0 as long as m is finite.  A row that has not seen a
+            // visible key yet has m_ref = -inf (and only -inf scores): its exponent reference is taken as 0 so that no nan
+            // appears.
             float ps[4] = {0.f, 0.f, 0.f, 0.f};
             const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
             uint8_t* prow = sp + tid * 128;         // P row, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of 16 B
-            uint32_t pk[kKvTile / 4];               // first half of the row: computed while the previous P V may still run
+            uint32_t pk[kKvTile / 2];
 #pragma unroll
-            for (int j = 0; j < kKvTile / 4; ++j) {
+            for (int j = 0; j < kKvTile / 2; ++j) {
                 const float p0 = fast_exp2(fmaf(__uint_as_float(cur[2 * j]), p.scale_log2, neg_m));
                 const float p1 = fast_exp2(fmaf(__uint_as_float(cur[2 * j + 1]), p.scale_log2, neg_m));
                 pk[j] = Pack2<T>::pack(p0, p1);
                 ps[(2 * j) & 3] += p0;
                 ps[(2 * j + 1) & 3] += p1;
+            }
+            l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+            // ---- next tile's scores: requested once this tile's are dead (register pressure: 160 per thread with two CTAs per
+            // SM), awaited after P is handed over -- the TMEM read hides behind the P V wait, the P stores and the fences
+            if (t + 1 < ntiles) {
+                mbar_wait(&bar_s[(t + 1) & 1], ((t + 1) >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t tmem_s_next = tmem_base + ((t + 1) & 1) * kKvTile + lane_off;
+                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[0]);
+                uint32_t (&hi32)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[32]);
+#ifndef L32_ATT_NOLD
+                tmem_ld_32x32b_x32(tmem_s_next, lo);
+                tmem_ld_32x32b_x32(tmem_s_next + 32, hi32);
+#else
+#pragma unroll
+                for (int j = 0; j < kKvTile; ++j) nxt[j] = pk[j & 31] + t;
+#endif
+            } else {                                  // (defined on every path: the old contents are dead for the compiler too)
+#pragma unroll
+                for (int j = 0; j < kKvTile; ++j) nxt[j] = 0u;
             }
             // ---- the previous tile's P V must be complete before P is overwritten and before the accumulator is touched
             if (t > 0) {
@@ -335,34 +338,8 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 8; ++c)
                 *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-#pragma unroll
-            for (int c = 4; c < 8; ++c) {
-                uint32_t q[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(cur[c * 8 + 2 * j]), p.scale_log2, neg_m));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(cur[c * 8 + 2 * j + 1]), p.scale_log2, neg_m));
-                    q[j] = Pack2<T>::pack(p0, p1);
-                    ps[(2 * j) & 3] += p0;
-                    ps[(2 * j + 1) & 3] += p1;
-                }
-                *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(q[0], q[1], q[2], q[3]);
-            }
-            l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
-            if (t + 1 < ntiles) {
-                uint32_t (&hi32)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[32]);
-#ifndef L32_ATT_NOLD
-                tmem_ld_32x32b_x32(tmem_s_next + 32, hi32);
-#else
-#pragma unroll
-                for (int j = 0; j < 32; ++j) hi32[j] = cur[32 + j] + t;
-#endif
-            } else {
-#pragma unroll
-                for (int j = 32; j < kKvTile; ++j) nxt[j] = 0u;
-            }
             fence_proxy_async_smem();      // generic-proxy st.shared -> async-proxy (tensor core) reads
             tc_fence_before();             // this thread's tcgen05.ld / .st are ordered before the issuer's next tcgen05.mma
             mbar_arrive(bar_p);
@@ -386,7 +363,12 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
         }
         for (int t = 0; t < ntiles; t += 2) {
             process(t, sc_a, sc_b);
-            if (t + 1 < ntiles) process(t + 1, sc_b, sc_a);
+            if (t + 1 < ntiles) {
+                process(t + 1, sc_b, sc_a);
+            } else {                                  // (dead values: tells the compiler sc_a is not live across tile t)
+#pragma unroll
+                for (int j = 0; j < kKvTile; ++j) sc_a[j] = 0u;
+            }
         }
         if (ntiles > 0) {
             mbar_wait(bar_o, (ntiles - 1) & 1u);
