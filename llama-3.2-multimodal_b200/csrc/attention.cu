@@ -288,6 +288,16 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
             // tile's P V.  A masked score is -inf: 2^(-inf * scale - m) = 0 as long as m is finite.  A row that has not seen a
             // visible key yet has m_ref = -inf (and only -inf scores): its exponent reference is taken as 0 so that no nan
             // appears.
+            const uint32_t tmem_s_next = tmem_base + ((t + 1) & 1) * kKvTile + lane_off;
+            if (t + 1 < ntiles) {
+                mbar_wait(&bar_s[(t + 1) & 1], ((t + 1) >> 1) & 1u);
+                tc_fence_after();
+                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[0]);
+                tmem_ld_32x32b_x32(tmem_s_next, lo);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) nxt[j] = 0u;
+            }
             float ps[4] = {0.f, 0.f, 0.f, 0.f};
             const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
             uint8_t* prow = sp + tid * 128;         // P row, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of 16 B
@@ -304,21 +314,11 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
             // ---- next tile's scores: requested once this tile's are dead (register pressure: 160 per thread with two CTAs per
             // SM), awaited after P is handed over -- the TMEM read hides behind the P V wait, the P stores and the fences
             if (t + 1 < ntiles) {
-                mbar_wait(&bar_s[(t + 1) & 1], ((t + 1) >> 1) & 1u);
-                tc_fence_after();
-                const uint32_t tmem_s_next = tmem_base + ((t + 1) & 1) * kKvTile + lane_off;
-                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[0]);
                 uint32_t (&hi32)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[32]);
-#ifndef L32_ATT_NOLD
-                tmem_ld_32x32b_x32(tmem_s_next, lo);
                 tmem_ld_32x32b_x32(tmem_s_next + 32, hi32);
-#else
+            } else {
 #pragma unroll
-                for (int j = 0; j < kKvTile; ++j) nxt[j] = pk[j & 31] + t;
-#endif
-            } else {                                  // (defined on every path: the old contents are dead for the compiler too)
-#pragma unroll
-                for (int j = 0; j < kKvTile; ++j) nxt[j] = 0u;
+                for (int j = 32; j < kKvTile; ++j) nxt[j] = 0u;
             }
             // ---- the previous tile's P V must be complete before P is overwritten and before the accumulator is touched
             if (t > 0) {
