@@ -63,7 +63,6 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
     constexpr int kDAtoms = kD / 64;                       // 64-element (128-byte) column blocks of a head
     constexpr int kQBytes = kQTile * kD * 2;
     constexpr int kKBytes = kKvTile * kD * 2;              // also the V tile
-    constexpr int kPBytes = kQTile * kKvTile * 2;
     // 128-byte-swizzled tiles need 1024-byte alignment; the kernel has no static shared memory, so the dynamic window
     // starts aligned (checked: a misaligned base traps instead of corrupting tiles)
     extern __shared__ __align__(1024) uint8_t att_smem[];
@@ -71,16 +70,18 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
     uint8_t* sq = att_smem;
     uint8_t* sk = sq + kQBytes;                            // 2 stages
     uint8_t* sv = sk + 2 * kKBytes;                        // 2 stages
-    uint8_t* sp = sv + 2 * kKBytes;
-    uint64_t* bar_q = reinterpret_cast<uint64_t*>(sp + kPBytes);
+    uint64_t* bar_q = reinterpret_cast<uint64_t*>(sv + 2 * kKBytes);
     uint64_t* bar_k = bar_q + 1;                           // [2] K tile landed
     uint64_t* bar_v = bar_k + 2;                           // [2] V tile landed
     uint64_t* bar_s = bar_v + 2;                           // [2] S = Q K^T complete (two accumulators: S of tile t + 1 runs
                                                            //     on the tensor cores while the softmax of tile t is computed)
     uint64_t* bar_o = bar_s + 2;                           // P V complete (P and the V stage may be reused)
-    uint64_t* bar_p = bar_o + 1;                           // P of the tile is in shared memory, O is drained (128 arrivals)
-    uint64_t* bar_sd = bar_p + 1;                          // [2] the S accumulator has been read into registers (128 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_sd + 2);
+    uint64_t* bar_p = bar_o + 1;                           // [2] P of the tile is in tensor memory (128 arrivals).  Two, used
+                                                           //     alternately: a warp whose rows are all masked can finish tile
+                                                           //     t + 1 before a slow warp has handed over tile t (nothing makes
+                                                           //     it wait for the previous P V any more), and must not arrive
+                                                           //     on the phase of tile t a second time
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_p + 2);
 
     const int tid = threadIdx.x;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -104,9 +105,8 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
             mbar_init(&bar_s[i], 1);
         }
         mbar_init(bar_o, 1);
-        mbar_init(bar_p, kQTile);
-        mbar_init(&bar_sd[0], kQTile);
-        mbar_init(&bar_sd[1], kQTile);
+        mbar_init(&bar_p[0], kQTile);
+        mbar_init(&bar_p[1], kQTile);
         fence_mbar_init();
     }
     constexpr uint32_t kTmemCols = 256u;                   // S[2] (2 x 64 columns) + P V (kD columns)
@@ -154,7 +154,7 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
                     tma_load_2d(sv + s * kKBytes + a * (kKvTile * 128), &p.map_v, &bar_v[s], a * 64, kv_row0 + t * kKvTile, kEvictNormal);
             };
             // S[128, 64] = Q[128, kD] K[64, kD]^T of tile t into accumulator t & 1
-            const uint32_t q_addr = smem_u32(sq), p_addr = smem_u32(sp);
+            const uint32_t q_addr = smem_u32(sq);
             auto issue_s = [&](int t) {
                 const int s = t & 1;
                 mbar_wait(&bar_k[s], (t >> 1) & 1u);
@@ -177,9 +177,10 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
             if (ntiles > 1) load_k(1);
             load_v(0);
             if (ntiles > 1) load_v(1);
-            // S runs TWO tiles ahead of the softmax: the softmax warps read S of tile t + 1 into registers while they work on
-            // tile t (bar_sd fires right after P of tile t), so S of tile t + 3 is issued behind P V of tile t and S of tile
-            // t + 2 -- which the softmax asks for a few hundred clocks after P of tile t -- has been complete for a whole tile.
+            // P (16-bit) is written by the softmax warps over the first 32 columns of the S accumulator it was computed from,
+            // and P V takes it from there (A operand in tensor memory): no shared-memory P tile, no generic -> async proxy
+            // fence.  The tensor pipe executes in issue order, so S of tile t + 2 -- issued right behind P V of tile t --
+            // overwrites that accumulator only after P V has read P from it.
             mbar_wait(bar_q, 0);
             issue_s(0);
             if (ntiles > 1) issue_s(1);
@@ -187,36 +188,26 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
                 mbar_wait(&bar_s[0], 0);
                 load_k(2);
             }
-            if (ntiles > 3) {
-                mbar_wait(&bar_s[1], 0);
-                load_k(3);
-            }
-            if (ntiles > 2) {                             // tile 0 is in registers before the softmax loop starts
-                mbar_wait(&bar_sd[0], 0);
-                issue_s(2);
-            }
             for (int t = 0; t < ntiles; ++t) {
                 const int s = t & 1;
                 // O[128, kD] (+)= P[128, 64] V[64, kD]   (V consumed MN-major: [64 keys][kD]); tile 0 overwrites
-                mbar_wait(bar_p, t & 1u);
+                mbar_wait(&bar_p[s], (t >> 1) & 1u);
                 mbar_wait(&bar_v[s], (t >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(sv + s * kKBytes);
+                const uint32_t p_tmem = tmem_base + s * kKvTile;
 #ifndef L32_ATT_NOPV
 #pragma unroll
                 for (int kk = 0; kk < kKvTile / kUmmaKAtt; ++kk)
-                    umma_f16<1>(tmem_o, make_smem_desc_sw128(p_addr + kk * 32, 0, 1024),
+                    umma_f16_ts(tmem_o, p_tmem + kk * (kUmmaKAtt / 2),
                                 make_smem_desc_sw128(v_addr + kk * (kUmmaKAtt * 128), kKvTile * 128, 1024), p.idesc_o,
                                 (t > 0 || kk > 0) ? 1u : 0u);
 #endif
                 umma_commit<1>(bar_o);
-                if (t + 3 < ntiles) {                     // S of tile t + 3 into the accumulator tile t + 1 was read from
-                    mbar_wait(&bar_sd[s ^ 1], ((t + 1) >> 1) & 1u);
-                    issue_s(t + 3);
-                }
-                if (t + 4 < ntiles) {                     // K stage t & 1 is free once S of tile t + 2 is complete
-                    mbar_wait(&bar_s[s], ((t + 2) >> 1) & 1u);
-                    load_k(t + 4);
+                if (t + 2 < ntiles) issue_s(t + 2);       // (K of tile t + 2 was requested a tile ago)
+                if (t + 3 < ntiles) {                     // K stage (t + 1) & 1 is free once S of tile t + 1 is complete
+                    mbar_wait(&bar_s[s ^ 1], ((t + 1) >> 1) & 1u);
+                    load_k(t + 3);
                 }
                 if (t + 2 < ntiles) {                     // V stage t & 1 is free once P V of tile t is complete
                     mbar_wait(bar_o, t & 1u);
@@ -288,19 +279,8 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
             // tile's P V.  A masked score is -inf: 2^(-inf * scale - m) = 0 as long as m is finite.  A row that has not seen a
             // visible key yet has m_ref = -inf (and only -inf scores): its exponent reference is taken as 0 so that no nan
             // appears.
-            const uint32_t tmem_s_next = tmem_base + ((t + 1) & 1) * kKvTile + lane_off;
-            if (t + 1 < ntiles) {
-                mbar_wait(&bar_s[(t + 1) & 1], ((t + 1) >> 1) & 1u);
-                tc_fence_after();
-                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[0]);
-                tmem_ld_32x32b_x32(tmem_s_next, lo);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) nxt[j] = 0u;
-            }
             float ps[4] = {0.f, 0.f, 0.f, 0.f};
             const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
-            uint8_t* prow = sp + tid * 128;         // P row, K-major with the 128-byte swizzle (A operand of P V): 8 chunks of 16 B
             uint32_t pk[kKvTile / 2];
 #pragma unroll
             for (int j = 0; j < kKvTile / 2; ++j) {
@@ -311,43 +291,53 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
                 ps[(2 * j + 1) & 3] += p1;
             }
             l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
-            // ---- next tile's scores: requested once this tile's are dead (register pressure: 160 per thread with two CTAs per
-            // SM), awaited after P is handed over -- the TMEM read hides behind the P V wait, the P stores and the fences
+            // ---- next tile's scores: S of tile t + 1 was issued behind P V of tile t - 1 and has had the whole exponential
+            // phase to complete; the read is awaited after P is handed over
             if (t + 1 < ntiles) {
+                mbar_wait(&bar_s[(t + 1) & 1], ((t + 1) >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t tmem_s_next = tmem_base + ((t + 1) & 1) * kKvTile + lane_off;
+                uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[0]);
                 uint32_t (&hi32)[32] = *reinterpret_cast<uint32_t (*)[32]>(&nxt[32]);
+                tmem_ld_32x32b_x32(tmem_s_next, lo);
                 tmem_ld_32x32b_x32(tmem_s_next + 32, hi32);
-            } else {
+            } else {                                  // (defined on every path: the old contents are dead for the compiler too)
 #pragma unroll
-                for (int j = 32; j < kKvTile; ++j) nxt[j] = 0u;
+                for (int j = 0; j < kKvTile; ++j) nxt[j] = 0u;
             }
-            // ---- the previous tile's P V must be complete before P is overwritten and before the accumulator is touched
-            if (t > 0) {
+            // ---- the accumulator is touched only when a row of this warp needs a new reference (rare after the first
+            // tiles): only then does the previous tile's P V have to be complete here
+            if (t > 0 && any) {
                 mbar_wait(bar_o, (t - 1) & 1u);
                 tc_fence_after();
-                if (any) {                                               // tile 0 overwrites the accumulator (no rescale needed)
 #pragma unroll
-                    for (int c = 0; c < kD / 8; ++c) {                // rare path: small chunks keep its register need low
-                        uint32_t v[8];
-                        tmem_ld_32x32b_x8(tmem_o + lane_off + c * 8, v);
-                        tmem_ld_wait();
+                for (int c = 0; c < kD / 8; ++c) {                    // small chunks keep the register need of the rare path low
+                    uint32_t v[8];
+                    tmem_ld_32x32b_x8(tmem_o + lane_off + c * 8, v);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-                        tmem_st_32x32b_x8(tmem_o + lane_off + c * 8, v);
-                    }
-                    tmem_st_wait();
+                    for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+                    tmem_st_32x32b_x8(tmem_o + lane_off + c * 8, v);
                 }
             }
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-            fence_proxy_async_smem();      // generic-proxy st.shared -> async-proxy (tensor core) reads
-            tc_fence_before();             // this thread's tcgen05.ld / .st are ordered before the issuer's next tcgen05.mma
-            mbar_arrive(bar_p);
-            if (t + 1 < ntiles) {
-                tmem_ld_wait();            // the next tile's scores are in registers: its accumulator may be overwritten
-                tc_fence_before();
-                mbar_arrive(&bar_sd[(t + 1) & 1]);
+            // ---- P -> tensor memory, over the first 32 columns of the accumulator S of this tile came from (this thread's
+            // lane; it read those columns into registers a tile ago): the A operand of P V
+            {
+                const uint32_t tmem_p = tmem_base + (t & 1) * kKvTile + lane_off;
+                uint32_t (&p_lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[0]);
+                uint32_t (&p_hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[16]);
+                tmem_st_32x32b_x16(tmem_p, p_lo);
+                tmem_st_32x32b_x16(tmem_p + 16, p_hi);
             }
+            tmem_st_wait();
+            // Every thread watches EVERY phase of bar_o (a parity wait can only tell the current phase from the previous one:
+            // a thread that skipped a phase would take "tile t - 2 complete" for "tile t complete", or hang on a parity that
+            // has come round again).  Here P V of tile t - 1 has had the whole tile to finish, and P V of tile t cannot have
+            // been issued yet (this thread has not arrived), so the wait is free and unambiguous.
+            if (t > 0 && !any) mbar_wait(bar_o, (t - 1) & 1u);
+            tc_fence_before();             // this thread's tcgen05.ld / .st are ordered before the issuer's next tcgen05.mma
+            mbar_arrive(&bar_p[t & 1]);
+            if (t + 1 < ntiles) tmem_ld_wait();    // the next tile's scores are in registers
         };
         uint32_t sc_a[kKvTile], sc_b[kKvTile];
         if (ntiles > 0) {
@@ -358,8 +348,6 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
             tmem_ld_32x32b_x32(tmem_base + lane_off, lo);
             tmem_ld_32x32b_x32(tmem_base + lane_off + 32, hi32);
             tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&bar_sd[0]);
         }
         for (int t = 0; t < ntiles; t += 2) {
             process(t, sc_a, sc_b);
@@ -516,7 +504,7 @@ __global__ void __launch_bounds__(256) rope_kv_append_kernel(T* q, const T* __re
 template <int kD, typename T>
 int launch_attention(const AttnParams& p, cudaStream_t s) {
     auto* kernel = gqa_attention_kernel<kD, T>;
-    size_t smem = kQTile * kD * 2 + 4 * kKvTile * kD * 2 + kQTile * kKvTile * 2 + 64;
+    size_t smem = kQTile * kD * 2 + 4 * kKvTile * kD * 2 + 128;   // tiles + barriers
     if (const char* v = getenv("L32_ATT_ONE_CTA_PER_SM")) {   // experiments only: pad so that only one CTA fits per SM
         if (*v == '1') smem = 160 * 1024;
     }

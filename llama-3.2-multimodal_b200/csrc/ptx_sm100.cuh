@@ -269,6 +269,18 @@ L32_DEVICE void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint
             "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
             : "memory");
 }
+// Same with the A operand in TENSOR MEMORY (lane = row of D, 16-bit elements packed two per 32-bit column, K-major):
+// D[tmem] (+)= A[tmem] * B[smem desc].
+L32_DEVICE void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Make an mbarrier track completion of all prior tcgen05.mma of this thread.
 // cta_group::2 : arrives on the barrier at this smem offset in BOTH CTAs of the pair.
 template <int kCtaGroup>

@@ -820,6 +820,37 @@ def test_attention_vs_reference_outputs(tag):
     close(cache.value_cache[0], g["cache_v"], FWD, "cache values")
 
 
+@pytest.mark.parametrize("b,t,heads,kv,d,causal,pad", [(1, 128, 1, 1, 128, True, 0), (1, 128, 1, 1, 128, True, 5), (1, 128, 1, 1, 128, True, 37),
+                                                       (1, 128, 1, 1, 128, True, 64), (1, 128, 1, 1, 128, True, 70),
+                                                       (2, 300, 4, 2, 128, True, 37), (2, 300, 4, 2, 64, True, 37),
+                                                       (2, 512, 8, 2, 128, False, 0), (1, 2048, 8, 2, 128, True, 100)])
+def test_attention_kernel_key_padding_and_warp_skew(b, t, heads, kv, d, causal, pad):
+    """The attention kernel alone (l32_gqa_attention_forward) with a key-padding vector against the softmax written out in
+    fp32.  With padding bytes the four softmax warps of a CTA take very different times per tile (a warp whose rows see no key
+    of a tile skips the mask loop), which is what exposes ordering mistakes between the warps, the MMA issuer and the
+    barriers' phases: left padding shorter / longer than a warp, a whole key tile, and more than a tile; dead rows must give
+    exact zeros."""
+    from llama32_b200 import ops
+    gen = torch.Generator().manual_seed(b * 131 + t + pad)
+    rep = lambda v: v.to(torch.bfloat16).float()
+    q, k, v = rep(torch.randn(b, t, heads * d, generator=gen)), rep(torch.randn(b, kv, t + 8, d, generator=gen)), rep(torch.randn(b, kv, t + 8, d, generator=gen))
+    keep = torch.ones(b, t, dtype=torch.uint8)
+    keep[0, :pad] = 0
+    y = ops.gqa_attention_forward(dev(q), dev(k), dev(v), t, 0, causal=causal, key_keep=keep.to(DEV))
+    q4 = q.view(b, t, heads, d).transpose(1, 2)
+    k4, v4 = k[:, :, :t].repeat_interleave(heads // kv, 1), v[:, :, :t].repeat_interleave(heads // kv, 1)
+    sc = q4 @ k4.transpose(-1, -2) / d ** 0.5
+    m = torch.ones(t, t, dtype=torch.bool)
+    if causal:
+        m &= torch.arange(t)[None] <= torch.arange(t)[:, None]
+    m = m[None, None] & keep[:, None, None, :].bool()
+    pr = torch.nan_to_num(torch.softmax(sc.masked_fill(~m, float("-inf")), -1), nan=0.0)     # a row without keys: zeros
+    ref = (pr @ v4).transpose(1, 2).reshape(b, t, heads * d)
+    close(y, ref, FWD, "attention with key padding")
+    dead = ~m.any(-1)[:, 0]                                                       # [b, t]: rows that see no key at all
+    assert (y.float().cpu()[dead] == 0).all(), "rows without any visible key must be exact zeros"
+
+
 @pytest.mark.parametrize("b,t,hidden,heads,kv,steps", [(2, 300, 1024, 8, 2, 3), (1, 512, 4096, 32, 8, 2), (3, 129, 512, 8, 8, 1),
                                                      (2, 64, 256, 4, 1, 2)])
 def test_attention_shapes_vs_oracle(b, t, hidden, heads, kv, steps):
