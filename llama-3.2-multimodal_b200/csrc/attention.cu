@@ -53,7 +53,7 @@ L32_DEVICE float fast_exp2(float x) {
     return x * 0.001f;
 #else
     float y;
-    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // not volatile: a pure function the scheduler may interleave freely
     return y;
 #endif
 }
