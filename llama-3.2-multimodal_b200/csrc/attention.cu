@@ -58,6 +58,29 @@ L32_DEVICE float fast_exp2(float x) {
 #endif
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2): half the FMA-pipe instructions of the exponent arguments and the row sums.
+L32_DEVICE uint64_t pack_f32x2(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+L32_DEVICE void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+    uint32_t a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+    lo = __uint_as_float(a);
+    hi = __uint_as_float(b);
+}
+L32_DEVICE uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+L32_DEVICE uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 template <int kD, typename T>
 __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ AttnParams p) {
     constexpr int kDAtoms = kD / 64;                       // 64-element (128-byte) column blocks of a head
@@ -279,18 +302,25 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
             // tile's P V.  A masked score is -inf: 2^(-inf * scale - m) = 0 as long as m is finite.  A row that has not seen a
             // visible key yet has m_ref = -inf (and only -inf scores): its exponent reference is taken as 0 so that no nan
             // appears.
-            float ps[4] = {0.f, 0.f, 0.f, 0.f};
             const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+            const uint64_t scale2 = pack_f32x2(__float_as_uint(p.scale_log2), __float_as_uint(p.scale_log2));
+            const uint64_t neg_m2 = pack_f32x2(__float_as_uint(neg_m), __float_as_uint(neg_m));
+            uint64_t ps2[2] = {0ull, 0ull};         // four independent row-sum chains, two per packed accumulator
             uint32_t pk[kKvTile / 2];
 #pragma unroll
             for (int j = 0; j < kKvTile / 2; ++j) {
-                const float p0 = fast_exp2(fmaf(__uint_as_float(cur[2 * j]), p.scale_log2, neg_m));
-                const float p1 = fast_exp2(fmaf(__uint_as_float(cur[2 * j + 1]), p.scale_log2, neg_m));
+                float x0, x1;
+                unpack_f32x2(fma_f32x2(pack_f32x2(cur[2 * j], cur[2 * j + 1]), scale2, neg_m2), x0, x1);
+                const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
                 pk[j] = Pack2<T>::pack(p0, p1);
-                ps[(2 * j) & 3] += p0;
-                ps[(2 * j + 1) & 3] += p1;
+                ps2[j & 1] = add_f32x2(ps2[j & 1], pack_f32x2(__float_as_uint(p0), __float_as_uint(p1)));
             }
-            l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+            {
+                float s0, s1, s2, s3;
+                unpack_f32x2(ps2[0], s0, s1);
+                unpack_f32x2(ps2[1], s2, s3);
+                l += (s0 + s1) + (s2 + s3);
+            }
             // ---- next tile's scores: S of tile t + 1 was issued behind P V of tile t - 1 and has had the whole exponential
             // phase to complete; the read is awaited after P is handed over
             if (t + 1 < ntiles) {
