@@ -3,7 +3,7 @@ import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 if len(sys.argv) == 1:
-    settings = [{}]
+    settings = [{}, {"L32_DECODE_THREADS": "128"}, {"L32_DECODE_XSTAGES": "4", "L32_DECODE_STAGES": "5"}, {"L32_DECODE_DEBUG_NOX": "1"}]
     for st in settings:
         subprocess.run([sys.executable, __file__, "run", repr(st)], env={**os.environ, **st})
     sys.exit(0)
