@@ -11,7 +11,11 @@ OUT=gpurun_out
 TAG=${TAG:-r2}
 LIB=llama-3.2-multimodal_b200/libl32ffn.so
 DIGEST=$(sha256sum $LIB | cut -c1-16)
-echo "lib_sha256_16=$DIGEST  $(date -u +%FT%TZ)  $(nvidia-smi --query-gpu=name,driver_version --format=csv,noheader)" > $OUT/${TAG}_digest.txt
+# the .so hash changes from build to build of the SAME sources (nvcc's anonymous-namespace mangling); the source digest
+# (llama-3.2-multimodal_b200/build.py: sha256 over csrc/*.cu, the headers and the flags) is the reproducible one
+SRC=$(cut -c1-16 llama-3.2-multimodal_b200/_build/digest.txt 2>/dev/null)
+echo "src_sha256_16=$SRC" > $OUT/${TAG}_src_digest.txt
+echo "lib_sha256_16=$DIGEST  src_sha256_16=$SRC  $(date -u +%FT%TZ)  $(nvidia-smi --query-gpu=name,driver_version --format=csv,noheader)" > $OUT/${TAG}_digest.txt
 NCU="ncu --clock-control none"
 full() {   # name, kernel regex, skip, count, target args...
   local name=$1 regex=$2 skip=$3 count=$4; shift 4
@@ -20,7 +24,7 @@ full() {   # name, kernel regex, skip, count, target args...
       python scripts/profile_targets.py "$@" > $OUT/${TAG}_ncu_$name.log 2>&1
     echo "$name: ncu rc=$?" >> $OUT/${TAG}_digest.txt
     # summarise on the box (gpurun_out/ may carry at most 64 MiB back) and drop the raw report unless asked to keep it
-    python scripts/ncu_summary.py $OUT/${TAG}_full_$name.ncu-rep "lib_sha256_16=$DIGEST; ncu --set full --clock-control none --import-source on; python scripts/profile_targets.py $*; $(date -u +%F)" > $OUT/${TAG}_ncu_full_$name.txt 2>/dev/null
+    python scripts/ncu_summary.py $OUT/${TAG}_full_$name.ncu-rep "lib_sha256_16=$DIGEST src_sha256_16=$SRC; ncu --set full --clock-control none --import-source on; python scripts/profile_targets.py $*; $(date -u +%F)" > $OUT/${TAG}_ncu_full_$name.txt 2>/dev/null
     if [ "${KEEP_REP:-0}" = 0 ]; then rm -f $OUT/${TAG}_full_$name.ncu-rep; fi
   else
     echo "$name: plain run FAILED, not profiled" >> $OUT/${TAG}_digest.txt
