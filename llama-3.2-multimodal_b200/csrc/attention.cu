@@ -485,49 +485,82 @@ __global__ void __launch_bounds__(128) attention_combine_kernel(const float* __r
     }
 }
 
-// RoPE + cache append.  One thread handles one (token, head, pair index i < head_dim / 2): the rotate_half form
+// RoPE + cache append, the rotate_half form
 //   out[i] = x[i] cos - x[i + d/2] sin,  out[i + d/2] = x[i + d/2] cos + x[i] sin,  angle = position * base^(-2 i / d)
 // (reference Model/model.py:188-198; cos / sin in fp32 instead of the reference's storage-dtype cos / sin).
+// One CTA per token.  The d / 2 angles of the token are computed ONCE (the first d / 2 threads, fp32 sincosf) and shared by
+// its heads + 2 kv_heads head rows through shared memory; every thread then moves 16-byte vectors: thread (slot, j) takes
+// elements [8 j, 8 j + 8) of both halves of the head rows slot, slot + 16, ... (q heads rotated in place, k heads rotated
+// into the cache, v heads copied into the cache).
 template <typename T>
-__global__ void __launch_bounds__(256) rope_kv_append_kernel(T* q, const T* __restrict__ k_new, const T* __restrict__ v_new,
+__global__ void __launch_bounds__(128) rope_kv_append_kernel(T* q, const T* __restrict__ k_new, const T* __restrict__ v_new,
                                                             const long long* __restrict__ position_ids, T* cache_k, T* cache_v,
-                                                            int batch, int q_len, int heads, int kv_heads, int d, int max_len,
+                                                            int q_len, int heads, int kv_heads, int d, int max_len,
                                                             int past_len, float log2_base) {
+    __shared__ float cs_sh[64], sn_sh[64];             // d / 2 <= 64
     pdl_wait_prior_grid();
     const int half = d >> 1;
-    const int per_tok = (heads + 2 * kv_heads) * half;
-    const long long total = static_cast<long long>(batch) * q_len * per_tok;
-    for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
-        const int i = static_cast<int>(idx % half);
-        const int hh = static_cast<int>((idx / half) % (heads + 2 * kv_heads));
-        const long long tok = idx / per_tok;                 // b * q_len + t
-        const int t = static_cast<int>(tok % q_len);
-        const int b = static_cast<int>(tok / q_len);
-        if (hh >= heads + kv_heads) {                        // value head: plain copy into the cache
-            const int h = hh - heads - kv_heads;
-            const T* src = v_new + (tok * kv_heads + h) * d;
-            T* dst = cache_v + ((static_cast<long long>(b) * kv_heads + h) * max_len + past_len + t) * d;
-            dst[i] = src[i];
-            dst[i + half] = src[i + half];
-            continue;
-        }
+    const long long tok = blockIdx.x;                    // b * q_len + t
+    const int t = static_cast<int>(tok % q_len);
+    const int b = static_cast<int>(tok / q_len);
+    if (static_cast<int>(threadIdx.x) < half) {
+        const int i = threadIdx.x;
         const float pos = static_cast<float>(position_ids[tok]);
         const float inv_freq = exp2f(-log2_base * (2.0f * static_cast<float>(i) / static_cast<float>(d)));
         float sn, cs;
         sincosf(pos * inv_freq, &sn, &cs);
-        if (hh < heads) {
-            T* x = q + (tok * heads + hh) * d;
-            const float a = static_cast<float>(x[i]), c = static_cast<float>(x[i + half]);
-            x[i] = static_cast<T>(a * cs - c * sn);
-            x[i + half] = static_cast<T>(c * cs + a * sn);
+        cs_sh[i] = cs;
+        sn_sh[i] = sn;
+    }
+    __syncthreads();
+    const int vph = d >> 4;                              // 16-byte vectors per half row
+    const int j = threadIdx.x % vph;
+    const int slot = threadIdx.x / vph;                  // 0 .. 15
+    float cs[8], sn[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        cs[e] = cs_sh[8 * j + e];
+        sn[e] = sn_sh[8 * j + e];
+    }
+    const int units = heads + 2 * kv_heads;
+    for (int u = slot; u < units; u += 16) {
+        const T* src;
+        T* dst;
+        bool rotate = true;
+        if (u < heads) {
+            T* x = q + (tok * heads + u) * d;
+            src = x;
+            dst = x;
+        } else if (u < heads + kv_heads) {
+            const int h = u - heads;
+            src = k_new + (tok * kv_heads + h) * d;
+            dst = cache_k + ((static_cast<long long>(b) * kv_heads + h) * max_len + past_len + t) * d;
         } else {
-            const int h = hh - heads;
-            const T* x = k_new + (tok * kv_heads + h) * d;
-            T* dst = cache_k + ((static_cast<long long>(b) * kv_heads + h) * max_len + past_len + t) * d;
-            const float a = static_cast<float>(x[i]), c = static_cast<float>(x[i + half]);
-            dst[i] = static_cast<T>(a * cs - c * sn);
-            dst[i + half] = static_cast<T>(c * cs + a * sn);
+            const int h = u - heads - kv_heads;
+            src = v_new + (tok * kv_heads + h) * d;
+            dst = cache_v + ((static_cast<long long>(b) * kv_heads + h) * max_len + past_len + t) * d;
+            rotate = false;
         }
+        const uint4 lo = *reinterpret_cast<const uint4*>(src + 8 * j);
+        const uint4 hi = *reinterpret_cast<const uint4*>(src + half + 8 * j);
+        if (!rotate) {
+            *reinterpret_cast<uint4*>(dst + 8 * j) = lo;
+            *reinterpret_cast<uint4*>(dst + half + 8 * j) = hi;
+            continue;
+        }
+        const T* a = reinterpret_cast<const T*>(&lo);
+        const T* c = reinterpret_cast<const T*>(&hi);
+        uint4 olo, ohi;
+        T* oa = reinterpret_cast<T*>(&olo);
+        T* oc = reinterpret_cast<T*>(&ohi);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float av = static_cast<float>(a[e]), cv = static_cast<float>(c[e]);
+            oa[e] = static_cast<T>(av * cs[e] - cv * sn[e]);
+            oc[e] = static_cast<T>(cv * cs[e] + av * sn[e]);
+        }
+        *reinterpret_cast<uint4*>(dst + 8 * j) = olo;
+        *reinterpret_cast<uint4*>(dst + half + 8 * j) = ohi;
     }
 }
 
@@ -583,14 +616,15 @@ int gqa_attention_launch(const void* q, const void* cache_k, const void* cache_v
 int rope_kv_append(void* q, const void* k_new, const void* v_new, const long long* position_ids, void* cache_k, void* cache_v,
                    int batch, int q_len, int heads, int kv_heads, int head_dim, int max_len, int past_len, float rope_base,
                    int dtype, cudaStream_t s) {
-    const long long total = static_cast<long long>(batch) * q_len * (heads + 2 * kv_heads) * (head_dim / 2);
-    if (total == 0) return L32_OK;
-    long long blocks = (total + 255) / 256;
-    const long long cap = static_cast<long long>(num_sms()) * 16;
-    if (blocks > cap) blocks = cap;
+    const long long tokens = static_cast<long long>(batch) * q_len;
+    if (tokens == 0) return L32_OK;
+    if (head_dim != 64 && head_dim != 128) return L32_ERR_BAD_SHAPE;
+    if (tokens > 0x7fffffffll) return L32_ERR_BAD_SHAPE;
+    if (!is_aligned16(q) || !is_aligned16(k_new) || !is_aligned16(v_new) || !is_aligned16(cache_k) || !is_aligned16(cache_v))
+        return L32_ERR_BAD_ALIGN;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(blocks));
-    cfg.blockDim = dim3(256);
+    cfg.gridDim = dim3(static_cast<unsigned>(tokens));
+    cfg.blockDim = dim3(static_cast<unsigned>((head_dim / 16) * 16));
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -602,12 +636,12 @@ int rope_kv_append(void* q, const void* k_new, const void* v_new, const long lon
     if (dtype == L32_BF16)
         e = cudaLaunchKernelEx(&cfg, rope_kv_append_kernel<__nv_bfloat16>, static_cast<__nv_bfloat16*>(q),
                                static_cast<const __nv_bfloat16*>(k_new), static_cast<const __nv_bfloat16*>(v_new), position_ids,
-                               static_cast<__nv_bfloat16*>(cache_k), static_cast<__nv_bfloat16*>(cache_v), batch, q_len, heads,
+                               static_cast<__nv_bfloat16*>(cache_k), static_cast<__nv_bfloat16*>(cache_v), q_len, heads,
                                kv_heads, head_dim, max_len, past_len, log2_base);
     else
         e = cudaLaunchKernelEx(&cfg, rope_kv_append_kernel<__half>, static_cast<__half*>(q), static_cast<const __half*>(k_new),
                                static_cast<const __half*>(v_new), position_ids, static_cast<__half*>(cache_k),
-                               static_cast<__half*>(cache_v), batch, q_len, heads, kv_heads, head_dim, max_len, past_len, log2_base);
+                               static_cast<__half*>(cache_v), q_len, heads, kv_heads, head_dim, max_len, past_len, log2_base);
     if (e == cudaSuccess) count_launch();
     return static_cast<int>(e);
 }

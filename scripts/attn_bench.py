@@ -27,3 +27,12 @@ for B, Lk in ((64, 2048), (8, 8192), (1, 2048)):
     ms = timeit(lambda: ops.gqa_attention_forward(qd, ck, cv, Lk, Lk - 1, causal=True), iters=50)
     by = 2.0 * B * NKV * Lk * D * 2
     print(f"decode B={B} kv={Lk}: {ms * 1e3:.1f} us  {by / ms / 1e6:.0f} GB/s of K+V", flush=True)
+# RoPE + cache append (11B geometry): prefill 4 x 2048 tokens and a decode step of 64 sequences
+for B, T in ((4, 2048), (64, 1)):
+    NH, NKV, D = 32, 8, 128
+    qr, kn, vn = rnd(B, T, NH * D), rnd(B, T, NKV * D), rnd(B, T, NKV * D)
+    ck, cv = torch.zeros(B, NKV, T + 64, D, device=dev, dtype=dt), torch.zeros(B, NKV, T + 64, D, device=dev, dtype=dt)
+    pos = torch.arange(T, device=dev)[None].expand(B, -1).contiguous()
+    ms = timeit(lambda: ops.rope_kv_append(qr, kn, vn, pos, ck, cv, 0), iters=50)
+    by = (2 * B * T * NH * D + 4 * B * T * NKV * D) * 2
+    print(f"rope + cache append B={B} T={T}: {ms * 1e3:.1f} us  {by / ms / 1e6:.0f} GB/s", flush=True)

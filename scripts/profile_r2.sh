@@ -42,7 +42,7 @@ for t in ${TARGETS:-prefill train decode norm}; do
     train)   full train gemm_kernel 7 7 train ;;
     decode)  full decode_b64 ffn_decode 14 2 decode ;;
     norm)    full norm rmsnorm 8 4 norm ;;
-    attention) full attention gqa_attention 2 2 attention ;;
+    attention) full attention "gqa_attention|rope_kv" 2 5 attention ;;
     lmhead)  full lmhead "gemm_kernel|ce_" 3 3 lmhead ;;
   esac
 done

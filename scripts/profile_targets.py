@@ -55,6 +55,10 @@ elif what == "attention":
     ckd, cvd = rnd(64, NKV, 2112, D), rnd(64, NKV, 2112, D)
     for i in range(3):
         ops.gqa_attention_forward(qd, ckd, cvd, 2048, 2047, causal=True)
+    kn, vn = rnd(B, T, NKV * D), rnd(B, T, NKV * D)
+    pos = torch.arange(T, device=dev)[None].expand(B, -1).contiguous()
+    for i in range(3):
+        ops.rope_kv_append(q, kn, vn, pos, ck, cv, 0)
 elif what == "lmhead":
     T, H, V = 8192, 4096, 128256
     w = uni(V, H)
