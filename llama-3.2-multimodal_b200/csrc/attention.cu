@@ -258,23 +258,21 @@ __global__ void __maxnreg__(160) gqa_attention_kernel(const __grid_constant__ At
         // to be complete when P is stored and when the accumulator is rescaled.
         auto process = [&](int t, uint32_t (&cur)[kKvTile], uint32_t (&nxt)[kKvTile]) {
             const int j0 = (tile0 + t) * kKvTile;
-            // A tile every key of which is visible needs no per-element predicates (all but the diagonal / last tiles).
-            const bool full = (j0 + kKvTile <= p.kv_len) && (!p.causal || j0 + kKvTile - 1 <= qpos) && keep_row == nullptr;
+            // key padding: the tile's 64 keep bytes become two ballot words per warp (lane = key; every lane of the warp takes
+            // part: keep_row is CTA-uniform) -- two byte loads per thread and tile instead of a loop over the keys
+            uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
+            if (keep_row != nullptr) {
+                const int ka = j0 + static_cast<int>(lane_id()), kb = ka + 32;
+                keep_lo = __ballot_sync(0xffffffffu, ka < p.kv_len && keep_row[ka] != 0);
+                keep_hi = __ballot_sync(0xffffffffu, kb < p.kv_len && keep_row[kb] != 0);
+            }
+            // A tile every key of which is visible needs no per-element predicates (all but the diagonal / last / padded tiles).
+            const bool full = (j0 + kKvTile <= p.kv_len) && (!p.causal || j0 + kKvTile - 1 <= qpos) && (keep_lo & keep_hi) == 0xffffffffu;
             if (!full) {
-                // keys [0, lim) of the tile pass the length / causal tests; the padding bytes are folded into a bit mask by a
-                // rolled loop (rare path, keeps the unrolled code small)
+                // keys [0, lim) of the tile pass the length / causal tests
                 const int lim = min(p.kv_len, p.causal ? qpos + 1 : p.kv_len) - j0;
-                uint32_t vis_lo = lim >= 32 ? 0xffffffffu : (lim > 0 ? (1u << lim) - 1u : 0u);
-                uint32_t vis_hi = lim >= 64 ? 0xffffffffu : (lim > 32 ? (1u << (lim - 32)) - 1u : 0u);
-                if (keep_row != nullptr) {
-#pragma unroll 1
-                    for (int j = 0; j < kKvTile && j < lim; ++j) {
-                        if (keep_row[j0 + j] == 0) {
-                            if (j < 32) vis_lo &= ~(1u << j);
-                            else vis_hi &= ~(1u << (j - 32));
-                        }
-                    }
-                }
+                const uint32_t vis_lo = (lim >= 32 ? 0xffffffffu : (lim > 0 ? (1u << lim) - 1u : 0u)) & keep_lo;
+                const uint32_t vis_hi = (lim >= 64 ? 0xffffffffu : (lim > 32 ? (1u << (lim - 32)) - 1u : 0u)) & keep_hi;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     if (!(vis_lo & (1u << j))) cur[j] = 0xff800000u;      // -inf

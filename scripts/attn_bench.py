@@ -36,3 +36,10 @@ for B, T in ((4, 2048), (64, 1)):
     ms = timeit(lambda: ops.rope_kv_append(qr, kn, vn, pos, ck, cv, 0), iters=50)
     by = (2 * B * T * NH * D + 4 * B * T * NKV * D) * 2
     print(f"rope + cache append B={B} T={T}: {ms * 1e3:.1f} us  {by / ms / 1e6:.0f} GB/s", flush=True)
+# the same prefill with a key-padding vector (what a 4-D additive mask from the model becomes): no padded key, 100 padded keys
+B, T, NH, NKV, D = 4, 2048, 32, 8, 128
+q, ck, cv = rnd(B, T, NH * D), rnd(B, NKV, T, D), rnd(B, NKV, T, D)
+for pad in (0, 100):
+    keep = torch.ones(B, T, dtype=torch.uint8, device=dev); keep[:, :pad] = 0
+    ms = timeit(lambda: ops.gqa_attention_forward(q, ck, cv, T, 0, causal=True, key_keep=keep))
+    print(f"prefill B={B} T={T} with key padding ({pad} padded keys): {ms:.3f} ms", flush=True)
