@@ -132,6 +132,14 @@ L32_API int l32_swiglu_backward(const void* d_act, const void* x, const void* w_
 L32_API int l32_linear_forward(const void* a, const void* w, const void* bias, void* y, int64_t tokens, int in_features,
                        int out_features, int dtype, void* stream);
 
+/* Up to three projections of the SAME activations, y_i = a w_i^T (no bias), as one launch: the W_query / W_key / W_value
+ * calls of GroupQueryAttention.forward (Model/model.py:231-233; three nn.Linear calls in the reference).  tokens <= 128: the
+ * weight-streaming kernel walks the row blocks of all weights in one grid (one launch ramp and one tail instead of three);
+ * otherwise one grouped tcgen05 GEMM launch whose problems share the persistent tile loop.
+ *   w, y, out_features : arrays of `count` (1..3) entries; w[i] : [out_features[i], in_features], y[i] : [tokens, out_features[i]]. */
+L32_API int l32_linear_group_forward(const void* a, const void* const* w, void* const* y, const int* out_features, int count,
+                             int64_t tokens, int in_features, int dtype, void* stream);
+
 /* Whole feed-forward forward: y = (silu(x w_gate^T) * (x w_up^T)) w_down^T.
  * Replaces: swiglu_down_forward_cuda, Tools/swiglu/swiglu.cu:319-364 (python `swiglu_fused.forward_down`,
  *           swiglu_binding.cpp:24-31); module-level spec FusedFeedforward.forward, Model/model.py:216-217.

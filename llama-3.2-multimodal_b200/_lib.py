@@ -35,6 +35,7 @@ SIGNATURES = {
     "l32_swiglu_backward_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "l32_swiglu_backward": (c_int, [c_void_p] * 10 + [c_size_t, c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_linear_forward": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p]),
+    "l32_linear_group_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "l32_ffn_forward": (c_int, [c_void_p] * 11 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_block_tail_forward": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 6 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "l32_block_tail_forward_ex": (c_int, [c_void_p] * 3 + [c_float] + [c_void_p] * 11 + [c_float] + [c_void_p] * 2 +

@@ -209,6 +209,47 @@ int linear_forward_add(const void* a, const void* w, const void* bias, const voi
                        int in_features, int out_features, int dtype, void* stream);
 }
 
+int l32_linear_group_forward(const void* a, const void* const* w, void* const* y, const int* out_features, int count, int64_t tokens,
+                             int in_features, int dtype, void* stream) {
+    if (!dtype_ok(dtype)) return L32_ERR_BAD_DTYPE;
+    if (count < 1 || count > 3 || w == nullptr || y == nullptr || out_features == nullptr) return L32_ERR_BAD_SHAPE;
+    for (int i = 0; i < count; ++i) {
+        if (!shapes_ok(tokens, in_features, out_features[i])) return L32_ERR_BAD_SHAPE;
+        if (w[i] == nullptr || y[i] == nullptr) return L32_ERR_NULL;
+    }
+    if (tokens == 0) return L32_OK;
+    if (a == nullptr) return L32_ERR_NULL;
+    cudaStream_t s = as_stream(stream);
+    if (tokens <= decode_max_tokens()) {
+        const int rc = ffn_decode_linear_group(a, w, y, out_features, count, static_cast<int>(tokens), in_features, dtype, s);
+        if (rc != L32_ERR_BAD_SHAPE) return rc;
+    }
+    if (count == 1 || tokens <= 128) {          // (the grouped tile loop wants 2-CTA tiles of 256 rows)
+        for (int i = 0; i < count; ++i) {
+            const int rc = linear_forward_add(a, w[i], nullptr, nullptr, y[i], tokens, in_features, out_features[i], dtype, stream);
+            if (rc != L32_OK) return rc;
+        }
+        return L32_OK;
+    }
+    // tiled GEMMs: one grouped launch -- the problems' tiles share the persistent loop (no wave tail per projection)
+    GemmProblem g = blank(static_cast<int>(tokens), out_features[0], dtype);
+    g.k[0] = in_features;
+    g.a[0] = op(a, in_features, 0);
+    g.b[0] = op(w[0], in_features, 0);
+    g.epilogue = EPI_STORE;
+    g.d[0] = y[0];
+    g.ldd = out_features[0];
+    g.cta_group = 2;
+    g.group_count = count;
+    for (int i = 0; i < count; ++i) {
+        GroupMember& q = g.group[i];
+        q.a = a; q.lda = in_features; q.m = static_cast<int>(tokens);
+        q.b = w[i]; q.ldb = in_features; q.n = out_features[i];
+        q.d = y[i]; q.ldd = out_features[i];
+    }
+    return gemm_sm100(g, s);
+}
+
 int l32_linear_forward(const void* a, const void* w, const void* bias, void* y, int64_t tokens, int in_features,
                        int out_features, int dtype, void* stream) {
     return linear_forward_add(a, w, bias, nullptr, y, tokens, in_features, out_features, dtype, stream);

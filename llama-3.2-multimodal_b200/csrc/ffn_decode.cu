@@ -42,8 +42,16 @@ constexpr int kBarrierBytes = (2 * kMaxStages + 2 * kMaxXStages + 1) * 8 + 16;
 
 enum : int { DEC_LINEAR = 0, DEC_SWIGLU = 1 };
 
+constexpr int kMaxLinearGroup = 3;
 struct DecodeParams {
-    CUtensorMap map_w[2];   // weight matrices [rows, K]: [0] = gate (or the only matrix), [1] = up
+    CUtensorMap map_w[kMaxLinearGroup];   // weight matrices [rows, K]: [0] = gate (or the only matrix), [1] = up;
+                                          // grouped linear (ngroup > 1): one per problem
+    // Grouped linear (DEC_LINEAR, ngroup > 1): several y_i = x w_i^T with the SAME x -- e.g. the q / k / v projections of a
+    // decode step -- as one launch: row blocks [rb_start[i], rb_start[i + 1]) belong to problem i.  No bias / addend.
+    int ngroup;
+    int rb_start[kMaxLinearGroup + 1];
+    int rows_g[kMaxLinearGroup];
+    void* out_g[kMaxLinearGroup];
     CUtensorMap map_x;      // activations [tokens, K]
     void* out;              // [tokens, rows_out]
     const void* bias[2];    // optional per-output-row bias ([0] gate / linear, [1] up)
@@ -97,6 +105,14 @@ __global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_co
     const int split = static_cast<int>(cluster_ctarank());
     const int row_block = blockIdx.x / p.splits;
 
+    // grouped linear: which problem this row block belongs to, and its row block inside that problem
+    int prob = 0, rb_local = row_block;
+    if (kEpi == DEC_LINEAR && p.ngroup > 1) {
+        while (prob + 1 < p.ngroup && row_block >= p.rb_start[prob + 1]) ++prob;
+        rb_local = row_block - p.rb_start[prob];
+    }
+    const int rows_out = (kEpi == DEC_LINEAR && p.ngroup > 1) ? p.rows_g[prob] : p.rows_out;
+    const long long ldo = (kEpi == DEC_LINEAR && p.ngroup > 1) ? static_cast<long long>(p.rows_g[prob]) : p.ldo;
     // this CTA's slice of the reduction
     const int nkb = (p.k + kBlockK - 1) / kBlockK;
     const int kb_base = nkb / p.splits, kb_rem = nkb % p.splits;
@@ -105,7 +121,7 @@ __global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_co
     const int rot = (p.rotate && cnt > 0) ? static_cast<int>((static_cast<uint32_t>(row_block) * 40503u) % static_cast<uint32_t>(cnt)) : 0;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.map_w[0]);
+        tma_prefetch_desc(&p.map_w[prob]);
         if constexpr (kEpi == DEC_SWIGLU) tma_prefetch_desc(&p.map_w[1]);
         tma_prefetch_desc(&p.map_x);
         for (int i = 0; i < stages; ++i) {
@@ -135,7 +151,7 @@ __global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_co
         if (elect_one()) {   // elect.sync: single-lane branch the compiler can see (no ELECT / BRA.U.ANY loop per TMA / MMA)
             // ---------------------------------------------------------------- TMA producer: weights
             // (running stage / k-block counters: no integer divisions in the per-stage instruction stream)
-            const int row0 = row_block * (kEpi == DEC_SWIGLU ? 64 : kRowsA);
+            const int row0 = rb_local * (kEpi == DEC_SWIGLU ? 64 : kRowsA);
             int s = 0, kr = rot;
             uint32_t phase = 0;
             for (int kb = 0; kb < cnt; ++kb) {                  // weights do not depend on the previous kernel: no PDL wait here
@@ -147,7 +163,7 @@ __global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_co
                     tma_load_2d(sa, &p.map_w[0], &full_bar[s], kcol, row0, kEvictFirst);
                     tma_load_2d(sa + kABytes / 2, &p.map_w[1], &full_bar[s], kcol, row0, kEvictFirst);
                 } else {
-                    tma_load_2d(sa, &p.map_w[0], &full_bar[s], kcol, row0, kEvictFirst);
+                    tma_load_2d(sa, &p.map_w[prob], &full_bar[s], kcol, row0, kEvictFirst);
                 }
                 if (++kr == cnt) kr = 0;
                 if (++s == stages) { s = 0; phase ^= 1u; }
@@ -228,7 +244,7 @@ __global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_co
     const int row = static_cast<int>(quarter * 32 + lane);
     const uint32_t taddr = tmem_base + ((quarter * 32u) << 16);
     const int units = p.n_pad >> 3;            // even: n_pad is a multiple of 16
-    T* out = static_cast<T*>(p.out);
+    T* out = static_cast<T*>((kEpi == DEC_LINEAR && p.ngroup > 1) ? p.out_g[prob] : p.out);
 
     if (p.splits == 1) {
         // ---- fast path: the whole reduction ran in this CTA
@@ -280,8 +296,8 @@ __global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_co
                 }
             }
         } else {
-            const int col = row_block * kRowsA + row;
-            const bool col_ok = col < p.rows_out;
+            const int col = rb_local * kRowsA + row;
+            const bool col_ok = col < rows_out;
             float b = 0.f;
             if (col_ok && p.bias[0] != nullptr) b = static_cast<float>(static_cast<const T*>(p.bias[0])[col]);
             for (int u = pt; u < units; u += nparts) {
@@ -292,7 +308,7 @@ __global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_co
                 for (int j = 0; j < 8; ++j) {
                     const int n = u * 8 + j;
                     if (col_ok && n < p.tokens) {
-                        const size_t o_idx = static_cast<size_t>(n) * p.ldo + col;
+                        const size_t o_idx = static_cast<size_t>(n) * ldo + col;
                         float r = __uint_as_float(v[j]) + b;
                         if (p.addend != nullptr) r = static_cast<float>(static_cast<T>(r)) + static_cast<float>(static_cast<const T*>(p.addend)[o_idx]);
                         out[o_idx] = static_cast<T>(r);
@@ -358,12 +374,12 @@ __global__ void __launch_bounds__(kMaxThreads) ffn_decode_kernel(const __grid_co
             }
         }
     } else {
-        const int col = row_block * kRowsA + row;
-        const bool col_ok = col < p.rows_out;
+        const int col = rb_local * kRowsA + row;
+        const bool col_ok = col < rows_out;
         float b = 0.f;
         if (col_ok && p.bias[0] != nullptr) b = static_cast<float>(static_cast<const T*>(p.bias[0])[col]);
         auto store_out = [&](int nn, float r) {
-            const size_t o_idx = static_cast<size_t>(nn) * p.ldo + col;
+            const size_t o_idx = static_cast<size_t>(nn) * ldo + col;
             if (p.addend != nullptr) r = static_cast<float>(static_cast<T>(r)) + static_cast<float>(static_cast<const T*>(p.addend)[o_idx]);
             out[o_idx] = static_cast<T>(r);
         };
@@ -425,9 +441,17 @@ int launch_decode(const DecodeParams& p, int grid, int threads, size_t smem_byte
 }
 
 // Common host path.  rows_per_block = output rows one CTA produces (64 for SwiGLU: 64 gate + 64 up weight rows).
+struct LinearGroup {          // grouped linear: `count` problems y_i[tokens, rows[i]] = x w_i^T sharing x and K
+    int count;
+    const void* w[kMaxLinearGroup];
+    void* y[kMaxLinearGroup];
+    int rows[kMaxLinearGroup];
+};
+
 template <int kEpi>
 int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0, const void* bias1, const void* addend, void* out,
-                void* cache0, void* cache1, int tokens, int k, int rows_out, int dtype, cudaStream_t s) {
+                void* cache0, void* cache1, int tokens, int k, int rows_out, int dtype, cudaStream_t s,
+                const LinearGroup* group = nullptr) {
     if (tokens <= 0 || tokens > 128 || k <= 0 || rows_out <= 0) return L32_ERR_BAD_SHAPE;
     if ((k % 8) != 0 || (rows_out % 8) != 0) return L32_ERR_BAD_SHAPE;
     if (!is_aligned16(x) || !is_aligned16(w0) || (w1 != nullptr && !is_aligned16(w1))) return L32_ERR_BAD_ALIGN;
@@ -450,7 +474,21 @@ int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0
     p.tmem_cols = 32u;                     // TMEM allocations are powers of two >= 32 columns
     while (p.tmem_cols < static_cast<uint32_t>(p.n_pad)) p.tmem_cols *= 2u;
 
-    const int row_blocks = (rows_out + rows_per_block - 1) / rows_per_block;
+    int row_blocks = (rows_out + rows_per_block - 1) / rows_per_block;
+    if (group != nullptr && group->count > 1) {
+        if (kEpi != DEC_LINEAR || group->count > kMaxLinearGroup || bias0 != nullptr || addend != nullptr) return L32_ERR_BAD_SHAPE;
+        p.ngroup = group->count;
+        row_blocks = 0;
+        for (int i = 0; i < group->count; ++i) {
+            if (group->rows[i] <= 0 || (group->rows[i] % 8) != 0 || group->w[i] == nullptr || group->y[i] == nullptr) return L32_ERR_BAD_SHAPE;
+            if (!is_aligned16(group->w[i])) return L32_ERR_BAD_ALIGN;
+            p.rb_start[i] = row_blocks;
+            p.rows_g[i] = group->rows[i];
+            p.out_g[i] = group->y[i];
+            row_blocks += (group->rows[i] + kRowsA - 1) / kRowsA;
+        }
+        p.rb_start[group->count] = row_blocks;
+    }
     const int nkb = (k + kBlockK - 1) / kBlockK;
     const int sms = num_sms();
     // K splits (cluster size): enough CTAs to keep every SM streaming, each with at least 4 k-blocks.
@@ -499,9 +537,17 @@ int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0
     int rc = make_tensor_map_2d(&p.map_x, x, static_cast<uint64_t>(tokens), static_cast<uint64_t>(k), static_cast<uint64_t>(k),
                                 static_cast<uint32_t>(p.n_pad), kBlockK, dtype);
     if (rc != L32_OK) return rc;
-    rc = make_tensor_map_2d(&p.map_w[0], w0, static_cast<uint64_t>(rows_out), static_cast<uint64_t>(k), static_cast<uint64_t>(k),
-                            rows_per_block, kBlockK, dtype);
-    if (rc != L32_OK) return rc;
+    if (p.ngroup > 1) {
+        for (int i = 0; i < p.ngroup; ++i) {
+            rc = make_tensor_map_2d(&p.map_w[i], group->w[i], static_cast<uint64_t>(group->rows[i]), static_cast<uint64_t>(k),
+                                    static_cast<uint64_t>(k), rows_per_block, kBlockK, dtype);
+            if (rc != L32_OK) return rc;
+        }
+    } else {
+        rc = make_tensor_map_2d(&p.map_w[0], w0, static_cast<uint64_t>(rows_out), static_cast<uint64_t>(k), static_cast<uint64_t>(k),
+                                rows_per_block, kBlockK, dtype);
+        if (rc != L32_OK) return rc;
+    }
     if constexpr (kEpi == DEC_SWIGLU) {
         rc = make_tensor_map_2d(&p.map_w[1], w1, static_cast<uint64_t>(rows_out), static_cast<uint64_t>(k),
                                 static_cast<uint64_t>(k), rows_per_block, kBlockK, dtype);
@@ -520,6 +566,20 @@ int decode_gemm(const void* x, const void* w0, const void* w1, const void* bias0
 int ffn_decode_swiglu(const void* x, const void* w_gate, const void* w_up, const void* b_gate, const void* b_up, void* act,
                       void* gate_cache, void* up_cache, int tokens, int hidden, int inter, int dtype, cudaStream_t s) {
     return decode_gemm<DEC_SWIGLU>(x, w_gate, w_up, b_gate, b_up, nullptr, act, gate_cache, up_cache, tokens, hidden, inter, dtype, s);
+}
+
+int ffn_decode_linear_group(const void* a, const void* const* w, void* const* y, const int* out_features, int count, int tokens,
+                            int in_features, int dtype, cudaStream_t s) {
+    if (count < 1 || count > kMaxLinearGroup) return L32_ERR_BAD_SHAPE;
+    LinearGroup g;
+    g.count = count;
+    for (int i = 0; i < count; ++i) {
+        g.w[i] = w[i];
+        g.y[i] = y[i];
+        g.rows[i] = out_features[i];
+    }
+    return decode_gemm<DEC_LINEAR>(a, w[0], nullptr, nullptr, nullptr, nullptr, y[0], nullptr, nullptr, tokens, in_features,
+                                   out_features[0], dtype, s, count > 1 ? &g : nullptr);
 }
 
 int ffn_decode_linear(const void* a, const void* w, const void* bias, const void* addend, void* y, int tokens, int in_features,

@@ -138,6 +138,9 @@ int ffn_decode_swiglu(const void* x, const void* w_gate, const void* w_up, const
                       void* gate_cache, void* up_cache, int tokens, int hidden, int inter, int dtype, cudaStream_t s);
 int ffn_decode_linear(const void* a, const void* w, const void* bias, const void* addend, void* y, int tokens,
                       int in_features, int out_features, int dtype, cudaStream_t s);
+//      up to three y_i = a w_i^T with the same a (e.g. the q / k / v projections of a decode step) as ONE launch
+int ffn_decode_linear_group(const void* a, const void* const* w, void* const* y, const int* out_features, int count, int tokens,
+                            int in_features, int dtype, cudaStream_t s);
 
 // ---- lmhead.cu : cross-entropy reductions around the EPI_CE GEMM
 cudaError_t ce_reduce(const void* partials, const float* target, const long long* labels, long long ignore_index, int64_t rows,

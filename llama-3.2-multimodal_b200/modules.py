@@ -627,9 +627,15 @@ class GroupQueryAttention(nn.Module):
             position_ids = position_ids[None]
         if position_ids.shape[0] != b:
             position_ids = position_ids.expand(b, -1)
-        q = self._project(self.W_query, hidden_states)           # [b, t, heads * d]: the kernels read this layout as it is
-        k = self._project(self.W_key, hidden_states)
-        v = self._project(self.W_value, hidden_states)
+        projs = (self.W_query, self.W_key, self.W_value)
+        if (not torch.is_grad_enabled() or not _wants_grad(hidden_states, *[m.weight for m in projs])) and all(
+                not _is_lora(m) and m.bias is None and m.weight.dtype == hidden_states.dtype and _dims8(*m.weight.shape) for m in projs):
+            # inference: the three projections of the same activations in ONE launch (reference Model/model.py:231-233)
+            q, k, v = ops.linear_group_forward(hidden_states, [m.weight for m in projs])
+        else:
+            q = self._project(self.W_query, hidden_states)       # [b, t, heads * d]: the kernels read this layout as it is
+            k = self._project(self.W_key, hidden_states)
+            v = self._project(self.W_value, hidden_states)
         cache = kv_cache if kv_cache is not None else KVCache()
         layer = self.layer_idx if kv_cache is not None else 0
         past = cache.length(layer)

@@ -5,6 +5,7 @@ torch's current stream of the tensor's device.
 """
 from __future__ import annotations
 
+import ctypes
 import weakref
 
 import torch
@@ -215,6 +216,28 @@ def linear_forward(a, weight, bias=None):
         check(lib().l32_linear_forward(_ptr(a2), _ptr(w), _ptr(b), _ptr(y), tokens, in_f, out_f, _dtype_code(a2),
                                        _stream(a2)), "l32_linear_forward")
     return y.view(*a.shape[:-1], out_f)
+
+
+def linear_group_forward(a, weights):
+    """[a w^T for w in weights] (1..3 bias-free nn.Linear weights over the same activations) in one launch."""
+    _check_cuda(a, *weights)
+    if not 1 <= len(weights) <= 3:
+        raise L32Error("linear_group_forward takes one to three weights")
+    a2, tokens = _flat_tokens(a)
+    ws = [_weight(w, w.dtype) for w in weights]
+    in_f = a2.shape[1]
+    for w in ws:
+        if w.shape[1] != in_f or w.dtype != a2.dtype:
+            raise L32Error(f"linear group: a[..., {in_f}] {a2.dtype} vs weight{tuple(w.shape)} {w.dtype}")
+    ys = [torch.empty(tokens, w.shape[0], dtype=a2.dtype, device=a2.device) for w in ws]
+    n = len(ws)
+    w_arr = (ctypes.c_void_p * n)(*[_ptr(w) for w in ws])
+    y_arr = (ctypes.c_void_p * n)(*[_ptr(y) for y in ys])
+    o_arr = (ctypes.c_int * n)(*[w.shape[0] for w in ws])
+    with torch.cuda.device(a2.device):
+        check(lib().l32_linear_group_forward(_ptr(a2), w_arr, y_arr, o_arr, n, tokens, in_f, _dtype_code(a2), _stream(a2)),
+              "l32_linear_group_forward")
+    return [y.view(*a.shape[:-1], y.shape[1]) for y in ys]
 
 
 def ffn_forward(x, w_gate, w_up, w_down, b_gate=None, b_up=None, b_down=None, *, want_cache=False):

@@ -820,6 +820,26 @@ def test_attention_vs_reference_outputs(tag):
     close(cache.value_cache[0], g["cache_v"], FWD, "cache values")
 
 
+@pytest.mark.parametrize("tokens", [1, 5, 64, 128, 129, 300, 2048])
+@pytest.mark.parametrize("outs", [(4096, 1024, 1024), (512, 128, 128), (1024, 1024), (256,)])
+def test_linear_group_forward_vs_oracle(tokens, outs):
+    """l32_linear_group_forward (the W_query / W_key / W_value projections of GroupQueryAttention.forward, reference
+    Model/model.py:231-233, as one launch): small-M weight-streaming kernel over the row blocks of all weights (tokens <= 128)
+    and the grouped tcgen05 GEMM (above), against the three F.linear calls in fp32 and against the single-projection call."""
+    from llama32_b200 import ops
+    k = 4096 if outs[0] == 4096 else 512
+    gen = torch.Generator().manual_seed(tokens * 7 + len(outs))
+    rep = lambda v: v.to(torch.bfloat16).float()
+    a = rep(torch.randn(tokens, k, generator=gen))
+    ws = [rep((torch.rand(o, k, generator=gen) * 2 - 1) / k ** 0.5) for o in outs]
+    ys = ops.linear_group_forward(dev(a), [dev(w) for w in ws])
+    assert len(ys) == len(outs)
+    for y, w in zip(ys, ws):
+        close(y, a @ w.t(), FWD, f"grouped projection {tuple(w.shape)} at {tokens} tokens")
+        # (not bit-equal: the grouped grid may split K differently, i.e. sum the fp32 partials in another order)
+        close(y, ops.linear_forward(dev(a), dev(w)).float(), (4e-3, 2.0 ** -7), "grouped launch vs the single projection")
+
+
 @pytest.mark.parametrize("b,t,heads,kv,d,causal,pad", [(1, 128, 1, 1, 128, True, 0), (1, 128, 1, 1, 128, True, 5), (1, 128, 1, 1, 128, True, 37),
                                                        (1, 128, 1, 1, 128, True, 64), (1, 128, 1, 1, 128, True, 70),
                                                        (2, 300, 4, 2, 128, True, 37), (2, 300, 4, 2, 64, True, 37),
