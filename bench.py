@@ -223,18 +223,22 @@ def _time_cuda_graph(fn, iters, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        for _ in range(iters):
-            fn()
-    g.replay()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e-3   # seconds
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3   # seconds
+    except RuntimeError:                             # a capture this torch build refuses: time the eager launches instead
+        torch.cuda.synchronize()
+        return _time_cuda(fn, iters, warm=1)
 
 
 def _gpu_weights(hidden, inter, dev, seed, dt=torch.bfloat16):
