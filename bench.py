@@ -943,6 +943,10 @@ def run_ours(args):
         ev_cmp = [torch.cuda.Event() for _ in range(nbuf)]
         ev_out = [torch.cuda.Event() for _ in range(nbuf)]
 
+        y_keep = [None] * nbuf                             # the step's result stays referenced until its D2H copy has been
+                                                           # ordered before later compute (no record_stream: the caching
+                                                           # allocator then only ever reuses blocks on the compute stream)
+
         def e2e_steps(n):
             for i in range(n):
                 b = i % nbuf
@@ -952,6 +956,8 @@ def run_ours(args):
                     d_r[b].copy_(h_r[b], non_blocking=True)
                     ev_in[b].record(s_h2d)
                 s_cmp.wait_event(ev_in[b])
+                s_cmp.wait_event(ev_out[b])                # the D2H copy of the result held in this slot (nbuf steps ago) is
+                y_keep[b] = None                           # done: its memory may be reused by the compute below
                 with torch.no_grad():
                     if fused is not None:
                         y = fused.forward(d_x[b], d_r[b], tokens)
@@ -959,14 +965,13 @@ def run_ours(args):
                         normed = norm(d_x[b], residual=d_r[b])
                         y = tp(normed) if tp is not None else ffn(normed)
                 ev_cmp[b].record(s_cmp)
+                y_keep[b] = y
                 with torch.cuda.stream(s_d2h):
                     s_d2h.wait_event(ev_cmp[b])
-                    s_d2h.wait_event(ev_out[b])
                     h_y[b].copy_(y, non_blocking=True)
-                    y.record_stream(s_d2h)
                     ev_out[b].record(s_d2h)
 
-        e2e_steps(warm)
+        e2e_steps(max(warm, 8))
         barrier()
         e0.record()
         e2e_steps(args.steps)
@@ -990,6 +995,7 @@ def run_ours(args):
                               "PCIe and the host's memory system (all ranks share one host; the container's CPU set and the "
                               "pinned buffers sit on one NUMA node)",
                "api": api + "; pinned host buffers, copies on side streams double-buffered against compute"}
+        y_keep = None
         del h_x, h_r, h_y, d_x, d_r, d_y
 
     # ---- BASELINE.json configs[4] in every line: 90B, 4 x 2048 tokens in total, tensor-parallel over this run's GPUs
